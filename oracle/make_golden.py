@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the REAL,
+unmodified reference (``/root/reference/polyphonic`` + vendored ``mmdet``) on CPU
+through ``oracle/mmcv_shim.py``.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+The fixtures hold reference OUTPUTS only; inputs and weights are regenerated
+deterministically by ``oracle/synth.py`` on both sides.  ``load_state_dict(strict=True)``
+below also proves that the key/shape table in ``oracle/synth.py`` (and hence the
+drop-in modules' state-dict layout) equals the reference's.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import mmcv_shim as shim  # noqa: E402
+from oracle import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+DECODER_CASES = [
+    # name, B, H, W, seed
+    ('decoder_b2_h16_w24_s0', 2, 16, 24, 0),
+    ('decoder_b1_h10_w12_s1', 1, 10, 12, 1),   # HW=120: ragged tile tail
+]
+
+
+def build_reference_roi_head():
+    shim.install()
+    import polyphonic  # noqa: F401  (registers the reference modules)
+    from mmdet.models.builder import build_head
+    cfg = shim.load_config('/root/reference/configs/polyphonic_image/poly_r50_cityscapes_2x.py')
+    roi = cfg.model.roi_head
+    roi['train_cfg'] = None
+    roi['test_cfg'] = cfg.model.test_cfg.rcnn
+    head = build_head(roi)
+    head.eval()
+    return head
+
+
+def run_decoder_case(head, B, H, W, seed):
+    sd = synth.synth_decoder_state(num_stages=3, seed=seed)
+    missing = head.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    inp = synth.synth_decoder_inputs(B, H, W, seed=seed)
+    metas = [dict(img_shape=(8 * H, 8 * W, 3), ori_shape=(8 * H, 8 * W, 3), pad_shape=(8 * H, 8 * W, 3),
+                  scale_factor=1.0, flip=False, batch_input_shape=(8 * H, 8 * W)) for _ in range(B)]
+    out = {}
+    with torch.no_grad():
+        # kernel_update.py:299-300, 316-328 -- the stage loop of simple_test, verbatim calls
+        depth_preds = inp['depth_pred'].expand(-1, inp['depth_proposal'].shape[1], -1, -1)
+        object_feats, mask_preds, depth_proposal = inp['proposal_feats'], inp['mask_preds'], inp['depth_proposal']
+        for stage in range(head.num_stages):
+            r = head._mask_forward(stage, inp['x_feats'], object_feats, mask_preds, metas,
+                                   depth_preds, depth_proposal, inp['depth_feats'])
+            object_feats, mask_preds = r['object_feats'], r['mask_preds']
+            depth_proposal, depth_preds = r['depth_proposal'], r['depth_preds']
+            for k in ('cls_score', 'mask_preds', 'object_feats', 'depth_preds', 'depth_proposal'):
+                out[f's{stage}.{k}'] = r[k].numpy().astype(np.float32)
+        out['scaled_mask_preds'] = r['scaled_mask_preds'].numpy()
+        out['scaled_depth_preds'] = r['scaled_depth_preds'].numpy()
+        out['cls_score_sigmoid'] = r['cls_score'].sigmoid().numpy()
+        # simple_test_mask_preds (kernel_update.py:356-401) must agree with the loop above
+        of, cs, mp, smp = head.simple_test_mask_preds(
+            inp['x_feats'], inp['proposal_feats'], inp['mask_preds'], None, metas,
+            depth_preds=inp['depth_pred'], depth_feats=inp['depth_feats'],
+            depth_proposal=inp['depth_proposal'])
+        assert torch.equal(smp, r['scaled_mask_preds']) and torch.equal(cs, r['cls_score'].sigmoid())
+    return out
+
+
+def run_updator_case(head, seed=0, rows=37):
+    upd = head.mask_head[0].kernel_update_conv
+    sd = {k[len('mask_head.0.kernel_update_conv.'):]: v
+          for k, v in synth.synth_decoder_state(1, seed).items()
+          if k.startswith('mask_head.0.kernel_update_conv.')}
+    upd.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(1234 + seed)
+    update = torch.randn(rows, synth.C, generator=g) * 20.0
+    inputf = torch.randn(rows, 1, synth.C, generator=g)
+    with torch.no_grad():
+        y = upd(update, inputf)
+    return dict(update_feature=update.numpy(), input_feature=inputf.numpy(), out=y.numpy())
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    head = build_reference_roi_head()
+    for name, B, H, W, seed in DECODER_CASES:
+        out = run_decoder_case(head, B, H, W, seed)
+        path = os.path.join(GOLD, name + '.npz')
+        np.savez_compressed(path, B=B, H=H, W=W, seed=seed, **out)
+        print(name, {k: v.shape for k, v in out.items() if k.startswith('s2') or 'scaled' in k},
+              f'{os.path.getsize(path) / 1e6:.2f} MB')
+    u = run_updator_case(head)
+    np.savez_compressed(os.path.join(GOLD, 'updator_r37_s0.npz'), **u)
+    print('updator', u['out'].shape)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def rel_err(a, b):
+    """Norm-wise relative error and max-abs/max-abs."""
+    import torch
+    a, b = torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten()
+    l2 = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    mx = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+    return l2, mx
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+    return GOLDEN

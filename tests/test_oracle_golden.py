@@ -1,0 +1,52 @@
+"""Pins oracle/decoder_ref.py (the CPU restatement) against outputs of the
+reference's own code (tests/golden/*.npz, made by oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_ref as ref
+from oracle import synth
+from conftest import rel_err, GOLDEN
+
+CASES = ['decoder_b2_h16_w24_s0', 'decoder_b1_h10_w12_s1']
+TOL = 2e-5   # fp32 re-association between the reference's op order and the restatement
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_decoder_restatement_matches_reference(name):
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    B, H, W, seed = int(g['B']), int(g['H']), int(g['W']), int(g['seed'])
+    sd = synth.synth_decoder_state(3, seed)
+    inp = synth.synth_decoder_inputs(B, H, W, seed)
+    with torch.no_grad():
+        out = ref.decoder_forward(sd, inp['x_feats'], inp['proposal_feats'], inp['mask_preds'],
+                                  inp['depth_feats'], inp['depth_proposal'], return_all_stages=True)
+    for s, st in enumerate(out['stages']):
+        for k, v in st.items():
+            l2, mx = rel_err(v, g[f's{s}.{k}'])
+            assert l2 < TOL and mx < TOL, (name, s, k, l2, mx)
+        flips = (st['mask_preds'] > 0) != (torch.from_numpy(g[f's{s}.mask_preds']) > 0)
+        assert flips.float().mean().item() < 1e-4
+    for k, gk in (('scaled_mask_preds', 'scaled_mask_preds'), ('scaled_depth_preds', 'scaled_depth_preds'),
+                  ('cls_score', 'cls_score_sigmoid')):
+        l2, mx = rel_err(out[k], g[gk])
+        assert l2 < TOL and mx < TOL, (name, k, l2, mx)
+
+
+def test_updator_restatement_matches_reference():
+    g = np.load(os.path.join(GOLDEN, 'updator_r37_s0.npz'))
+    sd = {k[len('mask_head.0.kernel_update_conv.'):]: v
+          for k, v in synth.synth_decoder_state(1, 0).items()
+          if k.startswith('mask_head.0.kernel_update_conv.')}
+    with torch.no_grad():
+        y = ref.kernel_updator(sd, torch.from_numpy(g['update_feature']), torch.from_numpy(g['input_feature']))
+    l2, mx = rel_err(y, g['out'])
+    assert l2 < TOL and mx < TOL, (l2, mx)
+
+
+def test_state_table_matches_reference_layout():
+    """4.02 M parameters per stage."""
+    n = sum(int(np.prod(s)) for s in synth.stage_state_shapes().values())
+    assert abs(n / 1e6 - 4.02) < 0.01, n
