@@ -1,0 +1,167 @@
+/* pf_decoder.h -- C ABI of the B200-native PolyphonicFormer decoder (libpf_decoder.so).
+ *
+ * The reference (HarborYuan/PolyphonicFormer) is pure Python on top of mmcv/mmdet and has no FFI of its own; the
+ * hot path is the body of these Python methods (paths relative to the reference tree):
+ *
+ *   KernelUpdateIterHead.simple_test / _mask_forward   polyphonic/kernel_update.py:282-354, :125-157
+ *   KernelUpdateHead.forward                           polyphonic/kernel_update_head.py:212-353
+ *   KernelUpdator.forward                              polyphonic/funcs/kernel_updator.py:55-93
+ *   KernelHead initial pooling                         polyphonic/kernel_head.py:313-320
+ *
+ * Each entry point below replaces a contiguous slice of those bodies (cited per function).  The binding a reference
+ * maintainer would add is a ctypes stub inside those methods -- see INTEGRATION.md; the in-tree host mirror is
+ * polyphonicformer_b200/_cabi.py + decoder.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch host code) owns all
+ *     buffers; the library never allocates, frees or synchronises;
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes to that stream only, so calls can be captured
+ *     into a CUDA graph;
+ *   - returns PF_OK (0) or a negative pf_status; pf_last_error_string() describes the last failure on the calling
+ *     thread.  No exceptions cross the boundary.  There is no CPU fallback: on a machine without an sm_100 device
+ *     every compute entry point returns PF_ERR_ARCH;
+ *   - fixed by the model family (configs/_base_/models/polyphonic_former.py): C = 256 channels, 8 heads of 32,
+ *     N <= 128 kernels (111 at inference), num_classes <= 32.
+ *
+ * Device data layouts
+ *   feats   bf16  [2][B][256][HWp]   branch 0 = x_feats, branch 1 = depth_feats; HWp = row pitch in elements,
+ *                                    HWp % 8 == 0, HWp >= HW; columns >= HW are never read as data
+ *   bits    u32   [B][WORDS][128]    WORDS = ceil(HW/32); bit j of word w of row n = (mask logit[n][32w+j] > 0)
+ *                                    == sigmoid(logit) > 0.5 (kernel_update_head.py:236-238); rows >= N are zero
+ *   partial f32   [G][S][N][256]     per-split pooled sums, G = n_branch*B units (unit = branch*B + b)
+ *   cntp    f32   [G][S][N]          per-split mask pixel counts
+ *   kern    f32   [G][N][256]        dynamic 1x1-conv kernels with feat_transform already folded in
+ *   kbias   f32   [G][N]             per-kernel logit bias produced by that fold
+ *   logits  f32   [G][N][HW]         unit-major: branch 0 = new mask logits, branch 1 = new depth logits
+ */
+#ifndef PF_DECODER_H
+#define PF_DECODER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PF_C 256
+#define PF_MAX_N 128
+#define PF_MAX_CLASSES 32
+#define PF_HEADS 8
+
+typedef enum pf_status {
+    PF_OK = 0,
+    PF_ERR_ARG = -1,       /* bad shape / null pointer */
+    PF_ERR_ALIGN = -2,     /* pointer or pitch alignment */
+    PF_ERR_CUDA = -3,      /* CUDA runtime / driver error (message has the code) */
+    PF_ERR_ARCH = -4,      /* no sm_100 device */
+    PF_ERR_WORKSPACE = -5  /* workspace too small */
+} pf_status;
+
+int pf_version(void);
+const char* pf_last_error_string(void);
+
+/* ---- per-branch parameters of one KernelUpdateHead, after host-side packing (decoder.py: pack_stage_weights).
+ * All matrices are row-major [out][in] like nn.Linear.weight.  Folded ones are marked (*):
+ * feat_transform W_t,b_t (kernel_update_head.py:224-226) never touches the feature map; instead
+ *   dyn_w  = dynamic_layer.weight @ W_t,  dyn_cb = dynamic_layer.weight @ b_t   (pooled' = pooled W_t^T + count b_t)
+ *   kern_w = W_t^T @ fc_{mask,depth}.weight, kern_b = W_t^T @ fc.bias, kb_w = fc.weight^T @ b_t, kb_b = fc.bias . b_t
+ */
+typedef struct pf_branch_weights {
+    const float *dyn_w, *dyn_b, *dyn_cb;            /* (*) [512][256], [512], [512]; kernel_updator.py:58 */
+    const float *inp_w, *inp_b;                     /* input_layer [512][256]; :64 */
+    const float *gate_w, *gate_b;                   /* [input_gate; update_gate] [512][256]; :73-74 */
+    const float *ln_input_norm_in, *ln_norm_in;     /* each [2][256] = gamma, beta; :75-77 */
+    const float *ln_norm_out, *ln_input_norm_out;   /* :78-79 */
+    const float *fc_w, *fc_b, *ln_fc_norm;          /* fc_layer [256][256]; :89-91 */
+    const float *qkv_w, *qkv_b;                     /* attn.in_proj [768][256]; kernel_update_head.py:259-260 */
+    const float *out_w, *out_b, *ln_attn;           /* attn.out_proj, attention_norm */
+    const float *ffn1_w, *ffn1_b;                   /* ffn.layers.0.0 [FFN][256]; :271-272 */
+    const float *ffn2_w, *ffn2_b, *ln_ffn;          /* ffn.layers.1 [256][FFN], ffn_norm */
+    const float *head_w;                            /* mask branch: [cls_fcs.0; mask_fcs.0] [512][256]; depth: depth_regs.0 [256][256]; :278-283 */
+    const float *ln_head_a, *ln_head_b;             /* mask: cls_fcs.1, mask_fcs.1; depth: depth_regs.1, unused */
+    const float *cls_w, *cls_b;                     /* mask branch only: fc_cls padded to [32][256], [32]; :285 */
+    const float *kern_w, *kern_b;                   /* (*) [256][256], [256]; :287-288 with the fold */
+    const float *kb_w;                              /* (*) [256] */
+    float kb_b;                                     /* (*) scalar */
+    int head_relu;                                  /* 1 for the mask branch (mask_fcs has ReLU), 0 for depth_regs */
+} pf_branch_weights;
+
+typedef struct pf_stage_weights {
+    pf_branch_weights br[2]; /* 0 = mask branch, 1 = depth branch */
+    int ffn_channels;        /* 2048 */
+    int num_classes;         /* 19 */
+} pf_stage_weights;
+
+/* fp32 NCHW feature maps -> the bf16 [2][B][256][HWp] layout.  Replaces nothing in the reference (storage cast). */
+int pf_cast_feats(const float* x_feats, const float* depth_feats, uint16_t* feats, int B, int HW, int HWp,
+                  void* stream);
+
+/* kernel_update_head.py:236-238 (sigmoid > hard_mask_thr=0.5, .float()) as a packed bit mask. */
+int pf_binarise(const float* mask_logits, uint32_t* bits, int B, int N, int HW, void* stream);
+
+/* number of HW splits pf_mask_pool uses for this shape (size of the S dimension of partial / cntp) */
+int pf_pool_splits(int B, int n_branch, int HW);
+
+/* kernel_update_head.py:241-242 (and kernel_head.py:313-320): pooled[g][n][c] = sum_hw bit[b][n][hw] * feats[g][c][hw]
+ * on tcgen05 tensor cores, split over S slabs of HW per unit; sum over S is taken by pf_kernel_update / pf_pool_reduce. */
+int pf_mask_pool(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int B, int N, int HW,
+                 int HWp, int n_branch, int S, void* stream);
+
+/* sum the S partials: pooled [G][N][256], count [B][N] (used by KernelHead's init pooling and by tests) */
+int pf_pool_reduce(const float* partial, const float* cntp, float* pooled, float* count, int B, int N, int n_branch,
+                   int S, void* stream);
+
+/* bytes of scratch pf_kernel_update needs */
+size_t pf_update_workspace_bytes(int B, int N, int ffn_channels);
+
+/* kernel_update_head.py:245-288 + kernel_updator.py:55-93: both branches of the small-N block.
+ *   obj_in / dep_in    [B][N][256]   proposal_feat, depth_proposal (before the "+ proposal_feat" of :250)
+ *   obj_out / dep_out  [B][N][256]   obj_feat, depth_feat_new (post FFN+LN; next stage's inputs)
+ *   cls_out            [B][N][num_classes]  (sigmoid applied iff cls_sigmoid != 0, kernel_update.py:333-334)
+ *   kern / kbias       [2][B][N][256], [2][B][N]   folded dynamic kernels for pf_mask_einsum */
+int pf_kernel_update(const pf_stage_weights* w_host, const float* partial, const float* cntp, int S,
+                     const float* obj_in, const float* dep_in, float* obj_out, float* dep_out, float* cls_out,
+                     float* kern, float* kbias, void* workspace, size_t workspace_bytes, int B, int N,
+                     int cls_sigmoid, void* stream);
+
+/* kernel_update_head.py:308-334: logits[g][n][hw] = sum_c kern[g][n][c] * feats[g][c][hw] + kbias[g][n] on tcgen05.
+ * n_units = B (mask branch only) or 2B.  logits and/or bits_out may be NULL (bits are taken from units < B). */
+int pf_mask_einsum(const uint16_t* feats, const float* kern, const float* kbias, float* logits, uint32_t* bits_out,
+                   int B, int N, int HW, int HWp, int n_units, void* stream);
+
+/* kernel_update.py:133-143: F.interpolate(scale_factor=2, bilinear, align_corners=False) on `maps` [H][W] planes */
+int pf_upsample2x(const float* in, float* out, int maps, int H, int W, void* stream);
+
+/* bytes of scratch pf_decoder_forward needs */
+size_t pf_decoder_workspace_bytes(int B, int N, int HW, int ffn_channels);
+
+/* kernel_update.py:316-336: the whole stage loop of KernelUpdateIterHead.simple_test (no post-processing).
+ *   stages_host   array of n_stages pf_stage_weights (host memory, device pointers inside)
+ *   mask_logits   [B][N][H*W] initial mask logits (only their sign is used)
+ *   obj / dep     [B][N][256] in: proposal_feats, depth_proposal; out: final object_feats, depth_proposal
+ *   cls_out       [B][N][num_classes] sigmoid scores of the last stage
+ *   logits_out    [2][B][N][H*W] last-stage mask and depth logits
+ *   scaled_out    [2][B][N][2H*2W] their x2 upsampling, or NULL when mask_upsample_stride == 1
+ *   flags         PF_FWD_* below */
+#define PF_FWD_ALL_STAGE_OUTPUTS 1 /* also run the (unobservable) depth einsum + fp32 logits of stages 0..S-2 */
+int pf_decoder_forward(const pf_stage_weights* stages_host, int n_stages, const uint16_t* feats,
+                       const float* mask_logits, float* obj, float* dep, float* cls_out, float* logits_out,
+                       float* scaled_out, void* workspace, size_t workspace_bytes, int B, int N, int H, int W, int HWp,
+                       int flags, void* stream);
+
+/* number of kernels the last call on this thread launched (for bench.py's gpu_launches) */
+int pf_last_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_DECODER_H */

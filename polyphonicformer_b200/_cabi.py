@@ -1,0 +1,97 @@
+"""ctypes binding of include/pf_decoder.h (libpf_decoder.so).
+
+This is the only place the package touches the native library.  There is NO fallback: if the library is missing or
+a call fails, a ``PFError`` is raised -- nothing in this package computes the decoder with PyTorch ops.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'lib', 'libpf_decoder.so')
+
+PF_C = 256
+PF_MAX_N = 128
+PF_MAX_CLASSES = 32
+PF_HEADS = 8
+PF_FWD_ALL_STAGE_OUTPUTS = 1
+
+STATUS = {0: 'PF_OK', -1: 'PF_ERR_ARG', -2: 'PF_ERR_ALIGN', -3: 'PF_ERR_CUDA', -4: 'PF_ERR_ARCH',
+          -5: 'PF_ERR_WORKSPACE'}
+
+
+class PFError(RuntimeError):
+    def __init__(self, code, fn, msg):
+        super().__init__('%s failed with %s (%d): %s' % (fn, STATUS.get(code, '?'), code, msg))
+        self.code = code
+
+
+_fp = POINTER(c_float)
+
+
+class BranchWeights(Structure):
+    """struct pf_branch_weights -- field order must match include/pf_decoder.h."""
+    _PTRS = ['dyn_w', 'dyn_b', 'dyn_cb', 'inp_w', 'inp_b', 'gate_w', 'gate_b', 'ln_input_norm_in', 'ln_norm_in',
+             'ln_norm_out', 'ln_input_norm_out', 'fc_w', 'fc_b', 'ln_fc_norm', 'qkv_w', 'qkv_b', 'out_w', 'out_b',
+             'ln_attn', 'ffn1_w', 'ffn1_b', 'ffn2_w', 'ffn2_b', 'ln_ffn', 'head_w', 'ln_head_a', 'ln_head_b',
+             'cls_w', 'cls_b', 'kern_w', 'kern_b', 'kb_w']
+    _fields_ = [(n, c_void_p) for n in _PTRS] + [('kb_b', c_float), ('head_relu', c_int)]
+
+
+class StageWeights(Structure):
+    """struct pf_stage_weights."""
+    _fields_ = [('br', BranchWeights * 2), ('ffn_channels', c_int), ('num_classes', c_int)]
+
+
+_SIGS = {
+    'pf_version': (c_int, []),
+    'pf_last_error_string': (c_char_p, []),
+    'pf_last_launch_count': (c_int, []),
+    'pf_cast_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pf_binarise': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pf_pool_splits': (c_int, [c_int, c_int, c_int]),
+    'pf_mask_pool': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p]),
+    'pf_pool_reduce': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'pf_update_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'pf_kernel_update': (c_int, [POINTER(StageWeights), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int,
+                                 c_void_p]),
+    'pf_mask_einsum': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_void_p]),
+    'pf_upsample2x': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pf_decoder_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'pf_decoder_forward': (c_int, [POINTER(StageWeights), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+def load():
+    """Load libpf_decoder.so (once) and declare the prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PFError(-3, 'load', 'native library %s not found -- run `python -m polyphonicformer_b200.build` '
+                                   '(there is no CPU/PyTorch fallback for the decoder)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, fn):
+    if code != 0:
+        raise PFError(code, fn, load().pf_last_error_string().decode('utf-8', 'replace'))
+
+
+def call(fn, *args):
+    """Call an int-returning entry point and raise PFError on a non-zero status."""
+    check(getattr(load(), fn)(*args), fn)

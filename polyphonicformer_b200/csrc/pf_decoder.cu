@@ -1,0 +1,79 @@
+// The stage loop of KernelUpdateIterHead.simple_test (polyphonic/kernel_update.py:316-336 of the reference) as one
+// C call: binarise -> S x (pool -> update -> einsum) -> x2 upsample.  Launch-only (no allocation, no sync), so the
+// host may capture it into a CUDA graph.
+#include "pf_internal.h"
+
+namespace pf {
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DecoderScratch {
+    uint32_t* bits;
+    float *partial, *cntp, *kern, *kbias;
+    void* update_ws;
+    size_t update_ws_bytes, total;
+};
+
+static DecoderScratch carve(void* base, int B, int N, int HW, int ffn) {
+    DecoderScratch s;
+    const int words = (HW + 31) / 32;
+    const int S = pf_pool_splits(B, 2, HW);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off = align_up(off + bytes, 256);
+        return p;
+    };
+    s.bits = static_cast<uint32_t*>(take((size_t)B * words * 128 * 4));
+    s.partial = static_cast<float*>(take((size_t)2 * B * S * N * PF_C * 4));
+    s.cntp = static_cast<float*>(take((size_t)2 * B * S * N * 4));
+    s.kern = static_cast<float*>(take((size_t)2 * B * N * PF_C * 4));
+    s.kbias = static_cast<float*>(take((size_t)2 * B * N * 4));
+    s.update_ws_bytes = pf_update_workspace_bytes(B, N, ffn);
+    s.update_ws = take(s.update_ws_bytes);
+    s.total = off;
+    return s;
+}
+}  // namespace pf
+
+extern "C" size_t pf_decoder_workspace_bytes(int B, int N, int HW, int ffn_channels) {
+    if (B <= 0 || N <= 0 || HW <= 0 || ffn_channels <= 0) return 0;
+    return pf::carve(nullptr, B, N, HW, ffn_channels).total;
+}
+
+extern "C" int pf_decoder_forward(const pf_stage_weights* stages, int n_stages, const uint16_t* feats,
+                                  const float* mask_logits, float* obj, float* dep, float* cls_out, float* logits_out,
+                                  float* scaled_out, void* workspace, size_t workspace_bytes, int B, int N, int H, int W,
+                                  int HWp, int flags, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    reset_launch_count();
+    PF_REQUIRE(stages && n_stages > 0 && feats && mask_logits && obj && dep && cls_out && logits_out && workspace,
+               PF_ERR_ARG, "pf_decoder_forward: null pointer");
+    PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && H > 0 && W > 0, PF_ERR_ARG, "pf_decoder_forward: bad shape");
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PF_ERR_ALIGN, "pf_decoder_forward: workspace not 256-byte aligned");
+    const int HW = H * W;
+    const int ffn = stages[0].ffn_channels;
+    const DecoderScratch s = carve(workspace, B, N, HW, ffn);
+    PF_REQUIRE(workspace_bytes >= s.total, PF_ERR_WORKSPACE, "pf_decoder_forward: workspace %zu < %zu", workspace_bytes, s.total);
+    const int S = pf_pool_splits(B, 2, HW);
+
+    if (int e = pf_binarise(mask_logits, s.bits, B, N, HW, stream)) return e;
+    for (int st = 0; st < n_stages; ++st) {
+        const bool last = st == n_stages - 1;
+        if (int e = pf_mask_pool(feats, s.bits, s.partial, s.cntp, B, N, HW, HWp, 2, S, stream)) return e;
+        if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, s.kern, s.kbias,
+                                     s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
+            return e;
+        int e;
+        if (last)
+            e = pf_mask_einsum(feats, s.kern, s.kbias, logits_out, nullptr, B, N, HW, HWp, 2 * B, stream);
+        else if (flags & PF_FWD_ALL_STAGE_OUTPUTS)
+            e = pf_mask_einsum(feats, s.kern, s.kbias, logits_out, s.bits, B, N, HW, HWp, 2 * B, stream);
+        else  // only the sign of the next mask is observable (kernel_update_head.py:236-238)
+            e = pf_mask_einsum(feats, s.kern, s.kbias, nullptr, s.bits, B, N, HW, HWp, B, stream);
+        if (e) return e;
+    }
+    if (scaled_out)
+        if (int e = pf_upsample2x(logits_out, scaled_out, 2 * B * N, H, W, stream)) return e;
+    return PF_OK;
+}

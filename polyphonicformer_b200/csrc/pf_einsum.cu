@@ -1,0 +1,232 @@
+// K3 -- kernel x feature-map einsum (polyphonic/kernel_update_head.py:308-334 of the reference):
+//     logits[g][n][hw] = sum_c kern[g][n][c] * feats[g][c][hw] + kbias[g][n]
+// as a batched [128 x 256] x [256 x HW] GEMM on the tcgen05 tensor cores.
+//
+//   A  = kern[g] (fp32 in HBM) split on chip into bf16 hi + bf16 lo (two MMAs per K step, fp32 accumulate), K-major,
+//        resident in shared memory for the whole CTA (2 x 64 KB, 128-byte swizzle);
+//   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 3-stage ring;
+//   D  = [128 lanes][64 columns] fp32 in TMEM, 4 accumulator buffers so the epilogue overlaps the next tiles;
+//   epilogue: tcgen05.ld -> + bias -> fp32 logits (128-bit stores) and/or the packed sign bits consumed by the next
+//             stage's pooling (thread = kernel row n, 32 consecutive pixels = one u32 word).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// The kernel is HBM-bound (59 FLOP/B against a ridge of ~213): see DESIGN.md for the roofline.
+#include "pf_internal.h"
+#include "pf_sm100.cuh"
+
+namespace pf {
+
+constexpr int E_C = PF_C;            // 256 = K of the GEMM
+constexpr int E_BHW = 64;            // pixels per tile (= N of the MMA, one 128-byte swizzle atom of bf16)
+constexpr int E_STAGES = 3;
+constexpr int E_ACC = 4;             // TMEM accumulator buffers
+constexpr int E_TMEM_COLS = E_ACC * E_BHW;  // 256
+constexpr int E_A_BYTES = 128 * E_C * 2;    // 65536 per (hi | lo)
+constexpr int E_B_BYTES = E_C * E_BHW * 2;  // 32768 per stage
+constexpr int E_THREADS = 192;
+constexpr int E_SMEM = 2 * E_A_BYTES + E_STAGES * E_B_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+
+struct EinsumParams {
+    const float* kern;   // [G][N][256]
+    const float* kbias;  // [G][N]
+    float* logits;       // [G][N][HW] or null
+    uint32_t* bits;      // [B][WORDS][128] or null
+    int N, HW, words, B;
+    int tiles_per_unit, ctas_per_unit;
+};
+
+__global__ void __launch_bounds__(E_THREADS, 1)
+einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA_hi = smem;
+    uint8_t* sA_lo = smem + E_A_BYTES;
+    uint8_t* sB = smem + 2 * E_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + E_STAGES * E_B_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + E_STAGES;
+    uint64_t* tfull = bars + 2 * E_STAGES;
+    uint64_t* tempty = bars + 2 * E_STAGES + E_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * E_STAGES + 2 * E_ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x / p.ctas_per_unit;
+    const int j = blockIdx.x % p.ctas_per_unit;
+    const int tile_begin = (int)((long long)j * p.tiles_per_unit / p.ctas_per_unit);
+    const int tile_end = (int)((long long)(j + 1) * p.tiles_per_unit / p.ctas_per_unit);
+    const int ntiles = tile_end - tile_begin;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_feats);
+        for (int i = 0; i < E_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < E_ACC; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<E_TMEM_COLS>(tmem_slot);
+
+    // ---- A operand: fp32 kernels -> bf16 hi/lo, K-major 128B-swizzled, 4 K-blocks of [128 rows][64 k]
+    {
+        const float* kg = p.kern + (size_t)unit * p.N * E_C;
+        for (int item = threadIdx.x; item < 128 * 32; item += E_THREADS) {
+            const int r = item >> 5, c8 = item & 31;  // row, 8-element chunk along K
+            float v[8];
+            if (r < p.N) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(kg + (size_t)r * E_C + c8 * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(kg + (size_t)r * E_C + c8 * 8 + 4));
+                v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float h0 = bf16_round(v[2 * i]), h1 = bf16_round(v[2 * i + 1]);
+                hi[i] = pack_bf16x2(h0, h1);
+                lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+            }
+            const uint32_t off = (uint32_t)(c8 >> 3) * (128 * 128) + sw128_offset(r, c8 & 7);
+            *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % E_STAGES;
+                const uint32_t ph = (i / E_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], E_B_BYTES);
+                tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, unit * E_C,
+                            kEvictFirst);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, E_BHW, /*a_mn=*/0, /*b_mn=*/1);
+            const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % E_STAGES, a = i % E_ACC;
+                mbar_wait(&tempty[a], ((i / E_ACC) & 1) ^ 1);
+                mbar_wait(&full[s], (i / E_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + a * E_BHW;
+                const uint32_t b_base = smem_u32(sB + s * E_B_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < E_C / 16; ++kb) {
+                    // A: K-block kb/4 (16 KB each), 32 bytes per K=16 step inside the 128-byte row
+                    const uint32_t a_off = (kb >> 2) * (128 * 128) + (kb & 3) * 32;
+                    // B (MN-major): 16 K-rows of 128 bytes per step
+                    const uint64_t db = make_smem_desc_sw128(b_base + kb * 2048, 32768, 1024);
+                    umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_hi + a_off, 16, 1024), db, idesc, kb > 0);
+                    umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_lo + a_off, 16, 1024), db, idesc, 1);
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[a]);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
+        const int q = warp & 3;
+        const int n = q * 32 + lane;
+        const bool row_ok = n < p.N;
+        const float bias = row_ok ? __ldg(p.kbias + (size_t)unit * p.N + n) : 0.f;
+        float* orow = p.logits ? p.logits + ((size_t)unit * p.N + (row_ok ? n : 0)) * p.HW : nullptr;
+        const bool vec_ok = (p.HW & 3) == 0;
+        uint32_t* brow = (p.bits && unit < p.B) ? p.bits + (size_t)unit * p.words * 128 + n : nullptr;
+        for (int i = 0; i < ntiles; ++i) {
+            const int a = i % E_ACC;
+            mbar_wait(&tfull[a], (i / E_ACC) & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * E_BHW;
+            tmem_ld32(taddr, v0);
+            tmem_ld32(taddr + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+            const int hw0 = (tile_begin + i) * E_BHW;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t(&v)[32] = h ? v1 : v0;
+                const int hwb = hw0 + h * 32;
+                if (hwb >= p.HW) break;
+                uint32_t word = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float f = __uint_as_float(v[c]) + bias;
+                    v[c] = __float_as_uint(f);
+                    word |= (f > 0.f ? 1u : 0u) << c;
+                }
+                const int valid = p.HW - hwb;  // > 0
+                if (valid < 32) word &= (1u << valid) - 1u;
+                if (brow) brow[(size_t)(hwb >> 5) * 128] = word;
+                if (orow && row_ok) {
+                    float* dst = orow + hwb;
+                    if (vec_ok && valid >= 32) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            __stcs(reinterpret_cast<float4*>(dst + c),
+                                   make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                               __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (c < valid) dst[c] = __uint_as_float(v[c]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<E_TMEM_COLS>(tmem_base);
+}
+
+}  // namespace pf
+
+extern "C" int pf_mask_einsum(const uint16_t* feats, const float* kern, const float* kbias, float* logits,
+                              uint32_t* bits_out, int B, int N, int HW, int HWp, int n_units, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(feats && kern && kbias, PF_ERR_ARG, "pf_mask_einsum: null input");
+    PF_REQUIRE(logits || bits_out, PF_ERR_ARG, "pf_mask_einsum: no output requested");
+    PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_mask_einsum: bad shape B=%d N=%d HW=%d", B, N, HW);
+    PF_REQUIRE(n_units == B || n_units == 2 * B, PF_ERR_ARG, "pf_mask_einsum: n_units must be B or 2B");
+    PF_REQUIRE(HWp >= HW && HWp % 8 == 0, PF_ERR_ALIGN, "pf_mask_einsum: HWp=%d must be >= HW and a multiple of 8", HWp);
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(kern) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: kern not 16-byte aligned");
+    PF_REQUIRE(!logits || (reinterpret_cast<uintptr_t>(logits) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: logits not 16-byte aligned");
+
+    CUtensorMap tmap;
+    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_units * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
+
+    EinsumParams p;
+    p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
+    p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
+    p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
+    int cpu = num_sms() / n_units;
+    if (cpu < 1) cpu = 1;
+    if (cpu > p.tiles_per_unit) cpu = p.tiles_per_unit;
+    p.ctas_per_unit = cpu;
+
+    cudaError_t ea = cudaFuncSetAttribute(einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
+    if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
+    einsum_kernel<<<n_units * cpu, E_THREADS, E_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, p);
+    PF_CHECK_LAUNCH("einsum_kernel");
+    return PF_OK;
+}

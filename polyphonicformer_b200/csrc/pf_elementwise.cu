@@ -1,0 +1,162 @@
+// Streaming (HBM-bound) helper kernels of the decoder: storage cast, mask binarisation, x2 bilinear upsampling.
+#include "pf_internal.h"
+#include "pf_sm100.cuh"
+
+namespace pf {
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 [B][256][HW] (x2 tensors) -> bf16 [2][B][256][HWp]; pad columns [HW, HWp) are written as zero.
+__global__ void cast_feats_kernel(const float* __restrict__ x, const float* __restrict__ d,
+                                  uint16_t* __restrict__ out, int rows_per_branch, int HW, int HWp) {
+    const int row = blockIdx.y;  // 0 .. 2*rows_per_branch
+    const float* src = (row < rows_per_branch ? x + (size_t)row * HW : d + (size_t)(row - rows_per_branch) * HW);
+    uint16_t* dst = out + (size_t)row * HWp;
+    const bool vec = (HW & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < HWp; c += gridDim.x * blockDim.x * 4) {
+        float v[4];
+        if (vec && c + 3 < HW) {
+            const float4 f = __ldcs(reinterpret_cast<const float4*>(src + c));
+            v[0] = f.x, v[1] = f.y, v[2] = f.z, v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = (c + i < HW) ? src[c + i] : 0.f;
+        }
+        // HWp % 8 == 0 so c + 3 < HWp whenever c < HWp
+        *reinterpret_cast<uint2*>(dst + c) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mask logits fp32 [B][N][HW] -> bits u32 [B][WORDS][128]: one block per (b, group of 8 words); warp w ballots the
+// 32 pixels of a word for rows n = w, w+8, ...  (kernel_update_head.py:236-238: sigmoid(x) > 0.5  <=>  x > 0)
+constexpr int BIN_WORDS = 8;
+__global__ void __launch_bounds__(256) binarise_kernel(const float* __restrict__ logits, uint32_t* __restrict__ bits,
+                                                       int N, int HW, int words) {
+    __shared__ uint32_t s_bits[BIN_WORDS][128];
+    const int b = blockIdx.y;
+    const int w0 = blockIdx.x * BIN_WORDS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < BIN_WORDS * 128; i += 256) (&s_bits[0][0])[i] = 0u;
+    __syncthreads();
+    const float* base = logits + (size_t)b * N * HW;
+    for (int n = warp; n < N; n += 8) {
+        const float* row = base + (size_t)n * HW;
+#pragma unroll
+        for (int k = 0; k < BIN_WORDS; ++k) {
+            const int hw = (w0 + k) * 32 + lane;
+            const float v = (hw < HW) ? __ldcs(row + hw) : 0.f;
+            const uint32_t m = __ballot_sync(0xffffffffu, v > 0.f);
+            if (lane == 0) s_bits[k][n] = m;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BIN_WORDS * 128; i += 256) {
+        const int k = i >> 7, n = i & 127;
+        if (w0 + k < words) bits[((size_t)b * words + w0 + k) * 128 + n] = s_bits[k][n];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on [maps][H][W] planes
+// (polyphonic/kernel_update.py:133-143).  src = (dst + 0.5)/2 - 0.5 clamped at 0; weights follow ATen's
+// upsample_bilinear2d: h0l*(w0l*a + w1l*b) + h1l*(w0l*c + w1l*d).
+// Thread = 1 input pixel column pair -> 4 output columns x 2 output rows (the 2x2 outputs of input pixels x, x+1).
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+                                                         int W) {
+    const int map = blockIdx.z;
+    const int y = blockIdx.y;  // input row; produces output rows 2y, 2y+1
+    const float* src = in + (size_t)map * H * W;
+    float* dst = out + (size_t)map * (4 * (size_t)H * W);
+    const int W2 = 2 * W;
+    const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+    const float* r0 = src + (size_t)ym * W;
+    const float* r1 = src + (size_t)y * W;
+    const float* r2 = src + (size_t)yp * W;
+    // output row 2y   : src_y = y - 0.25 -> rows (y-1, y) weights (0.25, 0.75); at y = 0 clamps to row 0 weight 1
+    // output row 2y+1 : src_y = y + 0.25 -> rows (y, y+1) weights (0.75, 0.25); at y = H-1 both rows are H-1
+    const float t0 = (y == 0) ? 0.f : 0.25f;   // weight of r0 in the top output row (h0lambda) else
+    for (int xp = blockIdx.x * blockDim.x + threadIdx.x; xp * 2 < W; xp += gridDim.x * blockDim.x) {
+        const int x = xp * 2;
+        // input columns x-1 .. x+2 (clamped)
+        const int c0 = max(x - 1, 0), c1 = x, c2 = min(x + 1, W - 1), c3 = min(x + 2, W - 1);
+        float a[3][4];
+        a[0][0] = __ldg(r0 + c0), a[0][1] = __ldg(r0 + c1), a[0][2] = __ldg(r0 + c2), a[0][3] = __ldg(r0 + c3);
+        a[1][0] = __ldg(r1 + c0), a[1][1] = __ldg(r1 + c1), a[1][2] = __ldg(r1 + c2), a[1][3] = __ldg(r1 + c3);
+        a[2][0] = __ldg(r2 + c0), a[2][1] = __ldg(r2 + c1), a[2][2] = __ldg(r2 + c2), a[2][3] = __ldg(r2 + c3);
+        // horizontal pass for the 4 output columns 2x .. 2x+3 of each of the 3 input rows
+        float hrow[3][4];
+        const float l0 = (x == 0) ? 0.f : 0.25f;  // weight of column x-1 for output column 2x
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            // out col 2x   : (x-1, x) with lambdas (w0 = 1 - w1, w1): src = x - 0.25 -> x0 = x-1, w1 = 0.75
+            //               at x == 0: src clamps to 0 -> x0 = 0, w1 = 0 -> value a[r][1] (c0 == c1 == 0)
+            hrow[r][0] = (x == 0) ? (1.f * a[r][1] + 0.f * a[r][2]) : (l0 * a[r][0] + 0.75f * a[r][1]);
+            // out col 2x+1 : src = x + 0.25 -> (x, x+1) weights (0.75, 0.25)
+            hrow[r][1] = 0.75f * a[r][1] + 0.25f * a[r][2];
+            // out col 2x+2 : src = x + 0.75 -> (x, x+1) weights (0.25, 0.75)
+            hrow[r][2] = 0.25f * a[r][1] + 0.75f * a[r][2];
+            // out col 2x+3 : src = x + 1.25 -> (x+1, x+2) weights (0.75, 0.25)
+            hrow[r][3] = 0.75f * a[r][2] + 0.25f * a[r][3];
+        }
+        float o0[4], o1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o0[k] = (y == 0) ? (1.f * hrow[1][k] + 0.f * hrow[2][k]) : (t0 * hrow[0][k] + 0.75f * hrow[1][k]);
+            o1[k] = 0.75f * hrow[1][k] + 0.25f * hrow[2][k];
+        }
+        float* d0 = dst + (size_t)(2 * y) * W2 + 2 * x;
+        float* d1 = d0 + W2;
+        if (x + 1 < W && (W2 & 3) == 0) {
+            __stcs(reinterpret_cast<float4*>(d0), make_float4(o0[0], o0[1], o0[2], o0[3]));
+            __stcs(reinterpret_cast<float4*>(d1), make_float4(o1[0], o1[1], o1[2], o1[3]));
+        } else {
+            const int nout = (x + 1 < W) ? 4 : 2;
+            for (int k = 0; k < nout; ++k) d0[k] = o0[k], d1[k] = o1[k];
+        }
+    }
+}
+
+}  // namespace pf
+
+extern "C" int pf_cast_feats(const float* x_feats, const float* depth_feats, uint16_t* feats, int B, int HW, int HWp,
+                             void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(x_feats && depth_feats && feats, PF_ERR_ARG, "pf_cast_feats: null pointer");
+    PF_REQUIRE(B > 0 && HW > 0 && HWp >= HW && HWp % 8 == 0, PF_ERR_ARG, "pf_cast_feats: bad shape B=%d HW=%d HWp=%d", B, HW, HWp);
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(feats) & 15) == 0, PF_ERR_ALIGN, "pf_cast_feats: feats not 16-byte aligned");
+    const int rows = B * PF_C;
+    int gx = (HWp / 4 + 255) / 256;
+    if (gx > 32) gx = 32;
+    dim3 grid(gx, 2 * rows);
+    cast_feats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_feats, depth_feats, feats, rows, HW, HWp);
+    PF_CHECK_LAUNCH("cast_feats_kernel");
+    return PF_OK;
+}
+
+extern "C" int pf_binarise(const float* mask_logits, uint32_t* bits, int B, int N, int HW, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(mask_logits && bits, PF_ERR_ARG, "pf_binarise: null pointer");
+    PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_binarise: bad shape B=%d N=%d HW=%d", B, N, HW);
+    const int words = (HW + 31) / 32;
+    dim3 grid((words + BIN_WORDS - 1) / BIN_WORDS, B);
+    binarise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask_logits, bits, N, HW, words);
+    PF_CHECK_LAUNCH("binarise_kernel");
+    return PF_OK;
+}
+
+extern "C" int pf_upsample2x(const float* in, float* out, int maps, int H, int W, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(in && out, PF_ERR_ARG, "pf_upsample2x: null pointer");
+    PF_REQUIRE(maps > 0 && H > 0 && W > 0 && maps <= 65535 && H <= 65535, PF_ERR_ARG, "pf_upsample2x: bad shape maps=%d H=%d W=%d", maps, H, W);
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, PF_ERR_ALIGN, "pf_upsample2x: out not 16-byte aligned");
+    const int pairs = (W + 1) / 2;
+    int threads = 256;
+    while (threads > 32 && threads / 2 >= pairs) threads /= 2;
+    dim3 grid((pairs + threads - 1) / threads, H, maps);
+    upsample2x_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, H, W);
+    PF_CHECK_LAUNCH("upsample2x_kernel");
+    return PF_OK;
+}

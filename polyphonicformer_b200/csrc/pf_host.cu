@@ -1,0 +1,88 @@
+// Error reporting, device checks, TMA descriptor encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include "pf_internal.h"
+
+namespace pf {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return set_error(PF_ERR_ARCH, "no CUDA device: %s", cudaGetErrorString(e));
+    static thread_local int cached_dev = -1, cached_major = 0;
+    if (cached_dev != dev) {
+        int major = 0;
+        e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        if (e != cudaSuccess) return set_error(PF_ERR_ARCH, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+        cached_dev = dev;
+        cached_major = major;
+    }
+    if (cached_major != 10)
+        return set_error(PF_ERR_ARCH, "device %d is sm_%dx; libpf_decoder is built for sm_100a only", dev, cached_major);
+    return PF_OK;
+}
+
+int num_sms() {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    static thread_local int cached_dev = -1, cached_n = 0;
+    if (cached_dev == dev) return cached_n;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+    cached_n = n;
+    return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(PF_ERR_ALIGN, "TMA base not 16-byte aligned");
+    if ((pitch_elems * 2) % 16 != 0) return set_error(PF_ERR_ALIGN, "TMA row pitch %llu elems not a 16-byte multiple",
+                                                       (unsigned long long)pitch_elems);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return PF_OK;
+}
+
+}  // namespace pf
+
+extern "C" int pf_version(void) { return 100; }
+extern "C" const char* pf_last_error_string(void) { return pf::g_err; }
+extern "C" int pf_last_launch_count(void) { return pf::g_launches; }

@@ -1,0 +1,36 @@
+// Host-side plumbing shared by the translation units of libpf_decoder.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pf_decoder.h"
+
+namespace pf {
+
+int set_error(int code, const char* fmt, ...);
+int check_device();             // PF_OK iff the current device is sm_100
+int num_sms();                  // SM count of the current device
+void count_launch(int n = 1);   // per-thread launch counter (pf_last_launch_count)
+void reset_launch_count();
+
+// cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency).
+// 2-D bf16 tensor [rows][cols] with row pitch `pitch_elems`; box = [box_rows][box_cols]; 128-byte swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                      uint32_t box_rows, uint32_t box_cols);
+
+#define PF_CHECK_LAUNCH(name)                                                          \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess)                                                        \
+            return pf::set_error(PF_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
+        pf::count_launch();                                                            \
+    } while (0)
+
+#define PF_REQUIRE(cond, code, ...) \
+    do {                            \
+        if (!(cond)) return pf::set_error(code, __VA_ARGS__); \
+    } while (0)
+
+}  // namespace pf

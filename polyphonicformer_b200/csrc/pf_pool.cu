@@ -1,0 +1,223 @@
+// K1 -- mask pooling (polyphonic/kernel_update_head.py:236-242, polyphonic/kernel_head.py:313-320 of the reference):
+//     pooled[g][n][c] = sum_hw 1[mask_logit[b][n][hw] > 0] * feats[g][c][hw]
+// as a split-K [128 x HW] x [HW x 256] GEMM on tcgen05.  The mask operand is {0,1}, so every product is exact and
+// only the fp32 summation order differs from the reference.
+//
+//   A  = mask tile [128 n][64 hw] bf16, expanded on chip from the packed sign bits (1 KB per tile instead of the
+//        28 KB of fp32 logits), written K-major / 128-byte-swizzled by the 4 expander warps;
+//   B  = feats[g][:, hw0:hw0+64] bf16, TMA box [256 c][64 hw] = K-major operand with N = 256;
+//   D  = [128 n][256 c] fp32 in TMEM, accumulated over the CTA's slab of HW, then written as one split-K partial.
+//   Deterministic: partials are reduced in a fixed order by the consumer (pf_kernel_update / pf_pool_reduce).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = bit expanders, then epilogue.  HBM-bound: 2*C*HW*2 bytes of features per image dominate.
+#include "pf_internal.h"
+#include "pf_sm100.cuh"
+
+namespace pf {
+
+constexpr int P_C = PF_C;
+constexpr int P_BHW = 64;  // K per pipeline stage
+constexpr int P_STAGES = 4;
+constexpr int P_A_BYTES = 128 * P_BHW * 2;  // 16384
+constexpr int P_B_BYTES = P_C * P_BHW * 2;  // 32768
+constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr int P_TMEM_COLS = 256;
+constexpr int P_THREADS = 192;
+constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 256 + 1024;
+
+struct PoolParams {
+    const uint32_t* bits;  // [B][WORDS][128]
+    float* partial;        // [G][S][N][256]
+    float* cntp;           // [G][S][N]
+    int N, HW, words, B, S, tiles_per_unit;
+};
+
+// 8 mask bits -> 8 bf16 {0,1} packed in 4 u32 (element 2i in the low half)
+__device__ __forceinline__ uint4 expand8(uint32_t b) {
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        r[i] = ((b >> (2 * i)) & 1u) * 0x3F80u | ((b >> (2 * i + 1)) & 1u) * 0x3F800000u;
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
+    uint64_t* fullB = bars;
+    uint64_t* fullA = bars + P_STAGES;
+    uint64_t* empty = bars + 2 * P_STAGES;
+    uint64_t* accfull = bars + 3 * P_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * P_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x / p.S;  // branch * B + b
+    const int split = blockIdx.x % p.S;
+    const int b = unit % p.B;
+    const int tile_begin = (int)((long long)split * p.tiles_per_unit / p.S);
+    const int tile_end = (int)((long long)(split + 1) * p.tiles_per_unit / p.S);
+    const int ntiles = tile_end - tile_begin;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_feats);
+        for (int i = 0; i < P_STAGES; ++i) {
+            mbar_init(&fullB[i], 1);
+            mbar_init(&fullA[i], 128);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(accfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<P_TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % P_STAGES;
+                mbar_wait(&empty[s], ((i / P_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&fullB[s], P_B_BYTES);
+                tma_load_2d(smem + s * P_STAGE_BYTES + P_A_BYTES, &tmap_feats, &fullB[s], (tile_begin + i) * P_BHW,
+                            unit * P_C, kEvictFirst);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, P_C, 0, 0);
+            for (int i = 0; i < ntiles; ++i) {
+                const int s = i % P_STAGES;
+                const uint32_t ph = (i / P_STAGES) & 1;
+                mbar_wait(&fullA[s], ph);
+                mbar_wait(&fullB[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + s * P_STAGE_BYTES);
+                const uint32_t b_base = a_base + P_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < P_BHW / 16; ++k)
+                    umma_bf16_ss(tmem_base, make_smem_desc_sw128(a_base + k * 32, 16, 1024),
+                                 make_smem_desc_sw128(b_base + k * 32, 16, 1024), idesc, (i | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(accfull);
+        }
+    } else {
+        // ---- expanders: thread = mask row r (TMEM lane r later in the epilogue)
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t* brow = p.bits + (size_t)b * p.words * 128 + r;
+        uint32_t count = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i % P_STAGES;
+            const int w0 = (tile_begin + i) * 2;
+            const uint32_t m0 = (w0 < p.words) ? __ldg(brow + (size_t)w0 * 128) : 0u;
+            const uint32_t m1 = (w0 + 1 < p.words) ? __ldg(brow + (size_t)(w0 + 1) * 128) : 0u;
+            count += __popc(m0) + __popc(m1);
+            mbar_wait(&empty[s], ((i / P_STAGES) & 1) ^ 1);
+            uint8_t* sA = smem + s * P_STAGE_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(sA + sw128_offset(r, c)) = expand8((m0 >> (8 * c)) & 0xFFu);
+                *reinterpret_cast<uint4*>(sA + sw128_offset(r, c + 4)) = expand8((m1 >> (8 * c)) & 0xFFu);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&fullA[s]);
+        }
+        // ---- epilogue: one split-K partial per CTA
+        const size_t slab = (size_t)unit * p.S + split;
+        if (r < p.N) p.cntp[slab * p.N + r] = (float)count;
+        if (ntiles > 0) {
+            mbar_wait(accfull, 0);
+            tc_fence_after();
+        }
+        float* orow = p.partial + (slab * p.N + (r < p.N ? r : 0)) * P_C;
+#pragma unroll 1
+        for (int c0 = 0; c0 < P_C; c0 += 32) {
+            uint32_t v[32];
+            if (ntiles > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = 0u;
+            }
+            if (r < p.N) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<uint4*>(orow + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<P_TMEM_COLS>(tmem_base);
+}
+
+// sum over splits: pooled[g][n][c], count[b][n]
+__global__ void pool_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ cntp,
+                                   float* __restrict__ pooled, float* __restrict__ count, int G, int B, int N, int S) {
+    const int row = blockIdx.x;  // g * N + n
+    const int g = row / N, n = row % N;
+    const int c = threadIdx.x;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += partial[(((size_t)g * S + s) * N + n) * P_C + c];
+    pooled[(size_t)row * P_C + c] = acc;
+    if (c == 0 && g < B && count) {
+        float k = 0.f;
+        for (int s = 0; s < S; ++s) k += cntp[((size_t)g * S + s) * N + n];
+        count[g * N + n] = k;
+    }
+}
+
+}  // namespace pf
+
+extern "C" int pf_pool_splits(int B, int n_branch, int HW) {
+    if (B <= 0 || n_branch <= 0 || HW <= 0) return 0;
+    int sms = 148;
+    if (pf::check_device() == PF_OK) sms = pf::num_sms();
+    const int tiles = (HW + pf::P_BHW - 1) / pf::P_BHW;
+    int S = sms / (B * n_branch);
+    if (S < 1) S = 1;
+    if (S > tiles) S = tiles;
+    return S;
+}
+
+extern "C" int pf_mask_pool(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int B, int N,
+                            int HW, int HWp, int n_branch, int S, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(feats && bits && partial && cntp, PF_ERR_ARG, "pf_mask_pool: null pointer");
+    PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0 && (n_branch == 1 || n_branch == 2), PF_ERR_ARG,
+               "pf_mask_pool: bad shape B=%d N=%d HW=%d n_branch=%d", B, N, HW, n_branch);
+    PF_REQUIRE(HWp >= HW && HWp % 8 == 0, PF_ERR_ALIGN, "pf_mask_pool: HWp=%d must be >= HW and a multiple of 8", HWp);
+    const int tiles = (HW + P_BHW - 1) / P_BHW;
+    PF_REQUIRE(S >= 1 && S <= tiles, PF_ERR_ARG, "pf_mask_pool: S=%d out of range [1,%d]", S, tiles);
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 15) == 0, PF_ERR_ALIGN, "pf_mask_pool: partial not 16-byte aligned");
+
+    CUtensorMap tmap;
+    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_branch * B * P_C, (uint64_t)HW, (uint64_t)HWp, P_C, P_BHW)) return e;
+    PoolParams p;
+    p.bits = bits, p.partial = partial, p.cntp = cntp;
+    p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B, p.S = S, p.tiles_per_unit = tiles;
+    cudaError_t e = cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "pool smem attribute: %s", cudaGetErrorString(e));
+    pool_kernel<<<n_branch * B * S, P_THREADS, P_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, p);
+    PF_CHECK_LAUNCH("pool_kernel");
+    return PF_OK;
+}
+
+extern "C" int pf_pool_reduce(const float* partial, const float* cntp, float* pooled, float* count, int B, int N,
+                              int n_branch, int S, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(partial && cntp && pooled, PF_ERR_ARG, "pf_pool_reduce: null pointer");
+    pool_reduce_kernel<<<n_branch * B * N, P_C, 0, static_cast<cudaStream_t>(stream)>>>(partial, cntp, pooled, count,
+                                                                                       n_branch * B, B, N, S);
+    PF_CHECK_LAUNCH("pool_reduce_kernel");
+    return PF_OK;
+}

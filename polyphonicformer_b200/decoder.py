@@ -1,0 +1,243 @@
+"""Host side of the B200 decoder: weight packing (with the feat_transform fold), buffer management and the calls
+into libpf_decoder.so.  PyTorch is used for device memory and streams only; every arithmetic step of the decoder
+runs in the CUDA kernels behind include/pf_decoder.h.
+
+Reference being replaced (paths relative to the reference tree):
+  KernelUpdateHead.forward                         polyphonic/kernel_update_head.py:212-353
+  KernelUpdator.forward                            polyphonic/funcs/kernel_updator.py:55-93
+  KernelUpdateIterHead._mask_forward / simple_test polyphonic/kernel_update.py:125-157, 282-354
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+from ._cabi import PF_C, PF_MAX_CLASSES, PF_MAX_N, BranchWeights, StageWeights
+
+_BRANCHES = (
+    # suffix, updator, feat transform, head fcs, head norm, final fc
+    dict(sfx='', upd='kernel_update_conv', ft='feat_transform', fc='fc_mask'),
+    dict(sfx='_depth', upd='kernel_update_conv_depth', ft='feat_depth_transform', fc='fc_depth'),
+)
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class PackedStage:
+    """One KernelUpdateHead's parameters in the layout of ``struct pf_stage_weights``.
+
+    ``sd`` maps the reference's state-dict keys of one stage (e.g.
+    ``kernel_update_conv.dynamic_layer.weight``) to tensors.  Folding is done in fp64 and rounded once to fp32.
+    """
+
+    def __init__(self, sd, device, num_classes, ffn_channels):
+        f64 = {k: v.detach().to('cpu', torch.float64) for k, v in sd.items()}
+        parts = {}
+
+        def ln(name):
+            return torch.stack([f64[name + '.weight'], f64[name + '.bias']])
+
+        for bi, br in enumerate(_BRANCHES):
+            sfx, upd, ft, fc = br['sfx'], br['upd'], br['ft'], br['fc']
+            if ft + '.conv.weight' in f64:   # 1x1 conv with bias, no norm, no activation (kernel_update_head.py:124-140)
+                Wt = f64[ft + '.conv.weight'].reshape(PF_C, PF_C)
+                bt = f64[ft + '.conv.bias']
+            else:                            # feat_transform_cfg=None
+                Wt = torch.eye(PF_C, dtype=torch.float64)
+                bt = torch.zeros(PF_C, dtype=torch.float64)
+            Wdyn = f64[upd + '.dynamic_layer.weight']
+            assert Wdyn.shape == (2 * PF_C, PF_C), 'KernelUpdator with feat_channels != 256 is not supported'
+            Wfc, bfc = f64[fc + '.weight'], f64[fc + '.bias']
+            p = dict(
+                dyn_w=Wdyn @ Wt, dyn_b=f64[upd + '.dynamic_layer.bias'], dyn_cb=Wdyn @ bt,
+                inp_w=f64[upd + '.input_layer.weight'], inp_b=f64[upd + '.input_layer.bias'],
+                gate_w=torch.cat([f64[upd + '.input_gate.weight'], f64[upd + '.update_gate.weight']]),
+                gate_b=torch.cat([f64[upd + '.input_gate.bias'], f64[upd + '.update_gate.bias']]),
+                ln_input_norm_in=ln(upd + '.input_norm_in'), ln_norm_in=ln(upd + '.norm_in'),
+                ln_norm_out=ln(upd + '.norm_out'), ln_input_norm_out=ln(upd + '.input_norm_out'),
+                fc_w=f64[upd + '.fc_layer.weight'], fc_b=f64[upd + '.fc_layer.bias'], ln_fc_norm=ln(upd + '.fc_norm'),
+                qkv_w=f64['attention%s.attn.in_proj_weight' % sfx], qkv_b=f64['attention%s.attn.in_proj_bias' % sfx],
+                out_w=f64['attention%s.attn.out_proj.weight' % sfx], out_b=f64['attention%s.attn.out_proj.bias' % sfx],
+                ln_attn=ln('attention_norm%s' % sfx),
+                ffn1_w=f64['ffn%s.layers.0.0.weight' % sfx], ffn1_b=f64['ffn%s.layers.0.0.bias' % sfx],
+                ffn2_w=f64['ffn%s.layers.1.weight' % sfx], ffn2_b=f64['ffn%s.layers.1.bias' % sfx],
+                ln_ffn=ln('ffn_norm%s' % sfx),
+                kern_w=Wt.t() @ Wfc, kern_b=Wt.t() @ bfc, kb_w=Wfc.t() @ bt,
+            )
+            assert p['ffn1_w'].shape == (ffn_channels, PF_C)
+            if bi == 0:
+                p['head_w'] = torch.cat([f64['cls_fcs.0.weight'], f64['mask_fcs.0.weight']])
+                p['ln_head_a'], p['ln_head_b'] = ln('cls_fcs.1'), ln('mask_fcs.1')
+                cw = torch.zeros(PF_MAX_CLASSES, PF_C, dtype=torch.float64)
+                cb = torch.zeros(PF_MAX_CLASSES, dtype=torch.float64)
+                ncls = f64['fc_cls.weight'].shape[0]
+                assert ncls == num_classes <= PF_MAX_CLASSES
+                cw[:ncls], cb[:ncls] = f64['fc_cls.weight'], f64['fc_cls.bias']
+                p['cls_w'], p['cls_b'] = cw, cb
+            else:
+                p['head_w'] = f64['depth_regs.0.weight']
+                p['ln_head_a'] = ln('depth_regs.1')
+            parts[bi] = (p, float(bfc @ bt))
+
+        # one flat fp32 device buffer, every tensor 256-byte aligned
+        offs, total = {}, 0
+        for bi, (p, _) in parts.items():
+            for k, v in p.items():
+                offs[(bi, k)] = total
+                total += round_up(v.numel(), 64)
+        flat = torch.zeros(total, dtype=torch.float32)
+        for bi, (p, _) in parts.items():
+            for k, v in p.items():
+                o = offs[(bi, k)]
+                flat[o:o + v.numel()] = v.reshape(-1).to(torch.float32)
+        self.flat = flat.to(device)
+        self.views = {}
+        for bi, (p, _) in parts.items():
+            for k, v in p.items():
+                o = offs[(bi, k)]
+                self.views[(bi, k)] = self.flat[o:o + v.numel()].view(v.shape)
+        self.kb_b = {bi: kb for bi, (_, kb) in parts.items()}
+        base = self.flat.data_ptr()
+        self.struct = StageWeights()
+        self.struct.ffn_channels = ffn_channels
+        self.struct.num_classes = num_classes
+        for bi, (p, kb_b) in parts.items():
+            bw = self.struct.br[bi]
+            for name in BranchWeights._PTRS:
+                setattr(bw, name, base + 4 * offs[(bi, name)] if (bi, name) in offs else None)
+            bw.kb_b = kb_b
+            bw.head_relu = 1 if bi == 0 else 0
+
+
+class DecoderEngine:
+    """Runs decoder stages on the current CUDA device/stream through the C ABI.
+
+    Parameters: ``stage_dicts`` -- list (one per stage) of stage-local state dicts in the reference's key names.
+    """
+
+    def __init__(self, stage_dicts, device, num_classes=19, ffn_channels=2048):
+        _cabi.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _cabi.PFError(-4, 'DecoderEngine', 'the decoder runs on sm_100a CUDA devices only; there is no '
+                                                      'CPU path (got device %s)' % device)
+        self.num_classes = num_classes
+        self.ffn_channels = ffn_channels
+        self.stages = [PackedStage(sd, self.device, num_classes, ffn_channels) for sd in stage_dicts]
+        self.stage_array = (StageWeights * len(self.stages))(*[s.struct for s in self.stages])
+        self._ws = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _scratch(self, key, nbytes):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    @staticmethod
+    def pitch(HW):
+        return round_up(HW, 8)
+
+    def prepare_feats(self, x_feats, depth_feats):
+        """[B,256,H,W] x2 (fp32 or bf16) -> bf16 [2,B,256,HWp] in the library's layout."""
+        B, C, H, W = x_feats.shape
+        assert C == PF_C and depth_feats.shape == x_feats.shape
+        HW = H * W
+        HWp = self.pitch(HW)
+        feats = torch.empty((2, B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
+        if x_feats.dtype == torch.float32 and depth_feats.dtype == torch.float32:
+            x, d = x_feats.contiguous(), depth_feats.contiguous()
+            _cabi.call('pf_cast_feats', _ptr(x), _ptr(d), _ptr(feats), B, HW, HWp, _stream_ptr())
+        else:   # already in storage precision: plain strided copy (no arithmetic)
+            feats[0, :, :, :HW].copy_(x_feats.reshape(B, C, HW))
+            feats[1, :, :, :HW].copy_(depth_feats.reshape(B, C, HW))
+            if HWp != HW:
+                feats[:, :, :, HW:].zero_()
+        return feats
+
+    # ------------------------------------------------------------------ one stage (KernelUpdateHead.forward)
+    def stage_forward(self, stage, feats, mask_logits, obj, dep, H, W, cls_sigmoid=False):
+        """feats from prepare_feats; mask_logits [B,N,H,W] fp32; obj/dep [B,N,256] fp32.
+        Returns cls_score [B,N,classes], logits [2,B,N,H,W], obj_out, dep_out."""
+        B, N = obj.shape[:2]
+        assert N <= PF_MAX_N
+        HW, HWp = H * W, feats.shape[-1]
+        st = _stream_ptr()
+        lib = _cabi.load()
+        words = (HW + 31) // 32
+        S = lib.pf_pool_splits(B, 2, HW)
+        mask_logits = mask_logits.contiguous()
+        obj, dep = obj.contiguous(), dep.contiguous()
+        bits = torch.empty((B, words, 128), dtype=torch.int32, device=self.device)
+        partial = torch.empty((2 * B, S, N, PF_C), dtype=torch.float32, device=self.device)
+        cntp = torch.empty((2 * B, S, N), dtype=torch.float32, device=self.device)
+        kern = torch.empty((2, B, N, PF_C), dtype=torch.float32, device=self.device)
+        kbias = torch.empty((2, B, N), dtype=torch.float32, device=self.device)
+        obj_out, dep_out = torch.empty_like(obj), torch.empty_like(dep)
+        cls = torch.empty((B, N, self.num_classes), dtype=torch.float32, device=self.device)
+        logits = torch.empty((2, B, N, H, W), dtype=torch.float32, device=self.device)
+        ws_bytes = lib.pf_update_workspace_bytes(B, N, self.ffn_channels)
+        ws = self._scratch('update', ws_bytes)
+        _cabi.call('pf_binarise', _ptr(mask_logits), _ptr(bits), B, N, HW, st)
+        _cabi.call('pf_mask_pool', _ptr(feats), _ptr(bits), _ptr(partial), _ptr(cntp), B, N, HW, HWp, 2, S, st)
+        _cabi.call('pf_kernel_update', ctypes.byref(self.stages[stage].struct), _ptr(partial), _ptr(cntp), S,
+                   _ptr(obj), _ptr(dep), _ptr(obj_out), _ptr(dep_out), _ptr(cls), _ptr(kern), _ptr(kbias),
+                   _ptr(ws), ws_bytes, B, N, 1 if cls_sigmoid else 0, st)
+        _cabi.call('pf_mask_einsum', _ptr(feats), _ptr(kern), _ptr(kbias), _ptr(logits), None, B, N, HW, HWp,
+                   2 * B, st)
+        return cls, logits, obj_out, dep_out
+
+    def upsample2x(self, maps):
+        """[..., H, W] fp32 -> [..., 2H, 2W] (bilinear, align_corners=False)."""
+        maps = maps.contiguous()
+        H, W = maps.shape[-2:]
+        out = torch.empty(maps.shape[:-2] + (2 * H, 2 * W), dtype=torch.float32, device=self.device)
+        _cabi.call('pf_upsample2x', _ptr(maps), _ptr(out), maps.numel() // (H * W), H, W, _stream_ptr())
+        return out
+
+    # ------------------------------------------------------------------ the whole stage loop
+    def alloc_decode_buffers(self, B, N, H, W, upsample=True):
+        HW = H * W
+        lib = _cabi.load()
+        nbytes = lib.pf_decoder_workspace_bytes(B, N, HW, self.ffn_channels)
+        return dict(
+            ws=torch.empty(nbytes, dtype=torch.uint8, device=self.device), ws_bytes=nbytes,
+            obj=torch.empty((B, N, PF_C), dtype=torch.float32, device=self.device),
+            dep=torch.empty((B, N, PF_C), dtype=torch.float32, device=self.device),
+            cls=torch.empty((B, N, self.num_classes), dtype=torch.float32, device=self.device),
+            logits=torch.empty((2, B, N, H, W), dtype=torch.float32, device=self.device),
+            scaled=(torch.empty((2, B, N, 2 * H, 2 * W), dtype=torch.float32, device=self.device)
+                    if upsample else None))
+
+    def decode(self, feats, mask_logits, obj, dep, H, W, upsample=True, all_stage_outputs=False, buffers=None):
+        """KernelUpdateIterHead.simple_test's stage loop (kernel_update.py:316-336).  Returns a dict with
+        cls_score (sigmoid), mask_preds, depth_preds, scaled_mask_preds, scaled_depth_preds, object_feats,
+        depth_proposal; tensors alias ``buffers`` when given."""
+        B, N = obj.shape[:2]
+        buf = buffers or self.alloc_decode_buffers(B, N, H, W, upsample)
+        buf['obj'].copy_(obj.reshape(B, N, PF_C))
+        buf['dep'].copy_(dep.reshape(B, N, PF_C))
+        self.decode_inplace(feats, mask_logits.contiguous(), buf, H, W, all_stage_outputs)
+        scaled = buf['scaled'] if upsample else buf['logits']
+        return dict(cls_score=buf['cls'], mask_preds=buf['logits'][0], depth_preds=buf['logits'][1],
+                    scaled_mask_preds=scaled[0], scaled_depth_preds=scaled[1],
+                    object_feats=buf['obj'], depth_proposal=buf['dep'])
+
+    def decode_inplace(self, feats, mask_logits, buf, H, W, all_stage_outputs=False):
+        """Launch-only variant (graph-capturable): obj/dep in ``buf`` are updated in place."""
+        B, N = buf['obj'].shape[:2]
+        _cabi.call('pf_decoder_forward', self.stage_array, len(self.stages), _ptr(feats), _ptr(mask_logits),
+                   _ptr(buf['obj']), _ptr(buf['dep']), _ptr(buf['cls']), _ptr(buf['logits']), _ptr(buf['scaled']),
+                   _ptr(buf['ws']), buf['ws_bytes'], B, N, H, W, feats.shape[-1],
+                   _cabi.PF_FWD_ALL_STAGE_OUTPUTS if all_stage_outputs else 0, _stream_ptr())
