@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- decoder throughput on synthetic Cityscapes-shape frames (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--height H] [--width W]
+
+One "step" = the 3-stage kernel-update decoder (KernelUpdateIterHead.simple_test's stage loop incl. the x2 upsampling
+and cls sigmoid) over one batch of B frames.  Workload at N=1: BASELINE.json configs[1] -- 1024x2048 frames
+(128x256 decoder map, N=111 kernels, C=256), batch 4, bf16 feature maps.  N>1: one process per GPU (torchrun), each
+rank decodes its own batch (frames shard batch-wise, no data-path collective) -> "scaling": "weak".
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM, timed with CUDA events, max over
+ranks.  `e2e` = same metric through DecoderEngine with pinned HOST buffers: H2D of the step's inputs and D2H of the
+step's results inside the timed region.  `roofline` = dominant kernel against MEASURED_PEAKS.json; `kernels` lists
+every kernel of the step.  `cpu_baseline` / `--impl reference` = the CPU oracle (oracle/decoder_ref.py, a pinned
+restatement of the reference's forward; the reference itself needs mmcv, absent on the box) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+C, N_KERNELS, STAGES, NUM_CLASSES = 256, 111, 3, 19
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=4)
+    ap.add_argument('--height', type=int, default=1024)
+    ap.add_argument('--width', type=int, default=2048)
+    ap.add_argument('--all-stage-outputs', action='store_true',
+                    help='also materialise the (unobservable) fp32 logits + depth einsum of stages 0..S-2')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d['hbm_gbs']), tf=float(d.get('bf16_tflops_sustained', d.get('bf16_tflops'))),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tf=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+def synth_state(seed=0):
+    from oracle import synth
+    sd = synth.synth_decoder_state(STAGES, seed)
+    stage_dicts = [{k[len('mask_head.%d.' % s):]: v for k, v in sd.items() if k.startswith('mask_head.%d.' % s)}
+                   for s in range(STAGES)]
+    return sd, stage_dicts
+
+
+def host_inputs(B, H, W, seed):
+    """Synthetic decoder inputs in HOST memory (same generator as the parity tests, cheap variant for big shapes)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = (torch.relu(torch.randn(B, C, H, W, generator=g)) + torch.relu(torch.randn(B, C, H, W, generator=g)))
+    d = (torch.relu(torch.randn(B, C, H, W, generator=g)) + 0.5 * torch.relu(torch.randn(B, C, H, W, generator=g)))
+    coarse = torch.randn(B, N_KERNELS, max(H // 4, 1), max(W // 4, 1), generator=g)
+    mask = torch.nn.functional.interpolate(coarse, size=(H, W), mode='bilinear', align_corners=False) * 3 \
+        + torch.randn(B, N_KERNELS, H, W, generator=g) - 0.4
+    prop = torch.randn(B, N_KERNELS, C, generator=g) * 0.5
+    dprop = (torch.randn(1, 1, C, generator=g) * 0.1).expand(B, N_KERNELS, C).contiguous()
+    return dict(x=x.to(torch.bfloat16), d=d.to(torch.bfloat16), mask=mask.contiguous(), prop=prop, dprop=dprop)
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own algorithm on the host cores: oracle/decoder_ref.py (pinned against the real reference's
+    outputs by tests/test_oracle_golden.py).  Each step = ONE frame (bounded sample of the batch-4 workload)."""
+    if rank != 0:
+        return
+    from oracle import decoder_ref as ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, _ = synth_state()
+    H, W = args.height // 8, args.width // 8
+    inp = host_inputs(1, H, W, 0)
+    x, d = inp['x'].float(), inp['d'].float()
+    prop, dprop = inp['prop'].reshape(1, N_KERNELS, C, 1, 1), inp['dprop'].reshape(1, N_KERNELS, C, 1, 1)
+    steps = max(1, min(args.steps, 8))
+    warm = max(1, min(args.warmup, 2))
+    with torch.no_grad():
+        for _ in range(warm):
+            ref.decoder_forward(sd, x, prop, inp['mask'], d, dprop)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ref.decoder_forward(sd, x, prop, inp['mask'], d, dprop)
+        dt = time.perf_counter() - t0
+    fps = steps / dt
+    sample = '%d steps x 1 frame of %dx%d (decoder map %dx%d), fp32, torch %d threads' % (
+        steps, args.height, args.width, H, W, cores)
+    line = dict(impl='reference', metric='decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)',
+                value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=1e3 * dt / steps,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=workload_config(args, 1),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(args, B):
+    return dict(workload='poly_r50 image decoder, %dx%d synthetic Cityscapes-shape frames, batch=%d per GPU, '
+                         'N=111 kernels (100 queries + 11 stuff), C=256, 3 stages, bf16 feature maps' %
+                         (args.height, args.width, B),
+                global_batch=B * args.gpus, decoder_map='%dx%d' % (args.height // 8, args.width // 8),
+                parallelism='dp%d (batch-sharded frames, no collective)' % args.gpus,
+                l2='per-step working set %.0f MB > 126 MB L2 (no flush needed)' % working_set_mb(args, B)
+                if working_set_mb(args, B) > 126 else 'L2 flushed between timed iterations',
+                stage_outputs='all' if args.all_stage_outputs else 'observable-only')
+
+
+def working_set_mb(args, B):
+    HW = (args.height // 8) * (args.width // 8)
+    return (2 * B * C * HW * 2 + 2 * B * N_KERNELS * HW * 4 * 5) / 1e6
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.strip().lower() == 'active':
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def flush_l2(buf):
+    buf.zero_()
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from polyphonicformer_b200 import _cabi
+    from polyphonicformer_b200.decoder import DecoderEngine, _ptr, _stream_ptr
+    lib = _cabi.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    B, H, W = args.batch, args.height // 8, args.width // 8
+    HW = H * W
+    N = N_KERNELS
+    sd, stage_dicts = synth_state()
+    eng = DecoderEngine(stage_dicts, dev, NUM_CLASSES, 2048)
+    hin = host_inputs(B, H, W, rank)
+    # resident inputs
+    feats = eng.prepare_feats(hin['x'].to(dev), hin['d'].to(dev))
+    mask = hin['mask'].to(dev)
+    prop, dprop = hin['prop'].to(dev), hin['dprop'].to(dev)
+    buf = eng.alloc_decode_buffers(B, N, H, W, upsample=True)
+    need_flush = working_set_mb(args, B) <= 126
+    l2buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if need_flush else None
+
+    def step():
+        buf['obj'].copy_(prop), buf['dep'].copy_(dprop)
+        eng.decode_inplace(feats, mask, buf, H, W, args.all_stage_outputs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches_per_step = lib.pf_last_launch_count() + 2      # + the two 57 KB proposal copies (torch memcpy kernels)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        if need_flush:
+            flush_l2(l2buf)
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---------------- per-kernel timing (same arguments as inside the step), CUDA events on the launching stream
+    kernels = kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, dev) if rank == 0 else None
+
+    # ---------------- e2e through the public API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    for k in kernels:
+        if k['bound'] == 'hbm':
+            k['achieved'] = k['alg_bytes'] / (k['ms'] * 1e-3) / 1e9
+            k['peak'], k['unit'] = pk['hbm'], 'GB/s'
+        else:
+            k['achieved'] = k['alg_flops'] / (k['ms'] * 1e-3) / 1e12
+            k['peak'], k['unit'] = pk['tf'], 'TFLOP/s'
+        k['frac'] = k['achieved'] / k['peak']
+    dom = max((k for k in kernels if k['bound'] == 'hbm'), key=lambda k: k['ms'] * k['calls_per_step'])
+    roofline = dict(kernel=dom['name'], bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'],
+                    unit=dom['unit'], frac=dom['frac'], traffic=None, peak_source=pk['source'],
+                    alg_bytes_per_launch=dom['alg_bytes'], ms_per_launch=dom['ms'])
+    line = dict(metric='decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)', value=value,
+                unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='bf16', data='synthetic', config=workload_config(args, B), clocks=clocks,
+                gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
+                roofline=roofline, kernels=kernels, ms_per_stage=ms_total / args.steps / STAGES)
+    if e2e:
+        line['e2e'] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_baseline(args)
+    print(json.dumps(line))
+
+
+def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, dev):
+    from polyphonicformer_b200 import _cabi
+    from polyphonicformer_b200.decoder import _ptr, _stream_ptr
+    HW, HWp = H * W, feats.shape[-1]
+    words = (HW + 31) // 32
+    S = lib.pf_pool_splits(B, 2, HW)
+    bits = torch.empty((B, words, 128), dtype=torch.int32, device=dev)
+    partial = torch.empty((2 * B, S, N, C), dtype=torch.float32, device=dev)
+    cntp = torch.empty((2 * B, S, N), dtype=torch.float32, device=dev)
+    kern = torch.randn((2, B, N, C), dtype=torch.float32, device=dev) * 0.1
+    kbias = torch.zeros((2, B, N), dtype=torch.float32, device=dev)
+    wsb = lib.pf_update_workspace_bytes(B, N, 2048)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    obj, dep = prop.clone(), dprop.clone()
+    obj_o, dep_o = torch.empty_like(obj), torch.empty_like(dep)
+    cls = torch.empty((B, N, NUM_CLASSES), dtype=torch.float32, device=dev)
+    st = _stream_ptr()
+    reps = max(5, min(args.steps, 20))
+    sx = 2   # bytes / feature element (bf16)
+    specs = [
+        ('binarise', 1, 'hbm', B * N * HW * 4 + B * words * 128 * 4, 0,
+         lambda: _cabi.call('pf_binarise', _ptr(mask), _ptr(bits), B, N, HW, st)),
+        ('mask_pool', STAGES, 'hbm', 2 * B * C * HW * sx + B * words * 128 * 4 + 2 * B * S * N * C * 4,
+         2 * 2 * B * N * C * HW,
+         lambda: _cabi.call('pf_mask_pool', _ptr(feats), _ptr(bits), _ptr(partial), _ptr(cntp), B, N, HW, HWp, 2, S,
+                            st)),
+        ('kernel_update (12 launches)', STAGES, 'latency', 0, 0,
+         lambda: _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[0].struct), _ptr(partial), _ptr(cntp), S,
+                            _ptr(obj), _ptr(dep), _ptr(obj_o), _ptr(dep_o), _ptr(cls), _ptr(kern), _ptr(kbias),
+                            _ptr(ws), wsb, B, N, 0, st)),
+        ('mask_einsum (bits only, mask branch)', 0 if args.all_stage_outputs else STAGES - 1, 'hbm',
+         B * C * HW * sx + B * N * C * 4 + B * words * 128 * 4, 2 * B * N * C * HW,
+         lambda: _cabi.call('pf_mask_einsum', _ptr(feats), _ptr(kern), _ptr(kbias), None, _ptr(bits), B, N, HW, HWp,
+                            B, st)),
+        ('mask_einsum (fp32 logits, both branches)', STAGES if args.all_stage_outputs else 1, 'hbm',
+         2 * B * C * HW * sx + 2 * B * N * C * 4 + 2 * B * N * HW * 4, 2 * 2 * B * N * C * HW,
+         lambda: _cabi.call('pf_mask_einsum', _ptr(feats), _ptr(kern), _ptr(kbias), _ptr(buf['logits']), None, B, N,
+                            HW, HWp, 2 * B, st)),
+        ('upsample2x', 1, 'hbm', 2 * B * N * HW * 4 * 5, 0,
+         lambda: _cabi.call('pf_upsample2x', _ptr(buf['logits']), _ptr(buf['scaled']), 2 * B * N, H, W, st)),
+    ]
+    l2buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+    for name, calls, bound, nbytes, flops, fn in specs:
+        if calls == 0:
+            continue
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            l2buf.zero_()            # flush L2 so every launch starts cold, like inside the step
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        k = dict(name=name, calls_per_step=calls, bound=bound if bound != 'latency' else 'latency',
+                 ms=tot / reps, alg_bytes=nbytes, alg_flops=flops)
+        if bound == 'latency':
+            k.update(bound='latency')
+        out.append(k)
+    res = []
+    for k in out:
+        if k['bound'] == 'latency':
+            k2 = dict(k)
+            k2['bound'] = 'hbm'
+            k2['alg_bytes'] = 3 * 4.02e6 * 4 / 3   # one stage's fp32 weights, for scale only
+            k2['note'] = 'latency / weight-streaming bound; fraction shown is weights bytes / time, for scale only'
+            res.append(k2)
+        else:
+            res.append(k)
+    return res
+
+
+def run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier):
+    """Public API with pinned host buffers: per step H2D of (x_feats, depth_feats) bf16 + mask logits + proposal
+    kernels, decode, D2H of cls scores and the x2-upsampled mask / depth logits."""
+    import torch.distributed as dist
+    pin = {k: v.pin_memory() for k, v in hin.items()}
+    out_cls = torch.empty((B, N, NUM_CLASSES), dtype=torch.float32).pin_memory()
+    out_scaled = torch.empty((2, B, N, 2 * H, 2 * W), dtype=torch.float32).pin_memory()
+    d_x = torch.empty_like(hin['x'], device=dev)
+    d_d = torch.empty_like(hin['d'], device=dev)
+    d_mask = torch.empty_like(hin['mask'], device=dev)
+    d_prop = torch.empty_like(hin['prop'], device=dev)
+    d_dprop = torch.empty_like(hin['dprop'], device=dev)
+    buf = eng.alloc_decode_buffers(B, N, H, W, upsample=True)
+    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ('x', 'd', 'mask', 'prop', 'dprop'))
+    d2h = out_cls.numel() * 4 + out_scaled.numel() * 4
+
+    def step():
+        d_x.copy_(pin['x'], non_blocking=True), d_d.copy_(pin['d'], non_blocking=True)
+        d_mask.copy_(pin['mask'], non_blocking=True)
+        d_prop.copy_(pin['prop'], non_blocking=True), d_dprop.copy_(pin['dprop'], non_blocking=True)
+        feats = eng.prepare_feats(d_x, d_d)
+        out = eng.decode(feats, d_mask, d_prop, d_dprop, H, W, upsample=True, buffers=buf,
+                         all_stage_outputs=args.all_stage_outputs)
+        out_cls.copy_(out['cls_score'], non_blocking=True)
+        out_scaled.copy_(buf['scaled'], non_blocking=True)
+
+    steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return dict(value=world * B * steps / (t.item() / 1e3), unit='frames/s', h2d_bytes_per_step=h2d,
+                d2h_bytes_per_step=d2h, steps=steps, ms_per_step=t.item() / steps,
+                note='serial H2D -> decode -> D2H per step on one stream; PCIe-bound')
+
+
+def cpu_baseline(args):
+    from oracle import decoder_ref as ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, _ = synth_state()
+    H, W = args.height // 8, args.width // 8
+    inp = host_inputs(1, H, W, 0)
+    x, d = inp['x'].float(), inp['d'].float()
+    prop, dprop = inp['prop'].reshape(1, N_KERNELS, C, 1, 1), inp['dprop'].reshape(1, N_KERNELS, C, 1, 1)
+    with torch.no_grad():
+        ref.decoder_forward(sd, x, prop, inp['mask'], d, dprop)
+        n, t0 = 0, time.perf_counter()
+        while n < 3 or (time.perf_counter() - t0 < 10 and n < 20):
+            ref.decoder_forward(sd, x, prop, inp['mask'], d, dprop)
+            n += 1
+        dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit='frames/s', cores=cores, kind='port',
+                sample='%d frames of %dx%d, one frame per call, fp32 oracle/decoder_ref.py on %d torch threads' %
+                       (n, args.height, args.width, cores))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
