@@ -129,6 +129,13 @@ int pf_kernel_update(const pf_stage_weights* w_host, const float* partial, const
                      float* kern, float* kbias, void* workspace, size_t workspace_bytes, int B, int N,
                      int cls_sigmoid, void* stream);
 
+/* KernelUpdator.forward alone (kernel_updator.py:55-93), for callers that use the module outside the stage:
+ * `bw` holds the module's own (un-folded) dyn_w [512][256] / dyn_b, inp_*, gate_*, the four gate LayerNorms, fc_*,
+ * ln_fc_norm; other fields are ignored.  update_feature, input_feature, out: [R][256]. */
+size_t pf_updator_workspace_bytes(int R);
+int pf_kernel_updator(const pf_branch_weights* bw_host, const float* update_feature, const float* input_feature,
+                      float* out, void* workspace, size_t workspace_bytes, int R, void* stream);
+
 /* kernel_update_head.py:308-334: logits[g][n][hw] = sum_c kern[g][n][c] * feats[g][c][hw] + kbias[g][n] on tcgen05.
  * n_units = B (mask branch only) or 2B.  logits and/or bits_out may be NULL (bits are taken from units < B). */
 int pf_mask_einsum(const uint16_t* feats, const float* kern, const float* kbias, float* logits, uint32_t* bits_out,

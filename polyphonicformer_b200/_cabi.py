@@ -57,6 +57,9 @@ _SIGS = {
     'pf_kernel_update': (c_int, [POINTER(StageWeights), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int,
                                  c_void_p]),
+    'pf_updator_workspace_bytes': (c_size_t, [c_int]),
+    'pf_kernel_updator': (c_int, [POINTER(BranchWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                  c_void_p]),
     'pf_mask_einsum': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
     'pf_upsample2x': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -525,3 +525,56 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
     }
     return PF_OK;
 }
+
+extern "C" size_t pf_updator_workspace_bytes(int R) { return R > 0 ? (size_t)R * 1536 * sizeof(float) : 0; }
+
+// KernelUpdator.forward on its own (polyphonic/funcs/kernel_updator.py:55-93): no feat_transform fold, one branch.
+extern "C" int pf_kernel_updator(const pf_branch_weights* bw, const float* update_feature, const float* input_feature,
+                                 float* out, void* workspace, size_t workspace_bytes, int R, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(bw && update_feature && input_feature && out && workspace, PF_ERR_ARG, "pf_kernel_updator: null pointer");
+    PF_REQUIRE(R > 0, PF_ERR_ARG, "pf_kernel_updator: R=%d", R);
+    PF_REQUIRE(workspace_bytes >= pf_updator_workspace_bytes(R), PF_ERR_WORKSPACE, "pf_kernel_updator: workspace %zu < %zu",
+               workspace_bytes, pf_updator_workspace_bytes(R));
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(update_feature) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(input_feature) & 15) == 0,
+               PF_ERR_ALIGN, "pf_kernel_updator: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* params = static_cast<float*>(workspace);
+    float* inp = params + (size_t)R * 512;
+    float* gate = inp + (size_t)R * 512;
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.R = R, a.K = 256, a.B = 1, a.N = R, a.S = 1;
+    GemmBranch g;
+
+    a.pro = PRO_PLAIN;
+    g = blank();
+    g.X = update_feature, g.ldx = 256, g.W = bw->dyn_w, g.bias = bw->dyn_b, g.ln[1] = bw->ln_norm_out;
+    g.Y = params, g.ldy = 512, g.Nout = 512, g.nstore = 512;
+    a.br[0] = g;
+    if (int e = launch_gemm(a, 512, 1, st)) return e;
+
+    g = blank();
+    g.X = input_feature, g.ldx = 256, g.W = bw->inp_w, g.bias = bw->inp_b, g.ln[1] = bw->ln_input_norm_out;
+    g.Y = inp, g.ldy = 512, g.Nout = 512, g.nstore = 512;
+    a.br[0] = g;
+    if (int e = launch_gemm(a, 512, 1, st)) return e;
+
+    a.pro = PRO_MUL;
+    g = blank();
+    g.X = inp, g.ldx = 512, g.X2 = params, g.ldx2 = 512, g.W = bw->gate_w, g.bias = bw->gate_b;
+    g.ln[0] = bw->ln_input_norm_in, g.ln[1] = bw->ln_norm_in, g.act[0] = g.act[1] = ACT_SIGMOID;
+    g.Y = gate, g.ldy = 512, g.Nout = 512, g.nstore = 512;
+    a.br[0] = g;
+    if (int e = launch_gemm(a, 512, 1, st)) return e;
+
+    a.pro = PRO_MIX;
+    g = blank();
+    g.X = gate + 256, g.ldx = 512, g.X2 = params + 256, g.ldx2 = 512, g.X3 = gate, g.ldx3 = 512, g.X4 = inp + 256, g.ldx4 = 512;
+    g.W = bw->fc_w, g.bias = bw->fc_b, g.ln[0] = bw->ln_fc_norm, g.act[0] = ACT_RELU;
+    g.Y = out, g.ldy = 256, g.Nout = 256, g.nstore = 256;
+    a.br[0] = g;
+    return launch_gemm(a, 256, 1, st);
+}

@@ -119,6 +119,40 @@ class PackedStage:
             bw.head_relu = 1 if bi == 0 else 0
 
 
+class PackedUpdator:
+    """A standalone KernelUpdator's parameters (no feat_transform fold) as a ``struct pf_branch_weights``."""
+
+    def __init__(self, sd, device):
+        f = {k: v.detach().to(device, torch.float32) for k, v in sd.items()}
+
+        def ln(name):
+            return torch.stack([f[name + '.weight'], f[name + '.bias']]).contiguous()
+
+        self.t = dict(
+            dyn_w=f['dynamic_layer.weight'].contiguous(), dyn_b=f['dynamic_layer.bias'].contiguous(),
+            inp_w=f['input_layer.weight'].contiguous(), inp_b=f['input_layer.bias'].contiguous(),
+            gate_w=torch.cat([f['input_gate.weight'], f['update_gate.weight']]).contiguous(),
+            gate_b=torch.cat([f['input_gate.bias'], f['update_gate.bias']]).contiguous(),
+            ln_input_norm_in=ln('input_norm_in'), ln_norm_in=ln('norm_in'), ln_norm_out=ln('norm_out'),
+            ln_input_norm_out=ln('input_norm_out'), fc_w=f['fc_layer.weight'].contiguous(),
+            fc_b=f['fc_layer.bias'].contiguous(), ln_fc_norm=ln('fc_norm'))
+        self.struct = BranchWeights()
+        for k, v in self.t.items():
+            setattr(self.struct, k, v.data_ptr())
+
+
+def run_kernel_updator(packed, update_feature, input_feature):
+    """[R,256], [R,256] fp32 CUDA tensors -> [R,256]."""
+    lib = _cabi.load()
+    R = update_feature.shape[0]
+    out = torch.empty((R, PF_C), dtype=torch.float32, device=update_feature.device)
+    nbytes = lib.pf_updator_workspace_bytes(R)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=update_feature.device)
+    _cabi.call('pf_kernel_updator', ctypes.byref(packed.struct), _ptr(update_feature), _ptr(input_feature), _ptr(out),
+               _ptr(ws), nbytes, R, _stream_ptr())
+    return out
+
+
 class DecoderEngine:
     """Runs decoder stages on the current CUDA device/stream through the C ABI.
 

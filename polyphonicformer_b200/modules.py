@@ -1,0 +1,385 @@
+"""Drop-in modules for the decoder hot path, registered under the reference's names.
+
+``KernelUpdator``, ``KernelUpdateHead`` and ``KernelUpdateIterHead`` take the reference's constructor kwargs
+(``configs/_base_/models/polyphonic_former.py:99-164``), expose the reference's ``state_dict`` keys and shapes
+ so its checkpoints load with ``strict=True``, and keep the reference's forward signatures:
+
+  KernelUpdator.forward(update_feature, input_feature)           polyphonic/funcs/kernel_updator.py:55-93
+  KernelUpdateHead.forward(x, proposal_feat, mask_preds, ...)    polyphonic/kernel_update_head.py:212-353
+  KernelUpdateIterHead._mask_forward / simple_test_mask_preds / simple_test
+                                                                  polyphonic/kernel_update.py:125-157, 282-401
+
+The ``nn`` layers below only HOLD parameters.  All forward arithmetic runs in libpf_decoder.so (sm_100a CUDA) through
+``DecoderEngine``; there is no PyTorch fallback -- on a non-CUDA tensor, or an unsupported configuration, the modules
+raise.  Inference only (``forward_train`` / losses are out of scope).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .decoder import DecoderEngine
+from .registry import ConfigDict, build_head, build_transformer_layer, to_config
+
+__all__ = ['KernelUpdator', 'KernelUpdateHead', 'KernelUpdateIterHead']
+
+
+def _unsupported(what):
+    raise NotImplementedError('polyphonicformer_b200: %s is not supported by the sm_100a decoder kernels '
+                              '(only the configuration family shipped in configs/_base_/models/polyphonic_former.py); '
+                              'there is no PyTorch fallback' % what)
+
+
+def _version_key(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class KernelUpdator(nn.Module):
+    """Adaptive kernel update (reference: polyphonic/funcs/kernel_updator.py:6-93)."""
+
+    def __init__(self, in_channels=256, feat_channels=64, out_channels=None, input_feat_shape=3, gate_sigmoid=True,
+                 gate_norm_act=False, activate_out=False, act_cfg=dict(type='ReLU', inplace=True),
+                 norm_cfg=dict(type='LN')):
+        super().__init__()
+        self.in_channels = in_channels
+        self.feat_channels = feat_channels
+        self.out_channels_raw = out_channels
+        self.gate_sigmoid = gate_sigmoid
+        self.gate_norm_act = gate_norm_act
+        self.activate_out = activate_out
+        if isinstance(input_feat_shape, int):
+            input_feat_shape = [input_feat_shape] * 2
+        self.input_feat_shape = input_feat_shape
+        self.act_cfg = act_cfg
+        self.norm_cfg = norm_cfg
+        self.out_channels = out_channels if out_channels else in_channels
+        if not (in_channels == feat_channels == self.out_channels == _cabi.PF_C):
+            _unsupported('KernelUpdator with in/feat/out channels != 256')
+        if not gate_sigmoid or gate_norm_act or activate_out:
+            _unsupported('KernelUpdator(gate_sigmoid=False | gate_norm_act=True | activate_out=True)')
+        if norm_cfg.get('type') != 'LN' or act_cfg.get('type') != 'ReLU':
+            _unsupported('KernelUpdator norm/activation other than LN/ReLU')
+        self.num_params_in = self.feat_channels
+        self.num_params_out = self.feat_channels
+        self.dynamic_layer = nn.Linear(in_channels, self.num_params_in + self.num_params_out)
+        self.input_layer = nn.Linear(in_channels, self.num_params_in + self.num_params_out, 1)
+        self.input_gate = nn.Linear(in_channels, feat_channels, 1)
+        self.update_gate = nn.Linear(in_channels, feat_channels, 1)
+        self.norm_in = nn.LayerNorm(feat_channels)
+        self.norm_out = nn.LayerNorm(feat_channels)
+        self.input_norm_in = nn.LayerNorm(feat_channels)
+        self.input_norm_out = nn.LayerNorm(feat_channels)
+        self.activation = nn.ReLU(inplace=True)
+        self.fc_layer = nn.Linear(feat_channels, self.out_channels, 1)
+        self.fc_norm = nn.LayerNorm(self.out_channels)
+        self._packed = None
+
+    def forward(self, update_feature, input_feature):
+        """update_feature [..., 256] (R rows), input_feature [R, 1, 256] -> [R, 1, 256]."""
+        from .decoder import PackedUpdator, run_kernel_updator
+        if not update_feature.is_cuda:
+            _unsupported('KernelUpdator.forward on a %s tensor' % update_feature.device.type)
+        key = _version_key(self)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, PackedUpdator(self.state_dict(), update_feature.device))
+        upd = update_feature.reshape(-1, self.in_channels).float().contiguous()
+        R = upd.shape[0]
+        inp = input_feature.reshape(R, -1, self.feat_channels)
+        if inp.shape[1] != 1:
+            _unsupported('conv_kernel_size != 1 (K*K=%d kernel positions)' % inp.shape[1])
+        out = run_kernel_updator(self._packed[1], upd, inp.reshape(R, self.feat_channels).float().contiguous())
+        return out.reshape(R, 1, self.out_channels)
+
+
+class _MHA(nn.Module):
+    """Parameter holder with mmcv MultiheadAttention's layout: ``attn`` = nn.MultiheadAttention."""
+
+    def __init__(self, embed_dims, num_heads, dropout):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, dropout)
+
+
+class _FFN(nn.Module):
+    """Parameter holder with mmcv FFN's layout: layers.0.0 = Linear(C, F), layers.1 = Linear(F, C)."""
+
+    def __init__(self, embed_dims, feedforward_channels, dropout):
+        super().__init__()
+        self.layers = nn.Sequential(
+            nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True), nn.Dropout(dropout)),
+            nn.Linear(feedforward_channels, embed_dims), nn.Dropout(dropout))
+
+
+class _Conv1x1(nn.Module):
+    """Parameter holder with mmcv ConvModule's layout (``conv``), bias because there is no norm."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 1)
+
+
+class _LossCfg(ConfigDict):
+    """Inference only needs ``loss_cls.use_sigmoid`` (kernel_update.py:333)."""
+
+
+class KernelUpdateHead(nn.Module):
+    """One decoder stage (reference: polyphonic/kernel_update_head.py:18-353)."""
+
+    def __init__(self, num_classes=80, num_thing_classes=80, num_stuff_classes=53, num_ffn_fcs=2, num_heads=8,
+                 num_cls_fcs=1, num_mask_fcs=3, feedforward_channels=2048, in_channels=256, out_channels=256,
+                 dropout=0.0, mask_thr=0.5, act_cfg=dict(type='ReLU', inplace=True),
+                 ffn_act_cfg=dict(type='ReLU', inplace=True), conv_kernel_size=3, feat_transform_cfg=None,
+                 hard_mask_thr=0.5, kernel_init=False, with_ffn=True, mask_out_stride=4, relative_coors=False,
+                 relative_coors_off=False, feat_gather_stride=1, mask_transform_stride=1, mask_upsample_stride=1,
+                 mask_assign_stride=4, ignore_label=255,
+                 kernel_updator_cfg=dict(type='DynamicConv', in_channels=256, feat_channels=64, out_channels=256,
+                                         input_feat_shape=1, act_cfg=dict(type='ReLU', inplace=True),
+                                         norm_cfg=dict(type='LN')),
+                 loss_rank=None, loss_mask=dict(type='CrossEntropyLoss', use_mask=True, loss_weight=1.0),
+                 loss_dice=dict(type='DiceLoss', loss_weight=3.0),
+                 loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+                 loss_depth=dict(type='DepthLoss', loss_weight=1.0, act=True, si_weight=1.0, sq_rel_weight=1.0,
+                                 abs_rel_weight=1.0),
+                 depth_act_mode='monodepth'):
+        super().__init__()
+        self.num_classes = num_classes
+        self.loss_cls = _LossCfg(to_config(loss_cls))
+        self.loss_cls.setdefault('use_sigmoid', False)
+        self.loss_mask, self.loss_dice = to_config(loss_mask), to_config(loss_dice)
+        self.loss_depth, self.loss_rank = to_config(loss_depth), to_config(loss_rank)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.mask_thr = mask_thr
+        self.fp16_enabled = False
+        self.dropout = dropout
+        self.num_heads = num_heads
+        self.hard_mask_thr = hard_mask_thr
+        self.kernel_init = kernel_init
+        self.with_ffn = with_ffn
+        self.mask_out_stride = mask_out_stride
+        self.relative_coors, self.relative_coors_off = relative_coors, relative_coors_off
+        self.conv_kernel_size = conv_kernel_size
+        self.feat_gather_stride = feat_gather_stride
+        self.mask_transform_stride = mask_transform_stride
+        self.mask_upsample_stride = mask_upsample_stride
+        self.num_thing_classes, self.num_stuff_classes = num_thing_classes, num_stuff_classes
+        self.mask_assign_stride = mask_assign_stride
+        self.ignore_label = ignore_label
+        self.feedforward_channels = feedforward_channels
+        self.depth_act_mode = depth_act_mode
+
+        if conv_kernel_size != 1:
+            _unsupported('conv_kernel_size=%d' % conv_kernel_size)
+        if in_channels != _cabi.PF_C or out_channels != _cabi.PF_C or num_heads != _cabi.PF_HEADS:
+            _unsupported('in/out channels != 256 or num_heads != 8')
+        if not with_ffn or num_ffn_fcs != 2 or num_cls_fcs != 1 or num_mask_fcs != 1:
+            _unsupported('with_ffn=False / num_ffn_fcs != 2 / num_cls_fcs != 1 / num_mask_fcs != 1')
+        if feat_gather_stride != 1 or mask_transform_stride != 1 or hard_mask_thr != 0.5 or dropout != 0.0:
+            _unsupported('feat_gather_stride / mask_transform_stride != 1, hard_mask_thr != 0.5 or dropout > 0')
+        if not self.loss_cls.use_sigmoid:
+            _unsupported('softmax classification (loss_cls.use_sigmoid=False)')
+        if num_classes > _cabi.PF_MAX_CLASSES or feedforward_channels % 256:
+            _unsupported('num_classes > 32 or feedforward_channels not a multiple of 256')
+
+        C = in_channels
+        self.attention = _MHA(C, num_heads, dropout)
+        self.attention_depth = _MHA(C, num_heads, dropout)
+        self.attention_norm = nn.LayerNorm(C)
+        self.attention_norm_depth = nn.LayerNorm(C)
+        self.kernel_update_conv = build_transformer_layer(kernel_updator_cfg)
+        self.kernel_update_conv_depth = build_transformer_layer(kernel_updator_cfg)
+        if feat_transform_cfg is not None:
+            kernel_size = feat_transform_cfg.pop('kernel_size', 1)   # the reference mutates the shared dict too (:125)
+            if kernel_size != 1 or feat_transform_cfg.get('act_cfg', None) is not None \
+                    or feat_transform_cfg.get('norm_cfg', None) is not None:
+                _unsupported('feat_transform other than a bare 1x1 conv')
+            self.feat_transform = _Conv1x1(C)
+            self.feat_depth_transform = _Conv1x1(C)
+        else:
+            self.feat_transform = None
+            self.feat_depth_transform = None
+        self.ffn = _FFN(C, feedforward_channels, dropout)
+        self.ffn_norm = nn.LayerNorm(C)
+        self.ffn_depth = _FFN(C, feedforward_channels, dropout)
+        self.ffn_norm_depth = nn.LayerNorm(C)
+        self.cls_fcs = nn.ModuleList([nn.Linear(C, C, bias=False), nn.LayerNorm(C), nn.ReLU(inplace=True)])
+        self.fc_cls = nn.Linear(C, num_classes)
+        self.mask_fcs = nn.ModuleList([nn.Linear(C, C, bias=False), nn.LayerNorm(C), nn.ReLU(inplace=True)])
+        self.depth_regs = nn.ModuleList([nn.Linear(C, C, bias=False), nn.LayerNorm(C)])
+        self.fc_mask = nn.Linear(C, out_channels)
+        self.fc_depth = nn.Linear(C, out_channels)
+        self._engine = None
+        self._feats_cache = None
+
+    def init_weights(self):
+        """kernel_update_head.py:193-210: xavier-uniform matrices, focal-loss prior on fc_cls.bias."""
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        if self.loss_cls.use_sigmoid:
+            nn.init.constant_(self.fc_cls.bias, float(-math.log((1 - 0.01) / 0.01)))
+        if self.kernel_init:
+            nn.init.normal_(self.fc_mask.weight, mean=0, std=0.01)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine(self, device):
+        key = (_version_key(self), str(device))
+        if self._engine is None or self._engine[0] != key:
+            self._engine = (key, DecoderEngine([self.state_dict()], device, self.num_classes,
+                                               self.feedforward_channels))
+        return self._engine[1]
+
+    def _prepared_feats(self, x, depth_feats):
+        key = (x.data_ptr(), x._version, depth_feats.data_ptr(), depth_feats._version, tuple(x.shape), x.dtype)
+        if self._feats_cache is None or self._feats_cache[0] != key:
+            self._feats_cache = (key, self.engine(x.device).prepare_feats(x, depth_feats))
+        return self._feats_cache[1]
+
+    def forward(self, x, proposal_feat, mask_preds, prev_cls_score=None, mask_shape=None, img_metas=None,
+                depth_preds=None, depth_proposal=None, depth_feats=None, _feats=None):
+        """Returns (cls_score [B,N,classes], new_mask_preds [B,N,H,W], obj_feat [B,N,C,1,1],
+        new_depth_preds [B,N,H,W], depth_feat_new [B,N,C,1,1]) like the reference."""
+        if not x.is_cuda:
+            _unsupported('KernelUpdateHead.forward on a %s tensor' % x.device.type)
+        B, N = proposal_feat.shape[:2]
+        C, H, W = x.shape[-3:]
+        if mask_preds.shape[-2:] != (H, W):
+            _unsupported('mask_preds at a different resolution than the feature map')
+        if mask_shape is not None and mask_shape[0] != H:
+            _unsupported('mask_shape resizing')
+        eng = self.engine(x.device)
+        feats = _feats if _feats is not None else self._prepared_feats(x, depth_feats)
+        cls, logits, obj, dep = eng.stage_forward(
+            0, feats, mask_preds.float(), proposal_feat.reshape(B, N, C).float(),
+            depth_proposal.reshape(B, N, C).float(), H, W)
+        return (cls, logits[0], obj.reshape(B, N, C, 1, 1), logits[1], dep.reshape(B, N, C, 1, 1))
+
+    # post-processing helpers used by KernelUpdateIterHead.get_panoptic live in postprocess.py ("next")
+
+
+class KernelUpdateIterHead(nn.Module):
+    """Stage loop (reference: polyphonic/kernel_update.py:13-157, 282-401)."""
+
+    def __init__(self, num_stages=6, recursive=False, assign_stages=5, stage_loss_weights=(1, 1, 1, 1, 1, 1),
+                 do_panoptic=False, proposal_feature_channel=256, merge_cls_scores=False, post_assign=False,
+                 hard_target=False, merge_joint=True, num_proposals=100, num_thing_classes=80, num_stuff_classes=53,
+                 mask_assign_stride=4, ignore_label=255, tracking=False, mask_head=None, mask_out_stride=4,
+                 train_cfg=None, test_cfg=None, **kwargs):
+        super().__init__()
+        assert mask_head is not None
+        assert len(stage_loss_weights) == num_stages
+        self.num_stages = num_stages
+        self.stage_loss_weights = stage_loss_weights
+        self.proposal_feature_channel = proposal_feature_channel
+        self.merge_cls_scores = merge_cls_scores
+        self.recursive = recursive
+        self.post_assign = post_assign
+        self.mask_out_stride = mask_out_stride
+        self.hard_target = hard_target
+        self.assign_stages = assign_stages
+        self.do_panoptic = do_panoptic
+        self.merge_joint = merge_joint
+        self.num_thing_classes, self.num_stuff_classes = num_thing_classes, num_stuff_classes
+        self.mask_assign_stride = mask_assign_stride
+        self.num_proposals = num_proposals
+        self.ignore_label = ignore_label
+        self.tracking = tracking
+        self.train_cfg = train_cfg
+        self.test_cfg = to_config(test_cfg) if test_cfg is not None else None
+        if not isinstance(mask_head, list):
+            mask_head = [mask_head for _ in range(num_stages)]
+        assert len(mask_head) == num_stages
+        self.mask_head = nn.ModuleList([build_head(h) for h in mask_head])
+        if recursive:
+            for i in range(num_stages):
+                self.mask_head[i] = self.mask_head[0]
+        self._engine = None
+
+    def init_weights(self):
+        for i in range(self.num_stages):
+            self.mask_head[i].init_weights()
+
+    @property
+    def with_mask(self):
+        return True
+
+    def engine(self, device):
+        key = (_version_key(self), str(device))
+        if self._engine is None or self._engine[0] != key:
+            h = self.mask_head[0]
+            self._engine = (key, DecoderEngine([m.state_dict() for m in self.mask_head], device, h.num_classes,
+                                               h.feedforward_channels))
+        return self._engine[1]
+
+    def _mask_forward(self, stage, x, object_feats, mask_preds, img_metas, depth_preds, depth_proposal, depth_feats):
+        """kernel_update.py:125-157 -- one stage through KernelUpdateHead.forward (all five outputs)."""
+        head = self.mask_head[stage]
+        feats = self.mask_head[0]._prepared_feats(x, depth_feats)     # cast once per frame, shared by the stages
+        cls_score, mask_preds, object_feats, depth_preds, depth_proposal = head(
+            x, object_feats, mask_preds, img_metas=img_metas, depth_preds=depth_preds,
+            depth_proposal=depth_proposal, depth_feats=depth_feats, _feats=feats)
+        if head.mask_upsample_stride > 1 and (stage == self.num_stages - 1 or self.training):
+            if head.mask_upsample_stride != 2:
+                _unsupported('mask_upsample_stride=%d' % head.mask_upsample_stride)
+            eng = head.engine(x.device)
+            scaled_mask_preds = eng.upsample2x(mask_preds)
+            scaled_depth_preds = eng.upsample2x(depth_preds)
+        else:
+            scaled_mask_preds, scaled_depth_preds = mask_preds, depth_preds
+        return dict(cls_score=cls_score, mask_preds=mask_preds, scaled_mask_preds=scaled_mask_preds,
+                    object_feats=object_feats, scaled_depth_preds=scaled_depth_preds, depth_preds=depth_preds,
+                    depth_proposal=depth_proposal)
+
+    def decode(self, x, proposal_feats, mask_preds, depth_feats, depth_proposal, all_stage_outputs=False):
+        """The fused stage loop of simple_test (kernel_update.py:316-336): one C call, dead intermediate outputs
+        skipped unless ``all_stage_outputs``.  Returns the dict of DecoderEngine.decode (cls_score has the sigmoid)."""
+        if not x.is_cuda:
+            _unsupported('KernelUpdateIterHead on a %s tensor' % x.device.type)
+        head = self.mask_head[-1]
+        if head.mask_upsample_stride not in (1, 2):
+            _unsupported('mask_upsample_stride=%d' % head.mask_upsample_stride)
+        B, N = proposal_feats.shape[:2]
+        H, W = x.shape[-2:]
+        if mask_preds.shape[-2:] != (H, W):
+            _unsupported('mask_preds at a different resolution than the feature map')
+        eng = self.engine(x.device)
+        feats = eng.prepare_feats(x, depth_feats)
+        out = eng.decode(feats, mask_preds.float(), proposal_feats.reshape(B, N, -1).float(),
+                         depth_proposal.reshape(B, N, -1).float(), H, W,
+                         upsample=head.mask_upsample_stride == 2, all_stage_outputs=all_stage_outputs)
+        C = proposal_feats.shape[2]
+        out['object_feats'] = out['object_feats'].reshape(B, N, C, 1, 1)
+        out['depth_proposal'] = out['depth_proposal'].reshape(B, N, C, 1, 1)
+        return out
+
+    def simple_test_mask_preds(self, x, proposal_feats, mask_preds, cls_score, img_metas, depth_preds=None,
+                               depth_feats=None, depth_proposal=None, imgs_whwh=None, rescale=False):
+        """kernel_update.py:356-401."""
+        out = self.decode(x, proposal_feats, mask_preds, depth_feats, depth_proposal)
+        return out['object_feats'], out['cls_score'], out['mask_preds'], out['scaled_mask_preds']
+
+    def simple_test(self, x, proposal_feats, mask_preds, cls_score, img_metas, depth_preds=None, depth_feats=None,
+                    depth_proposal=None, imgs_whwh=None, aspp_semantic=None, rescale=False, semantic_input=None):
+        """kernel_update.py:282-354: stage loop on the GPU kernels, then per-image panoptic merge (postprocess.py)."""
+        from . import postprocess
+        if not self.do_panoptic:
+            raise NotImplementedError
+        head = self.mask_head[-1]
+        out = self.decode(x, proposal_feats, mask_preds, depth_feats, depth_proposal)
+        depth_initial = depth_preds.clone().detach()
+        if self.mask_head[0].mask_upsample_stride > 1:
+            depth_initial = self.engine(x.device).upsample2x(depth_initial.float())
+            if aspp_semantic is not None:
+                aspp_semantic = self.engine(x.device).upsample2x(aspp_semantic.float())
+        results = []
+        for i in range(len(img_metas)):
+            results.append(postprocess.get_panoptic(
+                self, head, out['cls_score'][i], out['scaled_mask_preds'][i], self.test_cfg, img_metas[i],
+                depth_preds=out['scaled_depth_preds'][i], depth_init=depth_initial[i],
+                aspp_semantic=aspp_semantic[i] if aspp_semantic is not None else None))
+        return results
+
+    def forward_train(self, *args, **kwargs):
+        _unsupported('training (forward_train)')
+
+    def aug_test(self, features, proposal_list, img_metas, rescale=False):
+        raise NotImplementedError('SparseMask does not support `aug_test`')

@@ -1,0 +1,80 @@
+"""Drop-in boundary on CPU: registry names, constructor kwargs from the reference's config, state-dict layout."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import synth
+
+import polyphonicformer_b200 as pf
+
+REF_CFG = '/root/reference/configs/polyphonic_image/poly_r50_cityscapes_2x.py'
+ROI_HEAD_JSON = os.path.join(GOLDEN, 'roi_head_cfg.json')   # cfg.model.roi_head/test_cfg.rcnn dumped from the reference
+
+
+def roi_head_cfg():
+    if os.path.exists(REF_CFG):      # build container: read the reference's config file itself, unchanged
+        cfg = pf.load_config(REF_CFG)
+        roi, test = cfg.model.roi_head, cfg.model.test_cfg.rcnn
+        dumped = json.load(open(ROI_HEAD_JSON))
+        assert json.loads(json.dumps(roi)) == dumped['roi_head'], 'tests/golden/roi_head_cfg.json is stale'
+        return dict(roi, train_cfg=None, test_cfg=test)
+    d = json.load(open(ROI_HEAD_JSON))
+    return dict(d['roi_head'], train_cfg=None, test_cfg=d['test_cfg'])
+
+
+def test_registry_names():
+    for name in ('KernelUpdateHead', 'KernelUpdateIterHead'):
+        assert name in pf.MODELS
+    assert 'KernelUpdator' in pf.TRANSFORMER_LAYER
+    with pytest.raises(KeyError):
+        pf.build_head(dict(type='NoSuchHead'))
+    with pytest.raises(KeyError):
+        pf.MODELS.register_module(module=pf.KernelUpdateHead)       # duplicate without force, like mmcv
+
+
+def test_build_from_reference_config_and_state_dict_layout():
+    head = pf.build_head(roi_head_cfg())
+    assert isinstance(head, pf.KernelUpdateIterHead) and head.num_stages == 3 and len(head.mask_head) == 3
+    assert head.mask_head[0].mask_upsample_stride == 2 and head.mask_head[-1].loss_cls.use_sigmoid
+    assert head.test_cfg.max_per_img == 100 and head.num_proposals == 100
+    want = {'mask_head.%d.%s' % (s, k): tuple(v) for s in range(3) for k, v in synth.stage_state_shapes().items()}
+    got = {k: tuple(v.shape) for k, v in head.state_dict().items()}
+    assert got == want                                     # identical keys AND shapes as the reference (strict load)
+    sd = synth.synth_decoder_state(3, 0)
+    res = head.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert abs(sum(p.numel() for p in head.mask_head[0].parameters()) / 1e6 - 4.02) < 0.01
+
+
+def test_init_weights_matches_reference_recipe():
+    head = pf.build_head(roi_head_cfg())
+    head.init_weights()
+    h = head.mask_head[0]
+    assert torch.allclose(h.fc_cls.bias, torch.full_like(h.fc_cls.bias, -4.59511985013459))   # bias_init_with_prob(0.01)
+    w = h.fc_mask.weight
+    assert w.abs().max() <= (6.0 / 512) ** 0.5 + 1e-6      # xavier uniform bound for [256, 256]
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        pf.KernelUpdator(in_channels=256, feat_channels=64, out_channels=256)
+    with pytest.raises(NotImplementedError):
+        pf.build_head(dict(type='KernelUpdateHead', num_classes=19, conv_kernel_size=3, num_mask_fcs=1,
+                           kernel_updator_cfg=dict(type='KernelUpdator', in_channels=256, feat_channels=256,
+                                                   out_channels=256)))
+    head = pf.build_head(roi_head_cfg())
+    x = torch.zeros(1, 256, 4, 4)
+    with pytest.raises(NotImplementedError):              # no CPU / PyTorch fallback
+        head.decode(x, torch.zeros(1, 111, 256, 1, 1), torch.zeros(1, 111, 4, 4), x, torch.zeros(1, 111, 256, 1, 1))
+    with pytest.raises(NotImplementedError):
+        head.forward_train()
+
+
+def test_config_loader_merges_bases(tmp_path):
+    (tmp_path / 'base.py').write_text("a = dict(x=1, y=dict(z=2, w=3))\nb = [1, 2]\n")
+    (tmp_path / 'child.py').write_text("_base_ = ['./base.py']\na = dict(y=dict(z=5), q=dict(_delete_=True, k=1))\n")
+    cfg = pf.load_config(str(tmp_path / 'child.py'))
+    assert cfg.a.x == 1 and cfg.a.y.z == 5 and cfg.a.y.w == 3 and cfg.a.q == dict(k=1) and cfg.b == [1, 2]
