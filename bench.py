@@ -271,7 +271,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
     bits = torch.empty((B, words, 128), dtype=torch.int32, device=dev)
     partial = torch.empty((2 * B, S, N, C), dtype=torch.float32, device=dev)
     cntp = torch.empty((2 * B, S, N), dtype=torch.float32, device=dev)
-    kern = torch.randn((2, B, N, C), dtype=torch.float32, device=dev) * 0.1
+    kern = (torch.randn((2 * B, 2, N, C), dtype=torch.float32, device=dev) * 0.1).to(torch.bfloat16)
     kbias = torch.zeros((2, B, N), dtype=torch.float32, device=dev)
     wsb = lib.pf_update_workspace_bytes(B, N, 2048)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -290,7 +290,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
                             st)),
         ('kernel_update (12 launches)', STAGES, 'latency', 0, 0,
          lambda: _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[0].struct), _ptr(partial), _ptr(cntp), S,
-                            _ptr(obj), _ptr(dep), _ptr(obj_o), _ptr(dep_o), _ptr(cls), _ptr(kern), _ptr(kbias),
+                            _ptr(obj), _ptr(dep), _ptr(obj_o), _ptr(dep_o), _ptr(cls), None, _ptr(kern), _ptr(kbias),
                             _ptr(ws), wsb, B, N, 0, st)),
         ('mask_einsum (bits only, mask branch)', 0 if args.all_stage_outputs else STAGES - 1, 'hbm',
          B * C * HW * sx + B * N * C * 4 + B * words * 128 * 4, 2 * B * N * C * HW,

@@ -31,6 +31,8 @@
  *   partial f32   [G][S][N][256]     per-split pooled sums, G = n_branch*B units (unit = branch*B + b)
  *   cntp    f32   [G][S][N]          per-split mask pixel counts
  *   kern    f32   [G][N][256]        dynamic 1x1-conv kernels with feat_transform already folded in
+ *   kern_split bf16 [G][2][N][256]   the same kernels as bf16 hi (= bf16(x)) and lo (= bf16(x - hi)) planes: the
+ *                                    tensor-core einsum runs hi and lo as two MMAs so the product keeps ~16 mantissa bits
  *   kbias   f32   [G][N]             per-kernel logit bias produced by that fold
  *   logits  f32   [G][N][HW]         unit-major: branch 0 = new mask logits, branch 1 = new depth logits
  */
@@ -123,11 +125,14 @@ size_t pf_update_workspace_bytes(int B, int N, int ffn_channels);
  *   obj_in / dep_in    [B][N][256]   proposal_feat, depth_proposal (before the "+ proposal_feat" of :250)
  *   obj_out / dep_out  [B][N][256]   obj_feat, depth_feat_new (post FFN+LN; next stage's inputs)
  *   cls_out            [B][N][num_classes]  (sigmoid applied iff cls_sigmoid != 0, kernel_update.py:333-334)
- *   kern / kbias       [2][B][N][256], [2][B][N]   folded dynamic kernels for pf_mask_einsum */
+ *   kern (optional, may be NULL) / kern_split / kbias    folded dynamic kernels for pf_mask_einsum */
 int pf_kernel_update(const pf_stage_weights* w_host, const float* partial, const float* cntp, int S,
                      const float* obj_in, const float* dep_in, float* obj_out, float* dep_out, float* cls_out,
-                     float* kern, float* kbias, void* workspace, size_t workspace_bytes, int B, int N,
-                     int cls_sigmoid, void* stream);
+                     float* kern, uint16_t* kern_split, float* kbias, void* workspace, size_t workspace_bytes, int B,
+                     int N, int cls_sigmoid, void* stream);
+
+/* fp32 kernels [n_units][N][256] -> kern_split (for callers that produce the dynamic kernels themselves) */
+int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_units, int N, void* stream);
 
 /* KernelUpdator.forward alone (kernel_updator.py:55-93), for callers that use the module outside the stage:
  * `bw` holds the module's own (un-folded) dyn_w [512][256] / dyn_b, inp_*, gate_*, the four gate LayerNorms, fc_*,
@@ -138,8 +143,8 @@ int pf_kernel_updator(const pf_branch_weights* bw_host, const float* update_feat
 
 /* kernel_update_head.py:308-334: logits[g][n][hw] = sum_c kern[g][n][c] * feats[g][c][hw] + kbias[g][n] on tcgen05.
  * n_units = B (mask branch only) or 2B.  logits and/or bits_out may be NULL (bits are taken from units < B). */
-int pf_mask_einsum(const uint16_t* feats, const float* kern, const float* kbias, float* logits, uint32_t* bits_out,
-                   int B, int N, int HW, int HWp, int n_units, void* stream);
+int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern_split, const float* kbias, float* logits,
+                   uint32_t* bits_out, int B, int N, int HW, int HWp, int n_units, void* stream);
 
 /* kernel_update.py:133-143: F.interpolate(scale_factor=2, bilinear, align_corners=False) on `maps` [H][W] planes */
 int pf_upsample2x(const float* in, float* out, int maps, int H, int W, void* stream);

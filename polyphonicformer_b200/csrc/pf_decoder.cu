@@ -8,7 +8,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DecoderScratch {
     uint32_t* bits;
-    float *partial, *cntp, *kern, *kbias;
+    float *partial, *cntp, *kbias;
+    uint16_t* kern;
     void* update_ws;
     size_t update_ws_bytes, total;
 };
@@ -26,7 +27,7 @@ static DecoderScratch carve(void* base, int B, int N, int HW, int ffn) {
     s.bits = static_cast<uint32_t*>(take((size_t)B * words * 128 * 4));
     s.partial = static_cast<float*>(take((size_t)2 * B * S * N * PF_C * 4));
     s.cntp = static_cast<float*>(take((size_t)2 * B * S * N * 4));
-    s.kern = static_cast<float*>(take((size_t)2 * B * N * PF_C * 4));
+    s.kern = static_cast<uint16_t*>(take((size_t)2 * B * 2 * N * PF_C * 2));
     s.kbias = static_cast<float*>(take((size_t)2 * B * N * 4));
     s.update_ws_bytes = pf_update_workspace_bytes(B, N, ffn);
     s.update_ws = take(s.update_ws_bytes);
@@ -61,7 +62,7 @@ extern "C" int pf_decoder_forward(const pf_stage_weights* stages, int n_stages, 
     for (int st = 0; st < n_stages; ++st) {
         const bool last = st == n_stages - 1;
         if (int e = pf_mask_pool(feats, s.bits, s.partial, s.cntp, B, N, HW, HWp, 2, S, stream)) return e;
-        if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, s.kern, s.kbias,
+        if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, nullptr, s.kern, s.kbias,
                                      s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
             return e;
         int e;

@@ -2,8 +2,8 @@
 //     logits[g][n][hw] = sum_c kern[g][n][c] * feats[g][c][hw] + kbias[g][n]
 // as a batched [128 x 256] x [256 x HW] GEMM on the tcgen05 tensor cores.
 //
-//   A  = kern[g] (fp32 in HBM) split on chip into bf16 hi + bf16 lo (two MMAs per K step, fp32 accumulate), K-major,
-//        resident in shared memory for the whole CTA (2 x 64 KB, 128-byte swizzle);
+//   A  = kern[g] as bf16 hi + bf16 lo (the fp32 kernel split in two by its producer; two MMAs per K step, fp32
+//        accumulate), TMA-loaded once per CTA, K-major, resident in shared memory (2 x 64 KB, 128-byte swizzle);
 //   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 3-stage ring;
 //   D  = [128 lanes][64 columns] fp32 in TMEM, 4 accumulator buffers so the epilogue overlaps the next tiles;
 //   epilogue: tcgen05.ld -> + bias -> fp32 logits (128-bit stores) and/or the packed sign bits consumed by the next
@@ -27,7 +27,6 @@ constexpr int E_THREADS = 192;
 constexpr int E_SMEM = 2 * E_A_BYTES + E_STAGES * E_B_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 
 struct EinsumParams {
-    const float* kern;   // [G][N][256]
     const float* kbias;  // [G][N]
     float* logits;       // [G][N][HW] or null
     uint32_t* bits;      // [B][WORDS][128] or null
@@ -36,7 +35,8 @@ struct EinsumParams {
 };
 
 __global__ void __launch_bounds__(E_THREADS, 1)
-einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams p) {
+einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_kern,
+              const EinsumParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA_hi = smem;
@@ -47,7 +47,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams
     uint64_t* empty = bars + E_STAGES;
     uint64_t* tfull = bars + 2 * E_STAGES;
     uint64_t* tempty = bars + 2 * E_STAGES + E_ACC;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * E_STAGES + 2 * E_ACC);
+    uint64_t* abar = bars + 2 * E_STAGES + 2 * E_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * E_STAGES + 2 * E_ACC + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int unit = blockIdx.x / p.ctas_per_unit;
@@ -58,6 +59,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
+        tma_prefetch_desc(&tmap_kern);
+        mbar_init(abar, 1);
         for (int i = 0; i < E_STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
@@ -70,33 +73,6 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams
     }
     if (warp == 1) tmem_alloc<E_TMEM_COLS>(tmem_slot);
 
-    // ---- A operand: fp32 kernels -> bf16 hi/lo, K-major 128B-swizzled, 4 K-blocks of [128 rows][64 k]
-    {
-        const float* kg = p.kern + (size_t)unit * p.N * E_C;
-        for (int item = threadIdx.x; item < 128 * 32; item += E_THREADS) {
-            const int r = item >> 5, c8 = item & 31;  // row, 8-element chunk along K
-            float v[8];
-            if (r < p.N) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(kg + (size_t)r * E_C + c8 * 8));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(kg + (size_t)r * E_C + c8 * 8 + 4));
-                v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-            }
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float h0 = bf16_round(v[2 * i]), h1 = bf16_round(v[2 * i + 1]);
-                hi[i] = pack_bf16x2(h0, h1);
-                lo[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
-            }
-            const uint32_t off = (uint32_t)(c8 >> 3) * (128 * 128) + sw128_offset(r, c8 & 7);
-            *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async_smem();
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -105,6 +81,14 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            // A operand: [hi | lo] x 4 K-blocks of [128 rows][64 k]; rows >= N are out of bounds -> zero filled
+            mbar_arrive_expect_tx(abar, 2 * E_A_BYTES);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                    tma_load_3d(sA_hi + h * E_A_BYTES + kb * (128 * 128), &tmap_kern, abar, kb * 64, 0, unit * 2 + h,
+                                kEvictLast);
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % E_STAGES;
                 const uint32_t ph = (i / E_STAGES) & 1;
@@ -119,6 +103,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(128, E_BHW, /*a_mn=*/0, /*b_mn=*/1);
             const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
+            mbar_wait(abar, 0);
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % E_STAGES, a = i % E_ACC;
                 mbar_wait(&tempty[a], ((i / E_ACC) & 1) ^ 1);
@@ -200,7 +185,35 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const EinsumParams
 
 }  // namespace pf
 
-extern "C" int pf_mask_einsum(const uint16_t* feats, const float* kern, const float* kbias, float* logits,
+// fp32 kernels [G][N][256] -> bf16 hi / lo [G][2][N][256] (hi = bf16(x), lo = bf16(x - hi))
+namespace pf {
+__global__ void split_kernels_kernel(const float* __restrict__ kern, uint16_t* __restrict__ out, int N, int total4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4
+    if (i >= total4) return;
+    const int per_unit4 = N * E_C / 4;
+    const int unit = i / per_unit4, r = i % per_unit4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(kern) + i);
+    const float h0 = bf16_round(v.x), h1 = bf16_round(v.y), h2 = bf16_round(v.z), h3 = bf16_round(v.w);
+    uint2* dst_hi = reinterpret_cast<uint2*>(out) + (size_t)(unit * 2) * per_unit4 + r;
+    uint2* dst_lo = dst_hi + per_unit4;
+    *dst_hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    *dst_lo = make_uint2(pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
+}
+}  // namespace pf
+
+extern "C" int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_units, int N, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(kern && kern_split && n_units > 0 && N > 0 && N <= PF_MAX_N, PF_ERR_ARG, "pf_split_kernels: bad argument");
+    PF_REQUIRE(((reinterpret_cast<uintptr_t>(kern) | reinterpret_cast<uintptr_t>(kern_split)) & 15) == 0, PF_ERR_ALIGN,
+               "pf_split_kernels: pointers must be 16-byte aligned");
+    const int total4 = n_units * N * E_C / 4;
+    split_kernels_kernel<<<(total4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(kern, kern_split, N, total4);
+    PF_CHECK_LAUNCH("split_kernels_kernel");
+    return PF_OK;
+}
+
+extern "C" int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
                               uint32_t* bits_out, int B, int N, int HW, int HWp, int n_units, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
@@ -209,14 +222,17 @@ extern "C" int pf_mask_einsum(const uint16_t* feats, const float* kern, const fl
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_mask_einsum: bad shape B=%d N=%d HW=%d", B, N, HW);
     PF_REQUIRE(n_units == B || n_units == 2 * B, PF_ERR_ARG, "pf_mask_einsum: n_units must be B or 2B");
     PF_REQUIRE(HWp >= HW && HWp % 8 == 0, PF_ERR_ALIGN, "pf_mask_einsum: HWp=%d must be >= HW and a multiple of 8", HWp);
-    PF_REQUIRE((reinterpret_cast<uintptr_t>(kern) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: kern not 16-byte aligned");
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(kern) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: kern_split not 16-byte aligned");
     PF_REQUIRE(!logits || (reinterpret_cast<uintptr_t>(logits) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: logits not 16-byte aligned");
 
     CUtensorMap tmap;
     if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_units * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
 
+    CUtensorMap tmap_k;
+    if (int e = make_tmap_bf16_3d(&tmap_k, kern, (uint64_t)n_units * 2, (uint64_t)N, E_C, 128, 64)) return e;
+
     EinsumParams p;
-    p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
+    p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
     p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
     int cpu = num_sms() / n_units;
@@ -226,7 +242,7 @@ extern "C" int pf_mask_einsum(const uint16_t* feats, const float* kern, const fl
 
     cudaError_t ea = cudaFuncSetAttribute(einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
-    einsum_kernel<<<n_units * cpu, E_THREADS, E_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, p);
+    einsum_kernel<<<n_units * cpu, E_THREADS, E_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, tmap_k, p);
     PF_CHECK_LAUNCH("einsum_kernel");
     return PF_OK;
 }

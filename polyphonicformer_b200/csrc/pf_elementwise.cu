@@ -29,28 +29,41 @@ __global__ void cast_feats_kernel(const float* __restrict__ x, const float* __re
 // ---------------------------------------------------------------------------------------------------------------
 // mask logits fp32 [B][N][HW] -> bits u32 [B][WORDS][128]: one block per (b, group of 8 words); warp w ballots the
 // 32 pixels of a word for rows n = w, w+8, ...  (kernel_update_head.py:236-238: sigmoid(x) > 0.5  <=>  x > 0)
-constexpr int BIN_WORDS = 8;
-__global__ void __launch_bounds__(256) binarise_kernel(const float* __restrict__ logits, uint32_t* __restrict__ bits,
-                                                       int N, int HW, int words) {
+constexpr int BIN_WORDS = 4;
+constexpr int BIN_WARPS = 16;
+__global__ void __launch_bounds__(BIN_WARPS * 32) binarise_kernel(const float* __restrict__ logits,
+                                                                  uint32_t* __restrict__ bits, int N, int HW, int words) {
     __shared__ uint32_t s_bits[BIN_WORDS][128];
     const int b = blockIdx.y;
     const int w0 = blockIdx.x * BIN_WORDS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < BIN_WORDS * 128; i += 256) (&s_bits[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < BIN_WORDS * 128; i += BIN_WARPS * 32) (&s_bits[0][0])[i] = 0u;
     __syncthreads();
     const float* base = logits + (size_t)b * N * HW;
-    for (int n = warp; n < N; n += 8) {
-        const float* row = base + (size_t)n * HW;
+    // two rows x four words per iteration: 8 independent 128-byte loads in flight per warp
+    for (int n = warp; n < N; n += 2 * BIN_WARPS) {
+        float v[2][BIN_WORDS];
 #pragma unroll
-        for (int k = 0; k < BIN_WORDS; ++k) {
-            const int hw = (w0 + k) * 32 + lane;
-            const float v = (hw < HW) ? __ldcs(row + hw) : 0.f;
-            const uint32_t m = __ballot_sync(0xffffffffu, v > 0.f);
-            if (lane == 0) s_bits[k][n] = m;
+        for (int r = 0; r < 2; ++r) {
+            const int nn = n + r * BIN_WARPS;
+#pragma unroll
+            for (int k = 0; k < BIN_WORDS; ++k) {
+                const int hw = (w0 + k) * 32 + lane;
+                v[r][k] = (nn < N && hw < HW) ? __ldcs(base + (size_t)nn * HW + hw) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int nn = n + r * BIN_WARPS;
+#pragma unroll
+            for (int k = 0; k < BIN_WORDS; ++k) {
+                const uint32_t m = __ballot_sync(0xffffffffu, v[r][k] > 0.f);
+                if (lane == 0 && nn < N) s_bits[k][nn] = m;
+            }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < BIN_WORDS * 128; i += 256) {
+    for (int i = threadIdx.x; i < BIN_WORDS * 128; i += BIN_WARPS * 32) {
         const int k = i >> 7, n = i & 127;
         if (w0 + k < words) bits[((size_t)b * words + w0 + k) * 128 + n] = s_bits[k][n];
     }
@@ -141,7 +154,7 @@ extern "C" int pf_binarise(const float* mask_logits, uint32_t* bits, int B, int 
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_binarise: bad shape B=%d N=%d HW=%d", B, N, HW);
     const int words = (HW + 31) / 32;
     dim3 grid((words + BIN_WORDS - 1) / BIN_WORDS, B);
-    binarise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask_logits, bits, N, HW, words);
+    binarise_kernel<<<grid, BIN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(mask_logits, bits, N, HW, words);
     PF_CHECK_LAUNCH("binarise_kernel");
     return PF_OK;
 }

@@ -20,6 +20,10 @@ void reset_launch_count();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                       uint32_t box_rows, uint32_t box_cols);
 
+// 3-D bf16 tensor [d2][d1][d0] (dense); box = [1][box1][box0]; rows >= d1 read as zero.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
+                      uint32_t box0);
+
 #define PF_CHECK_LAUNCH(name)                                                          \
     do {                                                                               \
         cudaError_t e__ = cudaGetLastError();                                          \

@@ -216,7 +216,7 @@ class DecoderEngine:
         bits = torch.empty((B, words, 128), dtype=torch.int32, device=self.device)
         partial = torch.empty((2 * B, S, N, PF_C), dtype=torch.float32, device=self.device)
         cntp = torch.empty((2 * B, S, N), dtype=torch.float32, device=self.device)
-        kern = torch.empty((2, B, N, PF_C), dtype=torch.float32, device=self.device)
+        ksplit = torch.empty((2 * B, 2, N, PF_C), dtype=torch.bfloat16, device=self.device)
         kbias = torch.empty((2, B, N), dtype=torch.float32, device=self.device)
         obj_out, dep_out = torch.empty_like(obj), torch.empty_like(dep)
         cls = torch.empty((B, N, self.num_classes), dtype=torch.float32, device=self.device)
@@ -226,9 +226,9 @@ class DecoderEngine:
         _cabi.call('pf_binarise', _ptr(mask_logits), _ptr(bits), B, N, HW, st)
         _cabi.call('pf_mask_pool', _ptr(feats), _ptr(bits), _ptr(partial), _ptr(cntp), B, N, HW, HWp, 2, S, st)
         _cabi.call('pf_kernel_update', ctypes.byref(self.stages[stage].struct), _ptr(partial), _ptr(cntp), S,
-                   _ptr(obj), _ptr(dep), _ptr(obj_out), _ptr(dep_out), _ptr(cls), _ptr(kern), _ptr(kbias),
+                   _ptr(obj), _ptr(dep), _ptr(obj_out), _ptr(dep_out), _ptr(cls), None, _ptr(ksplit), _ptr(kbias),
                    _ptr(ws), ws_bytes, B, N, 1 if cls_sigmoid else 0, st)
-        _cabi.call('pf_mask_einsum', _ptr(feats), _ptr(kern), _ptr(kbias), _ptr(logits), None, B, N, HW, HWp,
+        _cabi.call('pf_mask_einsum', _ptr(feats), _ptr(ksplit), _ptr(kbias), _ptr(logits), None, B, N, HW, HWp,
                    2 * B, st)
         return cls, logits, obj_out, dep_out
 

@@ -113,7 +113,13 @@ def test_mask_einsum(dev, B, N, HW, units):
     words = (HW + 31) // 32
     logits = torch.full((units, N, HW), float('nan'), device=dev)
     bits = torch.full((B, words, 128), -1, dtype=torch.int32, device=dev)
-    cabi.call('pf_mask_einsum', P(feats), P(kern), P(kbias), P(logits), P(bits), B, N, HW, HWp, units, S())
+    ksplit = torch.full((2 * B, 2, N, 256), float('nan'), dtype=torch.bfloat16, device=dev)
+    cabi.call('pf_split_kernels', P(kern), P(ksplit), 2 * B, N, S())
+    torch.cuda.synchronize()
+    hi = kern.reshape(2 * B, N, 256).to(torch.bfloat16)
+    assert torch.equal(ksplit[:, 0], hi)
+    assert torch.equal(ksplit[:, 1], (kern.reshape(2 * B, N, 256) - hi.float()).to(torch.bfloat16))
+    cabi.call('pf_mask_einsum', P(feats), P(ksplit), P(kbias), P(logits), P(bits), B, N, HW, HWp, units, S())
     torch.cuda.synchronize()
     f = feats[:, :, :, :HW].double().reshape(2 * B, 256, HW)[:units]
     ref = torch.einsum('gnc,gch->gnh', kern.double().reshape(2 * B, N, 256)[:units], f) \
@@ -124,7 +130,7 @@ def test_mask_einsum(dev, B, N, HW, units):
     assert torch.equal(bits, pack_bits_ref(logits[:B] > 0, N, HW))   # bits are the sign of the emitted logits
     # bits-only mode must produce the same bits
     bits2 = torch.full_like(bits, -1)
-    cabi.call('pf_mask_einsum', P(feats), P(kern), P(kbias), None, P(bits2), B, N, HW, HWp, B, S())
+    cabi.call('pf_mask_einsum', P(feats), P(ksplit), P(kbias), None, P(bits2), B, N, HW, HWp, B, S())
     torch.cuda.synchronize()
     assert torch.equal(bits2, bits)
 
