@@ -158,18 +158,33 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
     if (warp == 1) tmem_dealloc<P_TMEM_COLS>(tmem_base);
 }
 
-// sum over splits: pooled[g][n][c], count[b][n]
-__global__ void pool_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ cntp,
-                                   float* __restrict__ pooled, float* __restrict__ count, int G, int B, int N, int S) {
-    const int row = blockIdx.x;  // g * N + n
+// sum over splits in a fixed order: pooled[g][n][c], count[b][n].  64 threads x float4 per row, 4 rows per block.
+__global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restrict__ partial,
+                                                          const float* __restrict__ cntp, float* __restrict__ pooled,
+                                                          float* __restrict__ count, int G, int B, int N, int S) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 6);  // g * N + n
+    if (row >= G * N) return;
     const int g = row / N, n = row % N;
-    const int c = threadIdx.x;
-    float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += partial[(((size_t)g * S + s) * N + n) * P_C + c];
-    pooled[(size_t)row * P_C + c] = acc;
-    if (c == 0 && g < B && count) {
+    const int c4 = threadIdx.x & 63;
+    const float4* src = reinterpret_cast<const float4*>(partial + (((size_t)g * S) * N + n) * P_C) + c4;
+    const size_t stride4 = (size_t)N * P_C / 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 6 <= S; s += 6) {
+        float4 v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = __ldg(src + (size_t)(s + i) * stride4);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc.x += v[i].x, acc.y += v[i].y, acc.z += v[i].z, acc.w += v[i].w;
+    }
+    for (; s < S; ++s) {
+        const float4 v = __ldg(src + (size_t)s * stride4);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(pooled + (size_t)row * P_C)[c4] = acc;
+    if (c4 == 0 && g < B && count) {
         float k = 0.f;
-        for (int s = 0; s < S; ++s) k += cntp[((size_t)g * S + s) * N + n];
+        for (int s2 = 0; s2 < S; ++s2) k += cntp[((size_t)g * S + s2) * N + n];
         count[g * N + n] = k;
     }
 }
@@ -216,7 +231,7 @@ extern "C" int pf_pool_reduce(const float* partial, const float* cntp, float* po
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(partial && cntp && pooled, PF_ERR_ARG, "pf_pool_reduce: null pointer");
-    pool_reduce_kernel<<<n_branch * B * N, P_C, 0, static_cast<cudaStream_t>(stream)>>>(partial, cntp, pooled, count,
+    pool_reduce_kernel<<<(n_branch * B * N + 3) / 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, cntp, pooled, count,
                                                                                        n_branch * B, B, N, S);
     PF_CHECK_LAUNCH("pool_reduce_kernel");
     return PF_OK;

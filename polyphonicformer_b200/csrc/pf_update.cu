@@ -210,11 +210,13 @@ __global__ void __launch_bounds__(V_THREADS, 2) rowgemm_kernel(const GemmArgs ar
     }
     if (tid < V_TM) s_cnt[tid] = (g.count && m0 + tid < args.R) ? __ldg(g.count + m0 + tid) : 0.f;
 
-    float acc[4][4];
+    // three independent accumulator sets (hi*hi, lo*hi, hi*lo): 12 independent mma chains per warp hide the
+    // mma.sync latency; they are summed once at the end (small terms first).
+    float acc[4][4], acc_lh[4][4], acc_hl[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.f;
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = acc_lh[i][jj] = acc_hl[i][jj] = 0.f;
 
     // ---------------- main loop: 3xTF32 (hi*hi + lo*hi + hi*lo), operands split at fragment-load time.
     // physical k = 16*k16 + 4*tq + {0,1 | 2,3} feeds the logical mma slots (tq, tq+4) of two k8 steps.
@@ -243,15 +245,19 @@ __global__ void __launch_bounds__(V_THREADS, 2) rowgemm_kernel(const GemmArgs ar
                 uint32_t bh[4], bl[4];
                 split_tf32(w.x, bh[0], bl[0]), split_tf32(w.y, bh[1], bl[1]);
                 split_tf32(w.z, bh[2], bl[2]), split_tf32(w.w, bh[3], bl[3]);
-                mma_tf32(acc[nt], Al_a, bh[0], bh[1]);
-                mma_tf32(acc[nt], Ah_a, bl[0], bl[1]);
+                mma_tf32(acc_lh[nt], Al_a, bh[0], bh[1]);
+                mma_tf32(acc_hl[nt], Ah_a, bl[0], bl[1]);
                 mma_tf32(acc[nt], Ah_a, bh[0], bh[1]);
-                mma_tf32(acc[nt], Al_b, bh[2], bh[3]);
-                mma_tf32(acc[nt], Ah_b, bl[2], bl[3]);
+                mma_tf32(acc_lh[nt], Al_b, bh[2], bh[3]);
+                mma_tf32(acc_hl[nt], Ah_b, bl[2], bl[3]);
                 mma_tf32(acc[nt], Ah_b, bh[2], bh[3]);
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] += acc_lh[i][jj] + acc_hl[i][jj];
 
     // ---------------- optional per-row dot of the input tile (the folded logit bias of the dynamic kernels)
     if (g.rowdot_out && tile == 0) {
@@ -354,24 +360,30 @@ __global__ void __launch_bounds__(V_THREADS, 2) rowgemm_kernel(const GemmArgs ar
 // Inter-kernel self-attention of one (branch, image, head): softmax(q k^T / sqrt(32)) v over the N kernels of the
 // image (mmcv MultiheadAttention -> nn.MultiheadAttention, seq-first; kernel_update_head.py:259-260).
 // qkv [R][768] = [q | k | v]; out [R][256] (heads concatenated), before out_proj.
-// 4 threads per query, each owning every 4th key: two-pass softmax (scores kept in registers), quad reduction.
-constexpr int ATT_KPT = (PF_MAX_N + 3) / 4;   // keys per thread
-__global__ void __launch_bounds__(512) attention_kernel(const float* __restrict__ qkv0, const float* __restrict__ qkv1,
-                                                        float* __restrict__ out0, float* __restrict__ out1, int N) {
-    __shared__ float s_k[PF_MAX_N][33];
-    __shared__ float s_v[PF_MAX_N][33];
-    const int h = blockIdx.x, b = blockIdx.y;
+// 4 threads per query; keys are dealt to the 4 threads in blocks of 4 consecutive keys so that K^T rows and V rows
+// are read as float4 (4 FMAs per shared-memory load).  Two-pass softmax with the scores kept in registers, quad
+// reduction by shuffles.  Two CTAs per (branch, image, head) split the queries.
+constexpr int ATT_NB = PF_MAX_N / 16;   // key blocks of 4 per thread (8 -> 32 keys per thread, 128 per quad)
+constexpr int ATT_QPC = PF_MAX_N / 2;   // queries per CTA
+__global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __restrict__ qkv0,
+                                                                const float* __restrict__ qkv1,
+                                                                float* __restrict__ out0, float* __restrict__ out1,
+                                                                int N) {
+    __shared__ __align__(16) float s_kt[32][PF_MAX_N + 4];   // K transposed: [d][key]
+    __shared__ __align__(16) float s_v[PF_MAX_N][36];
+    const int h = blockIdx.x >> 1, half = blockIdx.x & 1, b = blockIdx.y;
     pdl_wait();
     pdl_launch_dependents();
     const float* qkv = (blockIdx.z == 0 ? qkv0 : qkv1) + (size_t)b * N * 768;
     float* out = (blockIdx.z == 0 ? out0 : out1) + (size_t)b * N * 256;
-    for (int i = threadIdx.x; i < N * 32; i += 512) {
+    for (int i = threadIdx.x; i < PF_MAX_N * 32; i += ATT_QPC * 4) {
         const int n = i >> 5, d = i & 31;
-        s_k[n][d] = qkv[(size_t)n * 768 + 256 + h * 32 + d];
-        s_v[n][d] = qkv[(size_t)n * 768 + 512 + h * 32 + d];
+        const bool ok = n < N;
+        s_kt[d][n] = ok ? qkv[(size_t)n * 768 + 256 + h * 32 + d] : 0.f;
+        s_v[n][d] = ok ? qkv[(size_t)n * 768 + 512 + h * 32 + d] : 0.f;
     }
     __syncthreads();
-    const int n = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int n = half * ATT_QPC + (threadIdx.x >> 2), part = threadIdx.x & 3;
     const int nq = n < N ? n : N - 1;   // keep whole quads alive for the shuffles
     float q[32];
     const float scale = 0.17677669529663687f;  // 1/sqrt(32), applied to q before q k^T as torch does
@@ -380,19 +392,20 @@ __global__ void __launch_bounds__(512) attention_kernel(const float* __restrict_
         const float4 t = *reinterpret_cast<const float4*>(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
         q[d4 * 4] = t.x * scale, q[d4 * 4 + 1] = t.y * scale, q[d4 * 4 + 2] = t.z * scale, q[d4 * 4 + 3] = t.w * scale;
     }
-    float sc[ATT_KPT];
+    float sc[ATT_NB][4];
     float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < ATT_KPT; ++i) {
-        const int j = part + 4 * i;
-        float s = -INFINITY;
-        if (j < N) {
-            s = 0.f;
+    for (int i = 0; i < ATT_NB; ++i) {
+        const int j0 = 4 * (part + 4 * i);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int d = 0; d < 32; ++d) s += q[d] * s_k[j][d];
+        for (int d = 0; d < 32; ++d) {
+            const float4 kk = *reinterpret_cast<const float4*>(&s_kt[d][j0]);
+            a.x += q[d] * kk.x, a.y += q[d] * kk.y, a.z += q[d] * kk.z, a.w += q[d] * kk.w;
         }
-        sc[i] = s;
-        mx = fmaxf(mx, s);
+        sc[i][0] = j0 < N ? a.x : -INFINITY, sc[i][1] = j0 + 1 < N ? a.y : -INFINITY;
+        sc[i][2] = j0 + 2 < N ? a.z : -INFINITY, sc[i][3] = j0 + 3 < N ? a.w : -INFINITY;
+        mx = fmaxf(fmaxf(mx, fmaxf(sc[i][0], sc[i][1])), fmaxf(sc[i][2], sc[i][3]));
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
@@ -400,13 +413,17 @@ __global__ void __launch_bounds__(512) attention_kernel(const float* __restrict_
 #pragma unroll
     for (int d = 0; d < 32; ++d) o[d] = 0.f;
 #pragma unroll
-    for (int i = 0; i < ATT_KPT; ++i) {
-        const int j = part + 4 * i;
-        if (j < N) {
-            const float pj = expf(sc[i] - mx);
+    for (int i = 0; i < ATT_NB; ++i) {
+        const int j0 = 4 * (part + 4 * i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float pj = expf(sc[i][e] - mx);   // exp(-inf) = 0 for padded keys (their V rows are zero)
             den += pj;
 #pragma unroll
-            for (int d = 0; d < 32; ++d) o[d] += pj * s_v[j][d];
+            for (int d4 = 0; d4 < 8; ++d4) {
+                const float4 vv = *reinterpret_cast<const float4*>(&s_v[j0 + e][d4 * 4]);
+                o[d4 * 4] += pj * vv.x, o[d4 * 4 + 1] += pj * vv.y, o[d4 * 4 + 2] += pj * vv.z, o[d4 * 4 + 3] += pj * vv.w;
+            }
         }
     }
     den += __shfl_xor_sync(0xffffffffu, den, 1);
@@ -470,8 +487,8 @@ static int launch_attention(const float* q0, const float* q1, float* o0, float* 
                             cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(PF_HEADS, B, nbranch);
-    cfg.blockDim = dim3(512);
+    cfg.gridDim = dim3(PF_HEADS * 2, B, nbranch);
+    cfg.blockDim = dim3(ATT_QPC * 4);
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
