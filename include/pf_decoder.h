@@ -67,36 +67,51 @@ typedef enum pf_status {
 int pf_version(void);
 const char* pf_last_error_string(void);
 
-/* ---- per-branch parameters of one KernelUpdateHead, after host-side packing (decoder.py: pack_stage_weights).
- * All matrices are row-major [out][in] like nn.Linear.weight.  Folded ones are marked (*):
- * feat_transform W_t,b_t (kernel_update_head.py:224-226) never touches the feature map; instead
+/* ---- parameters of one KernelUpdateHead after host-side packing (decoder.py: PackedStage).
+ * Weight MATRICES live in two bf16 "stacks" (row-major, one matrix after the other):
+ *   wstack256  [rows][256]   every matrix with 256 input features,
+ *   wstack_ffn [rows][FFN]   ffn.layers.1 (256 x FFN),
+ * each matrix [out][in] (nn.Linear layout) stored as a hi plane (bf16(w)) followed by a lo plane (bf16(w - hi)), out
+ * padded to a multiple of 128 rows.  The tensor-core GEMMs run hi and lo as separate MMAs (fp32-level accuracy).  The
+ * struct holds the ROW of the hi plane; the lo plane starts `padded out` rows later.  Vectors stay fp32.
+ * feat_transform W_t,b_t (kernel_update_head.py:224-226) never touches the feature map; it is folded (in fp64):
  *   dyn_w  = dynamic_layer.weight @ W_t,  dyn_cb = dynamic_layer.weight @ b_t   (pooled' = pooled W_t^T + count b_t)
  *   kern_w = W_t^T @ fc_{mask,depth}.weight, kern_b = W_t^T @ fc.bias, kb_w = fc.weight^T @ b_t, kb_b = fc.bias . b_t
  */
 typedef struct pf_branch_weights {
-    const float *dyn_w, *dyn_b, *dyn_cb;            /* (*) [512][256], [512], [512]; kernel_updator.py:58 */
-    const float *inp_w, *inp_b;                     /* input_layer [512][256]; :64 */
-    const float *gate_w, *gate_b;                   /* [input_gate; update_gate] [512][256]; :73-74 */
-    const float *ln_input_norm_in, *ln_norm_in;     /* each [2][256] = gamma, beta; :75-77 */
-    const float *ln_norm_out, *ln_input_norm_out;   /* :78-79 */
-    const float *fc_w, *fc_b, *ln_fc_norm;          /* fc_layer [256][256]; :89-91 */
-    const float *qkv_w, *qkv_b;                     /* attn.in_proj [768][256]; kernel_update_head.py:259-260 */
-    const float *out_w, *out_b, *ln_attn;           /* attn.out_proj, attention_norm */
-    const float *ffn1_w, *ffn1_b;                   /* ffn.layers.0.0 [FFN][256]; :271-272 */
-    const float *ffn2_w, *ffn2_b, *ln_ffn;          /* ffn.layers.1 [256][FFN], ffn_norm */
-    const float *head_w;                            /* mask branch: [cls_fcs.0; mask_fcs.0] [512][256]; depth: depth_regs.0 [256][256]; :278-283 */
-    const float *ln_head_a, *ln_head_b;             /* mask: cls_fcs.1, mask_fcs.1; depth: depth_regs.1, unused */
-    const float *cls_w, *cls_b;                     /* mask branch only: fc_cls padded to [32][256], [32]; :285 */
-    const float *kern_w, *kern_b;                   /* (*) [256][256], [256]; :287-288 with the fold */
-    const float *kb_w;                              /* (*) [256] */
-    float kb_b;                                     /* (*) scalar */
+    int dyn_w;    /* (*) [512][256]  dynamic_layer, folded; kernel_updator.py:58 */
+    int inp_w;    /*     [512][256]  input_layer; :64 */
+    int gate_w;   /*     [512][256]  [input_gate; update_gate]; :73-74 */
+    int fc_w;     /*     [256][256]  fc_layer; :89 */
+    int qkv_w;    /*     [768][256]  attn.in_proj; kernel_update_head.py:259-260 */
+    int out_w;    /*     [256][256]  attn.out_proj */
+    int ffn1_w;   /*     [FFN][256]  ffn.layers.0.0; :271-272 */
+    int head_w;   /*     mask: [cls_fcs.0; mask_fcs.0] [512][256]; depth: depth_regs.0 [256][256]; :278-283 */
+    int cls_w;    /*     mask branch only: fc_cls padded to [128][256]; :285 */
+    int kern_w;   /* (*) [256][256]  fc_mask / fc_depth with the fold; :287-288 */
+    int ffn2_w;   /*     [256][FFN]  ffn.layers.1 -- row in wstack_ffn */
     int head_relu;                                  /* 1 for the mask branch (mask_fcs has ReLU), 0 for depth_regs */
+    const float *dyn_b, *dyn_cb;                    /* [512], (*) [512] */
+    const float *inp_b, *gate_b;                    /* [512], [512] */
+    const float *ln_input_norm_in, *ln_norm_in;     /* each [2][256] = gamma, beta; kernel_updator.py:75-77 */
+    const float *ln_norm_out, *ln_input_norm_out;   /* :78-79 */
+    const float *fc_b, *ln_fc_norm;                 /* :89-91 */
+    const float *qkv_b, *out_b, *ln_attn;           /* attention_norm */
+    const float *ffn1_b, *ffn2_b, *ln_ffn;          /* ffn_norm */
+    const float *ln_head_a, *ln_head_b;             /* mask: cls_fcs.1, mask_fcs.1; depth: depth_regs.1, unused */
+    const float *cls_b;                             /* [32] (padded) */
+    const float *kern_b, *kb_w;                     /* (*) [256], (*) [256] */
+    float kb_b;                                     /* (*) scalar */
+    int reserved;
 } pf_branch_weights;
 
 typedef struct pf_stage_weights {
-    pf_branch_weights br[2]; /* 0 = mask branch, 1 = depth branch */
-    int ffn_channels;        /* 2048 */
-    int num_classes;         /* 19 */
+    pf_branch_weights br[2];   /* 0 = mask branch, 1 = depth branch */
+    const uint16_t* wstack256; /* bf16 [wstack256_rows][256] */
+    const uint16_t* wstack_ffn;/* bf16 [wstack_ffn_rows][ffn_channels] */
+    int wstack256_rows, wstack_ffn_rows;
+    int ffn_channels;          /* 2048 */
+    int num_classes;           /* 19 */
 } pf_stage_weights;
 
 /* fp32 NCHW feature maps -> the bf16 [2][B][256][HWp] layout.  Replaces nothing in the reference (storage cast). */
@@ -135,10 +150,10 @@ int pf_kernel_update(const pf_stage_weights* w_host, const float* partial, const
 int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_units, int N, void* stream);
 
 /* KernelUpdator.forward alone (kernel_updator.py:55-93), for callers that use the module outside the stage:
- * `bw` holds the module's own (un-folded) dyn_w [512][256] / dyn_b, inp_*, gate_*, the four gate LayerNorms, fc_*,
- * ln_fc_norm; other fields are ignored.  update_feature, input_feature, out: [R][256]. */
+ * `w->br[0]` holds the module's own (un-folded) dyn_w / dyn_b, inp_*, gate_*, the four gate LayerNorms, fc_*,
+ * ln_fc_norm (rows in w->wstack256); other fields are ignored.  update_feature, input_feature, out: [R][256]. */
 size_t pf_updator_workspace_bytes(int R);
-int pf_kernel_updator(const pf_branch_weights* bw_host, const float* update_feature, const float* input_feature,
+int pf_kernel_updator(const pf_stage_weights* w_host, const float* update_feature, const float* input_feature,
                       float* out, void* workspace, size_t workspace_bytes, int R, void* stream);
 
 /* kernel_update_head.py:308-334: logits[g][n][hw] = sum_c kern[g][n][c] * feats[g][c][hw] + kbias[g][n] on tcgen05.

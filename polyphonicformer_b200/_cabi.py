@@ -31,16 +31,18 @@ _fp = POINTER(c_float)
 
 class BranchWeights(Structure):
     """struct pf_branch_weights -- field order must match include/pf_decoder.h."""
-    _PTRS = ['dyn_w', 'dyn_b', 'dyn_cb', 'inp_w', 'inp_b', 'gate_w', 'gate_b', 'ln_input_norm_in', 'ln_norm_in',
-             'ln_norm_out', 'ln_input_norm_out', 'fc_w', 'fc_b', 'ln_fc_norm', 'qkv_w', 'qkv_b', 'out_w', 'out_b',
-             'ln_attn', 'ffn1_w', 'ffn1_b', 'ffn2_w', 'ffn2_b', 'ln_ffn', 'head_w', 'ln_head_a', 'ln_head_b',
-             'cls_w', 'cls_b', 'kern_w', 'kern_b', 'kb_w']
-    _fields_ = [(n, c_void_p) for n in _PTRS] + [('kb_b', c_float), ('head_relu', c_int)]
+    _ROWS = ['dyn_w', 'inp_w', 'gate_w', 'fc_w', 'qkv_w', 'out_w', 'ffn1_w', 'head_w', 'cls_w', 'kern_w', 'ffn2_w']
+    _PTRS = ['dyn_b', 'dyn_cb', 'inp_b', 'gate_b', 'ln_input_norm_in', 'ln_norm_in', 'ln_norm_out',
+             'ln_input_norm_out', 'fc_b', 'ln_fc_norm', 'qkv_b', 'out_b', 'ln_attn', 'ffn1_b', 'ffn2_b', 'ln_ffn',
+             'ln_head_a', 'ln_head_b', 'cls_b', 'kern_b', 'kb_w']
+    _fields_ = ([(n, c_int) for n in _ROWS] + [('head_relu', c_int)] + [(n, c_void_p) for n in _PTRS] +
+                [('kb_b', c_float), ('reserved', c_int)])
 
 
 class StageWeights(Structure):
     """struct pf_stage_weights."""
-    _fields_ = [('br', BranchWeights * 2), ('ffn_channels', c_int), ('num_classes', c_int)]
+    _fields_ = [('br', BranchWeights * 2), ('wstack256', c_void_p), ('wstack_ffn', c_void_p),
+                ('wstack256_rows', c_int), ('wstack_ffn_rows', c_int), ('ffn_channels', c_int), ('num_classes', c_int)]
 
 
 _SIGS = {
@@ -59,7 +61,7 @@ _SIGS = {
                                  c_int, c_void_p]),
     'pf_split_kernels': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'pf_updator_workspace_bytes': (c_size_t, [c_int]),
-    'pf_kernel_updator': (c_int, [POINTER(BranchWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+    'pf_kernel_updator': (c_int, [POINTER(StageWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                   c_void_p]),
     'pf_mask_einsum': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),

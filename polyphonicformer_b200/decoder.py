@@ -33,12 +33,60 @@ def round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def _split_planes(w64, pad_rows):
+    """fp64 [out][in] -> bf16 [2*pad_rows][in]: hi plane (bf16(w)) then lo plane (bf16(w - hi)), rows zero-padded."""
+    w32 = w64.to(torch.float32)
+    hi = w32.to(torch.bfloat16)
+    lo = (w32 - hi.to(torch.float32)).to(torch.bfloat16)
+    out = torch.zeros((2 * pad_rows, w32.shape[1]), dtype=torch.bfloat16)
+    out[:w32.shape[0]] = hi
+    out[pad_rows:pad_rows + w32.shape[0]] = lo
+    return out
+
+
+class _Packer:
+    """Builds the bf16 weight stacks + one flat fp32 vector buffer and fills ``struct pf_branch_weights``."""
+
+    def __init__(self):
+        self.mats256, self.mats_ffn, self.vecs = [], [], []
+        self.rows256 = self.rows_ffn = self.nvec = 0
+
+    def add_matrix(self, w64, ffn=False):
+        pad = round_up(w64.shape[0], 128)
+        planes = _split_planes(w64, pad)
+        if ffn:
+            row, self.rows_ffn = self.rows_ffn, self.rows_ffn + planes.shape[0]
+            self.mats_ffn.append(planes)
+        else:
+            assert w64.shape[1] == PF_C
+            row, self.rows256 = self.rows256, self.rows256 + planes.shape[0]
+            self.mats256.append(planes)
+        return row
+
+    def add_vector(self, v64):
+        off, self.nvec = self.nvec, self.nvec + round_up(v64.numel(), 64)
+        self.vecs.append((off, v64.reshape(-1).to(torch.float32)))
+        return off
+
+    def finish(self, device, ffn_channels):
+        flat = torch.zeros(max(self.nvec, 64), dtype=torch.float32)
+        for off, v in self.vecs:
+            flat[off:off + v.numel()] = v
+        self.flat = flat.to(device)
+        self.stack256 = (torch.cat(self.mats256) if self.mats256 else torch.zeros((128, PF_C), dtype=torch.bfloat16)).to(device)
+        self.stack_ffn = (torch.cat(self.mats_ffn) if self.mats_ffn
+                          else torch.zeros((128, ffn_channels), dtype=torch.bfloat16)).to(device)
+
+
 class PackedStage:
     """One KernelUpdateHead's parameters in the layout of ``struct pf_stage_weights``.
 
     ``sd`` maps the reference's state-dict keys of one stage (e.g.
-    ``kernel_update_conv.dynamic_layer.weight``) to tensors.  Folding is done in fp64 and rounded once to fp32.
+    ``kernel_update_conv.dynamic_layer.weight``) to tensors.  Folding is done in fp64 and rounded once to fp32
+    (``views``: the folded fp32 parameters, used by the CPU algebra test), then matrices are split into bf16 hi/lo.
     """
+
+    MATS = ('dyn_w', 'inp_w', 'gate_w', 'fc_w', 'qkv_w', 'out_w', 'ffn1_w', 'head_w', 'cls_w', 'kern_w')
 
     def __init__(self, sd, device, num_classes, ffn_channels):
         f64 = {k: v.detach().to('cpu', torch.float64) for k, v in sd.items()}
@@ -89,56 +137,70 @@ class PackedStage:
                 p['ln_head_a'] = ln('depth_regs.1')
             parts[bi] = (p, float(bfc @ bt))
 
-        # one flat fp32 device buffer, every tensor 256-byte aligned
-        offs, total = {}, 0
+        pk = _Packer()
+        rows, vecs = {}, {}
         for bi, (p, _) in parts.items():
             for k, v in p.items():
-                offs[(bi, k)] = total
-                total += round_up(v.numel(), 64)
-        flat = torch.zeros(total, dtype=torch.float32)
-        for bi, (p, _) in parts.items():
-            for k, v in p.items():
-                o = offs[(bi, k)]
-                flat[o:o + v.numel()] = v.reshape(-1).to(torch.float32)
-        self.flat = flat.to(device)
-        self.views = {}
-        for bi, (p, _) in parts.items():
-            for k, v in p.items():
-                o = offs[(bi, k)]
-                self.views[(bi, k)] = self.flat[o:o + v.numel()].view(v.shape)
+                if k in self.MATS:
+                    rows[(bi, k)] = pk.add_matrix(v)
+                elif k == 'ffn2_w':
+                    rows[(bi, k)] = pk.add_matrix(v, ffn=True)
+                else:
+                    vecs[(bi, k)] = pk.add_vector(v)
+        pk.finish(device, ffn_channels)
+        self.packer = pk                      # keeps the device buffers alive
+        self.views = {k: v.to(torch.float32) for bi, (p, _) in parts.items() for k, v in
+                      (((bi, n), t) for n, t in p.items())}
         self.kb_b = {bi: kb for bi, (_, kb) in parts.items()}
-        base = self.flat.data_ptr()
         self.struct = StageWeights()
         self.struct.ffn_channels = ffn_channels
         self.struct.num_classes = num_classes
+        self.struct.wstack256 = pk.stack256.data_ptr()
+        self.struct.wstack_ffn = pk.stack_ffn.data_ptr()
+        self.struct.wstack256_rows = pk.stack256.shape[0]
+        self.struct.wstack_ffn_rows = pk.stack_ffn.shape[0]
+        base = pk.flat.data_ptr()
         for bi, (p, kb_b) in parts.items():
             bw = self.struct.br[bi]
+            for name in BranchWeights._ROWS:
+                setattr(bw, name, rows.get((bi, name), 0))
             for name in BranchWeights._PTRS:
-                setattr(bw, name, base + 4 * offs[(bi, name)] if (bi, name) in offs else None)
+                setattr(bw, name, base + 4 * vecs[(bi, name)] if (bi, name) in vecs else None)
             bw.kb_b = kb_b
             bw.head_relu = 1 if bi == 0 else 0
 
 
 class PackedUpdator:
-    """A standalone KernelUpdator's parameters (no feat_transform fold) as a ``struct pf_branch_weights``."""
+    """A standalone KernelUpdator's parameters (no feat_transform fold) as a ``struct pf_stage_weights`` (branch 0)."""
 
     def __init__(self, sd, device):
-        f = {k: v.detach().to(device, torch.float32) for k, v in sd.items()}
+        f = {k: v.detach().to('cpu', torch.float64) for k, v in sd.items()}
 
         def ln(name):
-            return torch.stack([f[name + '.weight'], f[name + '.bias']]).contiguous()
+            return torch.stack([f[name + '.weight'], f[name + '.bias']])
 
-        self.t = dict(
-            dyn_w=f['dynamic_layer.weight'].contiguous(), dyn_b=f['dynamic_layer.bias'].contiguous(),
-            inp_w=f['input_layer.weight'].contiguous(), inp_b=f['input_layer.bias'].contiguous(),
-            gate_w=torch.cat([f['input_gate.weight'], f['update_gate.weight']]).contiguous(),
-            gate_b=torch.cat([f['input_gate.bias'], f['update_gate.bias']]).contiguous(),
-            ln_input_norm_in=ln('input_norm_in'), ln_norm_in=ln('norm_in'), ln_norm_out=ln('norm_out'),
-            ln_input_norm_out=ln('input_norm_out'), fc_w=f['fc_layer.weight'].contiguous(),
-            fc_b=f['fc_layer.bias'].contiguous(), ln_fc_norm=ln('fc_norm'))
-        self.struct = BranchWeights()
-        for k, v in self.t.items():
-            setattr(self.struct, k, v.data_ptr())
+        pk = _Packer()
+        rows = dict(dyn_w=pk.add_matrix(f['dynamic_layer.weight']), inp_w=pk.add_matrix(f['input_layer.weight']),
+                    gate_w=pk.add_matrix(torch.cat([f['input_gate.weight'], f['update_gate.weight']])),
+                    fc_w=pk.add_matrix(f['fc_layer.weight']))
+        vecs = dict(dyn_b=pk.add_vector(f['dynamic_layer.bias']), inp_b=pk.add_vector(f['input_layer.bias']),
+                    gate_b=pk.add_vector(torch.cat([f['input_gate.bias'], f['update_gate.bias']])),
+                    ln_input_norm_in=pk.add_vector(ln('input_norm_in')), ln_norm_in=pk.add_vector(ln('norm_in')),
+                    ln_norm_out=pk.add_vector(ln('norm_out')), ln_input_norm_out=pk.add_vector(ln('input_norm_out')),
+                    fc_b=pk.add_vector(f['fc_layer.bias']), ln_fc_norm=pk.add_vector(ln('fc_norm')))
+        pk.finish(device, 2048)
+        self.packer = pk
+        self.struct = StageWeights()
+        self.struct.wstack256 = pk.stack256.data_ptr()
+        self.struct.wstack256_rows = pk.stack256.shape[0]
+        self.struct.wstack_ffn = pk.stack_ffn.data_ptr()
+        self.struct.wstack_ffn_rows = pk.stack_ffn.shape[0]
+        self.struct.ffn_channels, self.struct.num_classes = 2048, 1
+        bw = self.struct.br[0]
+        for k, r in rows.items():
+            setattr(bw, k, r)
+        for k, o in vecs.items():
+            setattr(bw, k, pk.flat.data_ptr() + 4 * o)
 
 
 def run_kernel_updator(packed, update_feature, input_feature):

@@ -37,12 +37,12 @@ def test_struct_layout_matches_header():
     hdr = open(os.path.join(ROOT, 'include', 'pf_decoder.h')).read()
     body = hdr[hdr.index('typedef struct pf_branch_weights {'):hdr.index('} pf_branch_weights;')]
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-    ptrs = []
-    for decl in re.findall(r'const float\s*([^;]+);', body):
-        ptrs += [n.strip().lstrip('*') for n in decl.split(',')]
+    ints = [n.strip() for decl in re.findall(r'^\s*int\s+([^;]+);', body, flags=re.M) for n in decl.split(',')]
+    ptrs = [n.strip().lstrip('*') for decl in re.findall(r'const float\s*([^;]+);', body) for n in decl.split(',')]
+    assert ints == _cabi.BranchWeights._ROWS + ['head_relu', 'reserved']
     assert ptrs == _cabi.BranchWeights._PTRS
-    assert ctypes.sizeof(_cabi.BranchWeights) == 8 * len(ptrs) + 8
-    assert ctypes.sizeof(_cabi.StageWeights) == 2 * ctypes.sizeof(_cabi.BranchWeights) + 8
+    assert ctypes.sizeof(_cabi.BranchWeights) == 4 * 12 + 8 * len(ptrs) + 8
+    assert ctypes.sizeof(_cabi.StageWeights) == 2 * ctypes.sizeof(_cabi.BranchWeights) + 16 + 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
@@ -81,6 +81,14 @@ def test_packed_weights_reproduce_reference_stage():
 
     for bi in (0, 1):
         v = {k[1]: t for k, t in ps.views.items() if k[0] == bi}
+        for name in PackedStage.MATS + ('ffn2_w',):   # the bf16 hi + lo planes reproduce the fp32 matrix to ~2^-17
+            if name not in v:
+                continue
+            row = getattr(ps.struct.br[bi], name)
+            stack = ps.packer.stack_ffn if name == 'ffn2_w' else ps.packer.stack256
+            pad = (v[name].shape[0] + 127) // 128 * 128
+            rec = stack[row:row + v[name].shape[0]].float() + stack[row + pad:row + pad + v[name].shape[0]].float()
+            assert (rec - v[name]).abs().max() <= 2.0 ** -16 * v[name].abs().max()
         pooled = torch.einsum('bnh,bch->bnc', m, x[bi])                       # raw features: no feat_transform
         params = pooled @ v['dyn_w'].t() + cnt[..., None] * v['dyn_cb'] + v['dyn_b']
         p_in, p_out = params[..., :256], ln(params[..., 256:], v['ln_norm_out'])
