@@ -36,7 +36,8 @@ constexpr int T_A_BYTES = 128 * T_K * 2;  // 65536 per plane: 4 K-blocks of [128
 constexpr int T_W_PLANE = T_TN * T_KC * 2;      // 16384
 constexpr int T_W_STAGE = 2 * T_W_PLANE;        // hi + lo
 constexpr int T_THREADS = 192;
-constexpr int T_SMEM = 2 * T_A_BYTES + T_WST * T_W_STAGE + 256 + 1024;
+constexpr int T_SMEM_USED = 2 * T_A_BYTES + T_WST * T_W_STAGE + 128 /*barriers*/ + 2048 /*LN mailbox*/;   // 231552
+constexpr int T_SMEM = 232448;            // the 227 KB opt-in maximum; the slack (896 B) absorbs the 1024-byte alignment
 constexpr float U_LN_EPS = 1e-5f;         // nn.LayerNorm default (mmcv build_norm_layer(dict(type='LN')))
 
 enum { PRO_PLAIN = 0, PRO_ADD = 1, PRO_MUL = 2, PRO_MIX = 3, PRO_SUMLN = 4, PRO_PLANES = 5 };
@@ -104,7 +105,8 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     uint64_t* accfull = bars + 2 * T_WST;
     uint64_t* abar = bars + 2 * T_WST + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_WST + 2);
-    __shared__ float s_mail[2][2][128];   // [LN pass][source CTA rank][row]
+    float(*s_mail)[2][128] = reinterpret_cast<float(*)[2][128]>(reinterpret_cast<uint8_t*>(bars) + 128);   // [LN pass][source CTA rank][row]
+    if (smem + T_SMEM_USED > smem_raw + T_SMEM) __trap();   // dynamic smem base less aligned than assumed
 
     const TcBranch& g = args.br[blockIdx.z];
     const int tile = blockIdx.x, nb = tile * T_TN;
