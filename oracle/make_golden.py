@@ -25,7 +25,12 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 DECODER_CASES = [
     # name, B, H, W, seed
-    ('decoder_b2_h16_w24_s0', 2, 16, 24, 0),
+    # seed 6: of seeds 0..7 the one whose intermediate mask logits stay furthest from 0 (min |logit| of stages 0/1 =
+    # 4.5e-4 / 6.3e-4).  The next stage consumes only sigmoid(logit) > 0.5 (kernel_update_head.py:236-238): a logit
+    # within fp32 rounding of 0 (seed 0 has one at -7e-5) flips a mask bit between ANY two implementations, and on a
+    # 384-pixel map one flipped pixel moves a pooled row by ~1e-2 -- the un-teacher-forced loop is only comparable
+    # away from that discontinuity.  Margins are stored in the fixture ('margin').
+    ('decoder_b2_h16_w24_s6', 2, 16, 24, 6),
     ('decoder_b1_h10_w12_s1', 1, 10, 12, 1),   # HW=120: ragged tile tail
 ]
 
@@ -95,7 +100,8 @@ def main():
     for name, B, H, W, seed in DECODER_CASES:
         out = run_decoder_case(head, B, H, W, seed)
         path = os.path.join(GOLD, name + '.npz')
-        np.savez_compressed(path, B=B, H=H, W=W, seed=seed, **out)
+        margin = np.array([np.abs(out['s%d.mask_preds' % s]).min() for s in range(3)], dtype=np.float32)
+        np.savez_compressed(path, B=B, H=H, W=W, seed=seed, margin=margin, **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith('s2') or 'scaled' in k},
               f'{os.path.getsize(path) / 1e6:.2f} MB')
     u = run_updator_case(head)

@@ -39,7 +39,7 @@ def flips(a, b):
     return ((torch.as_tensor(a) > 0) != (torch.as_tensor(b) > 0)).float().mean().item()
 
 
-@pytest.mark.parametrize('name', ['decoder_b2_h16_w24_s0', 'decoder_b1_h10_w12_s1'])
+@pytest.mark.parametrize('name', ['decoder_b2_h16_w24_s6', 'decoder_b1_h10_w12_s1'])
 def test_stage_forward_matches_reference_golden(dev, name):
     """KernelUpdateHead.forward per stage, fed with the reference's own inputs of that stage."""
     g = np.load(os.path.join(GOLDEN, name + '.npz'))
@@ -64,7 +64,7 @@ def test_stage_forward_matches_reference_golden(dev, name):
         dep = torch.from_numpy(g['s%d.depth_proposal' % s])
 
 
-@pytest.mark.parametrize('name', ['decoder_b2_h16_w24_s0', 'decoder_b1_h10_w12_s1'])
+@pytest.mark.parametrize('name', ['decoder_b2_h16_w24_s6', 'decoder_b1_h10_w12_s1'])
 @pytest.mark.parametrize('all_outputs', [False, True])
 def test_decode_loop_matches_reference_golden(dev, name, all_outputs):
     """The fused 3-stage loop (pf_decoder_forward) end to end, including the x2 upsampling and cls sigmoid."""

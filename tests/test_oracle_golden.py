@@ -10,7 +10,7 @@ from oracle import decoder_ref as ref
 from oracle import synth
 from conftest import rel_err, GOLDEN
 
-CASES = ['decoder_b2_h16_w24_s0', 'decoder_b1_h10_w12_s1']
+CASES = ['decoder_b2_h16_w24_s6', 'decoder_b1_h10_w12_s1']
 TOL = 2e-5   # fp32 re-association between the reference's op order and the restatement
 
 
