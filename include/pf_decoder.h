@@ -73,15 +73,19 @@ const char* pf_last_error_string(void);
  *   wstack_ffn [rows][FFN]   ffn.layers.1 (256 x FFN),
  * each matrix [out][in] (nn.Linear layout) stored as a hi plane (bf16(w)) followed by a lo plane (bf16(w - hi)), out
  * padded to a multiple of 128 rows.  The tensor-core GEMMs run hi and lo as separate MMAs (fp32-level accuracy).  The
- * struct holds the ROW of the hi plane; the lo plane starts `padded out` rows later.  Vectors stay fp32.
+ * struct holds the ROW of the hi plane; the lo plane starts `padded out` rows later.  Vectors stay fp32 (each padded
+ * to a multiple of 64 floats).
  * feat_transform W_t,b_t (kernel_update_head.py:224-226) never touches the feature map; it is folded (in fp64):
  *   dyn_w  = dynamic_layer.weight @ W_t,  dyn_cb = dynamic_layer.weight @ b_t   (pooled' = pooled W_t^T + count b_t)
- *   kern_w = W_t^T @ fc_{mask,depth}.weight, kern_b = W_t^T @ fc.bias, kb_w = fc.weight^T @ b_t, kb_b = fc.bias . b_t
+ *   kern_w = W_t^T @ fc_{mask,depth}.weight, kern_b = W_t^T @ fc.bias,
+ *   kbrow_w = (fc.weight^T @ b_t) as ONE weight row, kbrow_b[0] = fc.bias . b_t    (the per-kernel logit bias)
+ * gate_w / gate_b are stored interleaved in blocks of 64 output rows: [input_gate 0..63 | update_gate 0..63 |
+ * input_gate 64..127 | ...], so that one 128-column GEMM tile holds both gates of the same 64 features.
  */
 typedef struct pf_branch_weights {
     int dyn_w;    /* (*) [512][256]  dynamic_layer, folded; kernel_updator.py:58 */
     int inp_w;    /*     [512][256]  input_layer; :64 */
-    int gate_w;   /*     [512][256]  [input_gate; update_gate]; :73-74 */
+    int gate_w;   /*     [512][256]  input_gate / update_gate interleaved by 64; :73-74 */
     int fc_w;     /*     [256][256]  fc_layer; :89 */
     int qkv_w;    /*     [768][256]  attn.in_proj; kernel_update_head.py:259-260 */
     int out_w;    /*     [256][256]  attn.out_proj */
@@ -89,10 +93,11 @@ typedef struct pf_branch_weights {
     int head_w;   /*     mask: [cls_fcs.0; mask_fcs.0] [512][256]; depth: depth_regs.0 [256][256]; :278-283 */
     int cls_w;    /*     mask branch only: fc_cls padded to [128][256]; :285 */
     int kern_w;   /* (*) [256][256]  fc_mask / fc_depth with the fold; :287-288 */
+    int kbrow_w;  /* (*) [1][256] padded to [128][256] */
     int ffn2_w;   /*     [256][FFN]  ffn.layers.1 -- row in wstack_ffn */
     int head_relu;                                  /* 1 for the mask branch (mask_fcs has ReLU), 0 for depth_regs */
-    const float *dyn_b, *dyn_cb;                    /* [512], (*) [512] */
-    const float *inp_b, *gate_b;                    /* [512], [512] */
+    const float *dyn_b, *dyn_cb;                    /* [512], (*) [512] (dyn_cb may be NULL: no fold) */
+    const float *inp_b, *gate_b;                    /* [512], [512] (interleaved like gate_w) */
     const float *ln_input_norm_in, *ln_norm_in;     /* each [2][256] = gamma, beta; kernel_updator.py:75-77 */
     const float *ln_norm_out, *ln_input_norm_out;   /* :78-79 */
     const float *fc_b, *ln_fc_norm;                 /* :89-91 */
@@ -100,9 +105,7 @@ typedef struct pf_branch_weights {
     const float *ffn1_b, *ffn2_b, *ln_ffn;          /* ffn_norm */
     const float *ln_head_a, *ln_head_b;             /* mask: cls_fcs.1, mask_fcs.1; depth: depth_regs.1, unused */
     const float *cls_b;                             /* [32] (padded) */
-    const float *kern_b, *kb_w;                     /* (*) [256], (*) [256] */
-    float kb_b;                                     /* (*) scalar */
-    int reserved;
+    const float *kern_b, *kbrow_b;                  /* (*) [256], (*) [1] */
 } pf_branch_weights;
 
 typedef struct pf_stage_weights {

@@ -31,12 +31,12 @@ _fp = POINTER(c_float)
 
 class BranchWeights(Structure):
     """struct pf_branch_weights -- field order must match include/pf_decoder.h."""
-    _ROWS = ['dyn_w', 'inp_w', 'gate_w', 'fc_w', 'qkv_w', 'out_w', 'ffn1_w', 'head_w', 'cls_w', 'kern_w', 'ffn2_w']
+    _ROWS = ['dyn_w', 'inp_w', 'gate_w', 'fc_w', 'qkv_w', 'out_w', 'ffn1_w', 'head_w', 'cls_w', 'kern_w', 'kbrow_w',
+             'ffn2_w']
     _PTRS = ['dyn_b', 'dyn_cb', 'inp_b', 'gate_b', 'ln_input_norm_in', 'ln_norm_in', 'ln_norm_out',
              'ln_input_norm_out', 'fc_b', 'ln_fc_norm', 'qkv_b', 'out_b', 'ln_attn', 'ffn1_b', 'ffn2_b', 'ln_ffn',
-             'ln_head_a', 'ln_head_b', 'cls_b', 'kern_b', 'kb_w']
-    _fields_ = ([(n, c_int) for n in _ROWS] + [('head_relu', c_int)] + [(n, c_void_p) for n in _PTRS] +
-                [('kb_b', c_float), ('reserved', c_int)])
+             'ln_head_a', 'ln_head_b', 'cls_b', 'kern_b', 'kbrow_b']
+    _fields_ = [(n, c_int) for n in _ROWS] + [('head_relu', c_int)] + [(n, c_void_p) for n in _PTRS]
 
 
 class StageWeights(Structure):

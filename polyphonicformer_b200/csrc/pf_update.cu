@@ -3,22 +3,25 @@
 //   the cls / mask / depth FC heads (polyphonic/kernel_update_head.py:245-288), with feat_transform folded into the
 //   first and last linear layers (see include/pf_decoder.h).
 //
-// Building block: tcgemm_kernel -- Y[128 rows][128 cols] = epilogue(prologue(X...) @ W^T) per CTA on tcgen05.
-//   * M = 128 = the N (=111) kernels of ONE image (rows >= N are zero): weights are streamed once per image;
-//   * fp32-level accuracy from bf16 tensor cores: X = Xh + Xl, W = Wh + Wl (bf16 each) and
-//     D = Xl*Wh + Xh*Wl + Xh*Wh (3 MMAs per K step, fp32 accumulate in TMEM), error ~2^-16 per product --
-//     the reference computes these layers in fp32 and they feed LayerNorms;
-//   * A operand: built by the prologue (all 6 warps) from fp32 activations -- a+b, a*b, a*b + c*d for the updator
-//     gates, or LN(sum of split-K partials + bias + residual) after the FFN -- split into hi/lo and written K-major /
-//     128B-swizzled into shared memory; for the FFN's second layer it is TMA-loaded from the bf16 hi/lo planes the
-//     first layer emitted;
-//   * B operand: weights pre-split into bf16 hi/lo planes at pack time, TMA-loaded [128 n][64 k] boxes, 3-stage ring,
-//     issued BEFORE griddepcontrol.wait so the fetch overlaps the previous kernel (programmatic dependent launch);
-//   * epilogue: thread = row (TMEM lane): + bias (+ count * folded bias) (+ residual) -> LayerNorm over the 256-wide
-//     group (row statistics exchanged with the peer CTA of a 2-CTA cluster through DSMEM) -> ReLU / sigmoid ->
-//     fp32 and/or bf16 hi/lo planes.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
-// 13 launches per stage.  This block is latency / weight-streaming bound, not roofline bound; see DESIGN.md.
+// Data layout.  Every activation that feeds a GEMM lives in the "arena" as a pair of bf16 planes
+//   arena[unit][slot][hi|lo][128 rows][256 cols]      (x = hi + lo to ~2^-17; rows >= N are padding)
+// so that BOTH GEMM operands are TMA boxes and no kernel has a register-path prologue; values that are only used
+// element-wise (LayerNorm'ed halves, residuals, q/k/v, split-K partials) stay fp32 [B*N][...].
+//
+// tcgemm_kernel<MODE>: Y[128 rows][128 cols] per CTA on tcgen05.
+//   * M = 128 = the N (=111) kernels of ONE image;
+//   * fp32-level accuracy from bf16 tensor cores: D = Al*Wh + Ah*Wl + Ah*Wh (3 MMAs per K=16 step, fp32 accumulate
+//     in TMEM, error ~2^-16 per product) -- the reference runs these layers in fp32 and they feed LayerNorms;
+//   * one ring stage = [A hi | A lo | W hi | W lo] boxes of [128][64 k] (64 KB), 3 stages; the weight boxes of the
+//     first stages are issued BEFORE griddepcontrol.wait (programmatic dependent launch), the activation boxes after;
+//   * a CTA runs 1 or 2 "passes" of K = 256 into separate TMEM accumulators (MODE_DUAL: dynamic_layer and
+//     input_layer of the same output columns, so their product is formed in the epilogue);
+//   * epilogue: 8 warps, thread = (row, 64-column half): bias / count-bias / residual, LayerNorm over the 256-wide
+//     group (per-thread (mean, M2) over 64 columns merged across the halves and the CTAs of the cluster through
+//     DSMEM, one cluster barrier), ReLU / sigmoid, gate mixing, then fp32 rows and/or bf16 hi/lo planes.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// 12 launches per stage: prep, dyn+inp, gates, fc, qkv, attention, out-proj, ffn1, ffn2 (split-K), sum+LN, heads,
+// kernels+cls.  This block is latency / weight-streaming bound, not roofline bound; see DESIGN.md.
 #include <string.h>
 
 #include <mutex>
@@ -28,50 +31,57 @@
 
 namespace pf {
 
-constexpr int T_TN = 128;                 // output columns per CTA
-constexpr int T_KC = 64;                  // K per weight stage
-constexpr int T_WST = 3;                  // weight ring depth
-constexpr int T_K = 256;                  // K per CTA (FFN2 is split-K in slabs of 256)
-constexpr int T_A_BYTES = 128 * T_K * 2;  // 65536 per plane: 4 K-blocks of [128 rows][64 k]
-constexpr int T_W_PLANE = T_TN * T_KC * 2;      // 16384
-constexpr int T_W_STAGE = 2 * T_W_PLANE;        // hi + lo
-constexpr int T_THREADS = 192;
-constexpr int T_SMEM_USED = 2 * T_A_BYTES + T_WST * T_W_STAGE + 128 /*barriers*/ + 2048 /*LN mailbox*/;   // 231552
-constexpr int T_SMEM = 232448;            // the 227 KB opt-in maximum; the slack (896 B) absorbs the 1024-byte alignment
-constexpr float U_LN_EPS = 1e-5f;         // nn.LayerNorm default (mmcv build_norm_layer(dict(type='LN')))
+constexpr int T_THREADS = 320;
+constexpr int T_TN = 128;                       // output columns per CTA (per pass)
+constexpr int T_KC = 64;                        // K per ring stage
+constexpr int T_K = 256;                        // K per pass
+constexpr int T_NSTG = 3;
+constexpr int T_PLANE = 128 * T_KC * 2;         // 16384: one [128][64] bf16 box
+constexpr int T_STAGE = 4 * T_PLANE;            // A hi | A lo | W hi | W lo
+constexpr int T_BAR_OFF = T_NSTG * T_STAGE;     // 196608
+constexpr int T_MAIL_OFF = T_BAR_OFF + 256;
+constexpr int T_MAIL_BYTES = 2 * 4 * 128 * 8;   // [array][source][row] x (mean, M2)
+constexpr int T_SMEM_USED = T_MAIL_OFF + T_MAIL_BYTES;
+constexpr int T_SMEM = T_SMEM_USED + 1024;      // slack for the 1024-byte alignment of the ring
+constexpr int T_XCH_LD = 68;                    // floats per row of the gate exchange tile (16-byte rows, no conflicts)
+constexpr float U_LN_EPS = 1e-5f;               // nn.LayerNorm default (mmcv build_norm_layer(dict(type='LN')))
 
-enum { PRO_PLAIN = 0, PRO_ADD = 1, PRO_MUL = 2, PRO_MIX = 3, PRO_SUMLN = 4, PRO_PLANES = 5 };
+enum { SLOT_POOLED = 0, SLOT_INP, SLOT_GATEIN, SLOT_MIX, SLOT_OBJ0, SLOT_ATT, SLOT_OBJ1, SLOT_HID0,
+       SLOT_OBJ2 = SLOT_HID0 + 8, SLOT_HEAD0, SLOT_HEAD1, NSLOT };
+constexpr size_t SLOT_ELEMS = 2 * 128 * 256;    // bf16 elements per slot (hi + lo)
+
+enum { MODE_GENERIC = 0, MODE_DUAL = 1, MODE_GATE = 2 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
-struct TcBranch {
-    // ---- A operand
-    const float *X, *X2, *X3, *X4;
-    int ldx, ldx2, ldx3, ldx4;
-    const float* part;    // PRO_SUMLN: [nsplit][R][256] split-K partials
-    int nsplit;
-    const float* pbias;   // [256]
-    const float* pres;    // residual [R][256]
-    const float* pln;     // {gamma[256], beta[256]}
-    float* xout;          // LN result written back [R][256] (by the column-tile-0 CTAs)
-    int a_unit0;          // PRO_PLANES: first unit of this branch in the A planes
-    const float* rowdot_w;  // optional: rowdot_out[row] = X'[row,:] . rowdot_w + rowdot_b
-    float rowdot_b;
-    float* rowdot_out;
-    // ---- B operand: row of column 0 in the weight stack (hi plane); the lo plane starts w_lo_off rows later
-    int w_row, w_lo_off;
-    // ---- epilogue
-    const float *bias, *cbias, *count, *res;
-    int ldr;
-    const float* ln[2];   // LayerNorm {gamma[256], beta[256]} of 256-column group min(group,1), or null
-    int act[2];
-    float* Y;             // fp32 output or null; split-K partials when ksplit > 1
-    int ldy, Nout, nstore;
-    uint16_t* planes;     // optional bf16 hi/lo output [unit][2][plane_rows][plane_ld]
-    int plane_rows, plane_ld, plane_unit0;
+struct TcPass {
+    int a_slot;             // arena slot of the A operand (+ split when ksplit > 1)
+    int w_ffn;              // 0: weight stack with 256 columns, 1: the FFN-wide stack
+    int w_row, w_lo, w_k0;  // row of output column 0 (hi plane), rows to the lo plane, first K column (+256*split)
 };
+struct TcJob {
+    int unit0;              // arena unit of image 0 (= branch * B)
+    int ntiles;             // 128-column tiles of this job; CTAs with blockIdx.x >= ntiles idle
+    int npass;
+    TcPass pass[2];
+    // ---- epilogue
+    const float *bias0, *cbias0, *count, *bias1;
+    const float *ln0, *ln1;     // {gamma[256], beta[256]}: GENERIC -> 256-column group 0 / >= 1; DUAL -> acc0 / acc1
+                                // (out halves); GATE -> input_norm_in / norm_in
+    int act0, act1;
+    const float* res;           // residual [R][ldr]
+    int ldr;
+    const float *mul0, *mul1;   // GATE: LN'ed input_out / param_out [R][256]
+    float *Y, *Y1;              // fp32 outputs (Y1: DUAL acc1); split-K partials when ksplit > 1
+    int ldy, nstore;
+    int p_slot;                 // arena slot of 256-column group 0 of the bf16 output planes, or -1
+    uint16_t* xplanes;          // external planes [unit][2][xrows][256] (kern_split), or null
+    int xrows, xunit0;
+};
+constexpr int T_MAXJOBS = 5;
 struct TcArgs {
-    TcBranch br[2];
-    int B, N, R, pro, ksplit, cluster;
+    TcJob job[T_MAXJOBS];
+    uint16_t* arena;
+    int B, N, R, ksplit;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -82,195 +92,208 @@ __device__ __forceinline__ float warp_sum(float v) {
 // programmatic dependent launch: everything before pdl_wait() may overlap the previous kernel of the stream
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
-__device__ __forceinline__ void st_cluster_f32(float* local_smem_ptr, uint32_t rank, float v) {
+__device__ __forceinline__ void st_cluster_f32x2(const void* local_smem_ptr, uint32_t rank, float a, float b) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
+// 64 fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&y)[64]) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(taddr, v0);
+    tmem_ld32(taddr + 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v0[i]), y[32 + i] = __uint_as_float(v1[i]);
+}
+__device__ __forceinline__ void add_vec64(float (&y)[64], const float* __restrict__ v) {   // v: same address in all lanes
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+        const float4 t = ld4(v + c);
+        y[c] += t.x, y[c + 1] += t.y, y[c + 2] += t.z, y[c + 3] += t.w;
+    }
+}
+__device__ __forceinline__ void fma_vec64(float (&y)[64], float s, const float* __restrict__ v) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+        const float4 t = ld4(v + c);
+        y[c] += s * t.x, y[c + 1] += s * t.y, y[c + 2] += s * t.z, y[c + 3] += s * t.w;
+    }
+}
+__device__ __forceinline__ void mean_m2_64(const float (&y)[64], float& mean, float& m2) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) s += y[c];
+    mean = s * (1.f / 64.f);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) q += (y[c] - mean) * (y[c] - mean);
+    m2 = q;
+}
+__device__ __forceinline__ void ln_apply64(float (&y)[64], float mean, float rstd, const float* __restrict__ ln, int col) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+        const float4 ga = ld4(ln + col + c), be = ld4(ln + 256 + col + c);
+        y[c] = (y[c] - mean) * rstd * ga.x + be.x, y[c + 1] = (y[c + 1] - mean) * rstd * ga.y + be.y;
+        y[c + 2] = (y[c + 2] - mean) * rstd * ga.z + be.z, y[c + 3] = (y[c + 3] - mean) * rstd * ga.w + be.w;
+    }
+}
+__device__ __forceinline__ void act64(float (&y)[64], int act) {
+    if (act == ACT_RELU) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) y[c] = fmaxf(y[c], 0.f);
+    } else if (act == ACT_SIGMOID) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) y[c] = 1.f / (1.f + expf(-y[c]));
+    }
+}
+// 64 values -> bf16 hi / lo, 128 contiguous bytes in each plane
+__device__ __forceinline__ void store_planes64(const float (&y)[64], uint16_t* hi_ptr, uint16_t* lo_ptr, bool zero) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v0 = zero ? 0.f : y[c + 2 * i], v1 = zero ? 0.f : y[c + 2 * i + 1];
+            const float h0 = bf16_round(v0), h1 = bf16_round(v1);
+            hi[i] = pack_bf16x2(h0, h1);
+            lo[i] = pack_bf16x2(v0 - h0, v1 - h1);
+        }
+        *reinterpret_cast<uint4*>(hi_ptr + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(lo_ptr + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+__device__ __forceinline__ uint16_t* arena_row(uint16_t* arena, int unit, int slot, int plane, int r) {
+    return arena + ((size_t)unit * NSLOT + slot) * SLOT_ELEMS + ((size_t)plane * 128 + r) * 256;
+}
+
+// LayerNorm statistics of a 256-wide group held as 4 x 64 columns by (2 halves x 2 CTAs) or (1 half x 4 CTAs):
+// every holder publishes (mean, M2) of its 64 columns into mailbox[arr][src][row] of every CTA of the cluster.
+struct Mail {
+    float2 (*box)[4][128];
+    __device__ __forceinline__ void publish(int arr, int src, int r, float mean, float m2, int csize) const {
+        for (int k = 0; k < csize; ++k) st_cluster_f32x2(&box[arr][src][r], (uint32_t)k, mean, m2);
+    }
+    __device__ __forceinline__ void combine(int arr, int r, float& mean, float& rstd) const {
+        const float2 a = box[arr][0][r], b = box[arr][1][r], c = box[arr][2][r], d = box[arr][3][r];
+        mean = (a.x + b.x + c.x + d.x) * 0.25f;
+        const float m2 = a.y + b.y + c.y + d.y +
+                         64.f * ((a.x - mean) * (a.x - mean) + (b.x - mean) * (b.x - mean) + (c.x - mean) * (c.x - mean) +
+                                 (d.x - mean) * (d.x - mean));
+        rstd = 1.f / sqrtf(m2 * (1.f / 256.f) + U_LN_EPS);
+    }
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(T_THREADS, 1)
-tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcArgs args) {
+tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constant__ CUtensorMap tmap_wffn,
+              const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA_hi = smem;
-    uint8_t* sA_lo = smem + T_A_BYTES;
-    uint8_t* sW = smem + 2 * T_A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + T_WST * T_W_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T_BAR_OFF);
     uint64_t* full = bars;
-    uint64_t* empty = bars + T_WST;
-    uint64_t* accfull = bars + 2 * T_WST;
-    uint64_t* abar = bars + 2 * T_WST + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_WST + 2);
-    float(*s_mail)[2][128] = reinterpret_cast<float(*)[2][128]>(reinterpret_cast<uint8_t*>(bars) + 128);   // [LN pass][source CTA rank][row]
+    uint64_t* empty = bars + T_NSTG;
+    uint64_t* accfull = bars + 2 * T_NSTG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_NSTG + 1);
+    Mail mail{reinterpret_cast<float2(*)[4][128]>(smem + T_MAIL_OFF)};
     if (smem + T_SMEM_USED > smem_raw + T_SMEM) __trap();   // dynamic smem base less aligned than assumed
 
-    const TcBranch& g = args.br[blockIdx.z];
+    const TcJob& g = args.job[blockIdx.z];
     const int tile = blockIdx.x, nb = tile * T_TN;
     const int b = blockIdx.y / args.ksplit, split = blockIdx.y % args.ksplit;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool active = nb < g.Nout;   // uniform per cluster (Nout is a multiple of 256 whenever clusters are used)
+    const bool active = tile < g.ntiles;   // uniform per cluster (ntiles is a multiple of the cluster size)
     const int N = args.N;
-    constexpr int NK = T_K / T_KC;     // 4 weight stages per CTA
-    const int kbase = split * T_K;
+    const int unit = g.unit0 + b;
+    const int total_it = g.npass * (T_K / T_KC);
+    // LayerNorm anywhere in this CTA?  (decides the cluster barriers; uniform per cluster)
+    bool has_ln;
+    if (MODE == MODE_GATE) has_ln = true;
+    else if (MODE == MODE_DUAL) has_ln = nb >= 256;
+    else has_ln = (nb < 256 ? g.ln0 : g.ln1) != nullptr;
+    has_ln = has_ln && active;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmap_w);
-        for (int i = 0; i < T_WST; ++i) {
+        tma_prefetch_desc(&tmap_w256);
+        tma_prefetch_desc(&tmap_wffn);
+        tma_prefetch_desc(&tmap_a);
+        for (int i = 0; i < T_NSTG; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
         mbar_init(accfull, 1);
-        mbar_init(abar, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<T_TN>(tmem_slot);
-    __syncthreads();
-    // weights do not depend on the previous kernel: start the ring before the grid dependency is resolved
-    if (active && threadIdx.x == 0) {
-        for (int kc = 0; kc < T_WST; ++kc) {
-            mbar_arrive_expect_tx(&full[kc], T_W_STAGE);
-            tma_load_2d(sW + kc * T_W_STAGE, &tmap_w, &full[kc], kbase + kc * T_KC, g.w_row + nb, kEvictLast);
-            tma_load_2d(sW + kc * T_W_STAGE + T_W_PLANE, &tmap_w, &full[kc], kbase + kc * T_KC, g.w_row + g.w_lo_off + nb,
-                        kEvictLast);
-        }
-    }
-    pdl_wait();                 // activations written by the previous kernel are visible from here on
-    pdl_launch_dependents();    // let the next kernel start prefetching its weights
-
-    if (active) {
-        if (args.pro == PRO_PLANES) {
-            if (threadIdx.x == 0) {   // A = bf16 hi/lo planes [unit][2][128][K_total], K slab of this split
-                mbar_arrive_expect_tx(abar, 2 * T_A_BYTES);
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb)
-                        tma_load_3d(sA_hi + h * T_A_BYTES + kb * (128 * 128), &tmap_a, abar, kbase + kb * 64, 0,
-                                    (g.a_unit0 + b) * 2 + h, kEvictFirst);
-            }
-        } else {
-            // ---------------- prologue: warp per row, lane owns k = 8*lane .. 8*lane+7
-            const int k0 = lane * 8;
-            const uint32_t aoff_k = (uint32_t)(lane >> 3) * (128 * 128);
-            const bool do_side = (tile == 0 && split == 0);
-#pragma unroll 2
-            for (int r = warp; r < 128; r += T_THREADS / 32) {
-                float x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = 0.f;
-                if (r < N) {
-                    const size_t m = (size_t)b * N + r;
-                    if (args.pro == PRO_SUMLN) {
-                        for (int s2 = 0; s2 < g.nsplit; ++s2) {
-                            const float* pp = g.part + ((size_t)s2 * args.R + m) * 256 + k0;
-                            const float4 u = ld4(pp), v = ld4(pp + 4);
-                            x[0] += u.x, x[1] += u.y, x[2] += u.z, x[3] += u.w;
-                            x[4] += v.x, x[5] += v.y, x[6] += v.z, x[7] += v.w;
-                        }
-                        const float4 bu = ld4(g.pbias + k0), bv = ld4(g.pbias + k0 + 4);
-                        const float4 ru = ld4(g.pres + m * 256 + k0), rv = ld4(g.pres + m * 256 + k0 + 4);
-                        x[0] += bu.x + ru.x, x[1] += bu.y + ru.y, x[2] += bu.z + ru.z, x[3] += bu.w + ru.w;
-                        x[4] += bv.x + rv.x, x[5] += bv.y + rv.y, x[6] += bv.z + rv.z, x[7] += bv.w + rv.w;
-                        float sum = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) sum += x[i];
-                        const float mean = warp_sum(sum) * (1.f / 256.f);
-                        float sq = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) sq += (x[i] - mean) * (x[i] - mean);
-                        const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / 256.f) + U_LN_EPS);
-                        const float4 gu = ld4(g.pln + k0), gv = ld4(g.pln + k0 + 4);
-                        const float4 eu = ld4(g.pln + 256 + k0), ev = ld4(g.pln + 256 + k0 + 4);
-                        const float gam[8] = {gu.x, gu.y, gu.z, gu.w, gv.x, gv.y, gv.z, gv.w};
-                        const float bet[8] = {eu.x, eu.y, eu.z, eu.w, ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) x[i] = (x[i] - mean) * rstd * gam[i] + bet[i];
-                        if (do_side && g.xout) {
-                            *reinterpret_cast<float4*>(g.xout + m * 256 + k0) = make_float4(x[0], x[1], x[2], x[3]);
-                            *reinterpret_cast<float4*>(g.xout + m * 256 + k0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
-                        }
-                    } else {
-                        const float4 u = ld4(g.X + m * g.ldx + k0), v = ld4(g.X + m * g.ldx + k0 + 4);
-                        x[0] = u.x, x[1] = u.y, x[2] = u.z, x[3] = u.w, x[4] = v.x, x[5] = v.y, x[6] = v.z, x[7] = v.w;
-                        if (args.pro == PRO_ADD) {
-                            if (g.X2) {
-                                const float4 a = ld4(g.X2 + m * g.ldx2 + k0), c = ld4(g.X2 + m * g.ldx2 + k0 + 4);
-                                x[0] += a.x, x[1] += a.y, x[2] += a.z, x[3] += a.w;
-                                x[4] += c.x, x[5] += c.y, x[6] += c.z, x[7] += c.w;
-                            }
-                        } else if (args.pro == PRO_MUL || args.pro == PRO_MIX) {
-                            const float4 a = ld4(g.X2 + m * g.ldx2 + k0), c = ld4(g.X2 + m * g.ldx2 + k0 + 4);
-                            x[0] *= a.x, x[1] *= a.y, x[2] *= a.z, x[3] *= a.w;
-                            x[4] *= c.x, x[5] *= c.y, x[6] *= c.z, x[7] *= c.w;
-                            if (args.pro == PRO_MIX) {
-                                const float4 p3 = ld4(g.X3 + m * g.ldx3 + k0), q3 = ld4(g.X3 + m * g.ldx3 + k0 + 4);
-                                const float4 p4 = ld4(g.X4 + m * g.ldx4 + k0), q4 = ld4(g.X4 + m * g.ldx4 + k0 + 4);
-                                x[0] += p3.x * p4.x, x[1] += p3.y * p4.y, x[2] += p3.z * p4.z, x[3] += p3.w * p4.w;
-                                x[4] += q3.x * q4.x, x[5] += q3.y * q4.y, x[6] += q3.z * q4.z, x[7] += q3.w * q4.w;
-                            }
-                        }
-                    }
-                    if (do_side && g.rowdot_out) {
-                        const float4 wu = ld4(g.rowdot_w + k0), wv = ld4(g.rowdot_w + k0 + 4);
-                        float d = x[0] * wu.x + x[1] * wu.y + x[2] * wu.z + x[3] * wu.w + x[4] * wv.x + x[5] * wv.y +
-                                  x[6] * wv.z + x[7] * wv.w;
-                        d = warp_sum(d);
-                        if (lane == 0) g.rowdot_out[m] = d + g.rowdot_b;
-                    }
-                }
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float h0 = bf16_round(x[2 * i]), h1 = bf16_round(x[2 * i + 1]);
-                    hi[i] = pack_bf16x2(h0, h1);
-                    lo[i] = pack_bf16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
-                }
-                const uint32_t off = aoff_k + sw128_offset(r, lane & 7);
-                *reinterpret_cast<uint4*>(sA_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(sA_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            fence_proxy_async_smem();
-        }
-    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (has_ln) cluster_arrive();   // matched by the cluster_wait before the first DSMEM store: peers have started
+
+    auto issue_w = [&](int it) {
+        const TcPass& p = g.pass[it >> 2];
+        const int kb = it & 3, s = it % T_NSTG;
+        uint8_t* st = smem + s * T_STAGE;
+        const CUtensorMap* wm = p.w_ffn ? &tmap_wffn : &tmap_w256;
+        const int k = p.w_k0 + (p.w_ffn ? split * T_K : 0) + kb * T_KC;
+        mbar_arrive_expect_tx(&full[s], T_STAGE);
+        tma_load_2d(st + 2 * T_PLANE, wm, &full[s], k, p.w_row + nb, kEvictLast);
+        tma_load_2d(st + 3 * T_PLANE, wm, &full[s], k, p.w_row + p.w_lo + nb, kEvictLast);
+    };
+    auto issue_a = [&](int it) {
+        const TcPass& p = g.pass[it >> 2];
+        const int kb = it & 3, s = it % T_NSTG;
+        uint8_t* st = smem + s * T_STAGE;
+        const int row = ((unit * NSLOT + p.a_slot + (args.ksplit > 1 ? split : 0)) * 2) * 128;
+        tma_load_2d(st, &tmap_a, &full[s], kb * T_KC, row, kEvictFirst);
+        tma_load_2d(st + T_PLANE, &tmap_a, &full[s], kb * T_KC, row + 128, kEvictFirst);
+    };
+
+    // weights do not depend on the previous kernel: start the ring before the grid dependency is resolved
+    const int pre = total_it < T_NSTG ? total_it : T_NSTG;
+    if (active && threadIdx.x == 0)
+        for (int it = 0; it < pre; ++it) issue_w(it);
+    pdl_wait();                 // activations written by the previous kernels are visible from here on
+    pdl_launch_dependents();    // let the next kernel start prefetching its weights
 
     if (active && warp == 0 && lane == 0) {
-        // ================= weight producer: remaining stages =================
-        for (int kc = T_WST; kc < NK; ++kc) {
-            const int s = kc % T_WST;
-            mbar_wait(&empty[s], ((kc / T_WST) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[s], T_W_STAGE);
-            tma_load_2d(sW + s * T_W_STAGE, &tmap_w, &full[s], kbase + kc * T_KC, g.w_row + nb, kEvictLast);
-            tma_load_2d(sW + s * T_W_STAGE + T_W_PLANE, &tmap_w, &full[s], kbase + kc * T_KC, g.w_row + g.w_lo_off + nb,
-                        kEvictLast);
+        // ================= TMA producer =================
+        for (int it = 0; it < pre; ++it) issue_a(it);
+        for (int it = pre; it < total_it; ++it) {
+            mbar_wait(&empty[it % T_NSTG], ((it / T_NSTG) & 1) ^ 1);
+            issue_w(it);
+            issue_a(it);
         }
     } else if (active && warp == 1 && lane == 0) {
-        // ================= MMA issuer: D = Al*Bh + Ah*Bl + Ah*Bh =================
+        // ================= MMA issuer: D = Al*Wh + Ah*Wl + Ah*Wh =================
         constexpr uint32_t idesc = make_idesc_bf16(128, T_TN, 0, 0);
-        const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
-        if (args.pro == PRO_PLANES) mbar_wait(abar, 0);
-        for (int kc = 0; kc < NK; ++kc) {
-            const int s = kc % T_WST;
-            mbar_wait(&full[s], (kc / T_WST) & 1);
+        for (int it = 0; it < total_it; ++it) {
+            const int s = it % T_NSTG, kb = it & 3;
+            mbar_wait(&full[s], (it / T_NSTG) & 1);
             tc_fence_after();
-            const uint32_t w_hi = smem_u32(sW + s * T_W_STAGE), w_lo = w_hi + T_W_PLANE;
+            const uint32_t a_hi = smem_u32(smem + s * T_STAGE), a_lo = a_hi + T_PLANE;
+            const uint32_t w_hi = a_hi + 2 * T_PLANE, w_lo = a_hi + 3 * T_PLANE;
+            const uint32_t d = tmem_base + (uint32_t)(it >> 2) * T_TN;
 #pragma unroll
             for (int k16 = 0; k16 < T_KC / 16; ++k16) {
-                const uint32_t aoff = kc * (128 * 128) + k16 * 32;
-                const uint64_t dah = make_smem_desc_sw128(a_hi + aoff, 16, 1024);
-                const uint64_t dal = make_smem_desc_sw128(a_lo + aoff, 16, 1024);
-                const uint64_t dbh = make_smem_desc_sw128(w_hi + k16 * 32, 16, 1024);
-                const uint64_t dbl = make_smem_desc_sw128(w_lo + k16 * 32, 16, 1024);
-                umma_bf16_ss(tmem_base, dal, dbh, idesc, (kc | k16) != 0);
-                umma_bf16_ss(tmem_base, dah, dbl, idesc, 1);
-                umma_bf16_ss(tmem_base, dah, dbh, idesc, 1);
+                const uint64_t dah = make_smem_desc_sw128(a_hi + k16 * 32, 16, 1024);
+                const uint64_t dal = make_smem_desc_sw128(a_lo + k16 * 32, 16, 1024);
+                const uint64_t dwh = make_smem_desc_sw128(w_hi + k16 * 32, 16, 1024);
+                const uint64_t dwl = make_smem_desc_sw128(w_lo + k16 * 32, 16, 1024);
+                umma_bf16_ss(d, dal, dwh, idesc, (kb | k16) != 0);
+                umma_bf16_ss(d, dah, dwl, idesc, 1);
+                umma_bf16_ss(d, dah, dwh, idesc, 1);
             }
             umma_commit(&empty[s]);
         }
@@ -278,127 +301,308 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     }
     __syncwarp();
 
-    // ================= epilogue (warps 2..5: thread = TMEM lane = kernel row) =================
-    const int grp = tile >> 1;
-    const int gi = grp < 1 ? grp : 1;
-    const float* ln = active ? g.ln[gi] : nullptr;
-    const uint32_t crank = tile & 1;
+    // ================= epilogue: warps 2..9, thread = (TMEM lane = kernel row, 64-column half) =================
     const bool epi = active && warp >= 2;
-    const int q = warp & 3;
+    const int q = warp & 3, hsel = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const bool rok = r < N;
     const size_t m = (size_t)b * N + (rok ? r : 0);
-    float y[T_TN];
-    float mean = 0.f, rstd = 1.f;
+    const uint32_t crank = has_ln ? cluster_ctarank() : 0u;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hsel * 64;
+    const int c0 = nb + hsel * 64;          // first output column of this thread
+    float y[64];
+
     if (epi) {
         mbar_wait(accfull, 0);
         tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < T_TN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) y[c0 + i] = __uint_as_float(v[i]);
+    }
+
+    if (MODE == MODE_GENERIC) {
+        const float* ln = nb < 256 ? g.ln0 : g.ln1;
+        const int act = nb < 256 ? g.act0 : g.act1;
+        const int cg = c0 & 255;            // column inside the 256-wide group
+        float mean = 0.f, rstd = 1.f;
+        if (epi) {
+            tmem_ld64(taddr, y);
+            if (args.ksplit == 1) {
+                if (g.bias0) add_vec64(y, g.bias0 + c0);
+                if (g.res && rok) add_vec64(y, g.res + m * g.ldr + c0);
+            }
         }
-        if (args.ksplit == 1) {
-            const float cnt = (g.count && rok) ? __ldg(g.count + m) : 0.f;
+        if (has_ln) {
+            cluster_wait();
+            if (epi) {
+                float mu, m2;
+                mean_m2_64(y, mu, m2);
+                mail.publish(0, (int)crank * 2 + hsel, r, mu, m2, 2);
+            }
+            cluster_arrive();
+            cluster_wait();
+        }
+        if (epi) {
+            if (has_ln) {
+                mail.combine(0, r, mean, rstd);
+                ln_apply64(y, mean, rstd, ln, cg);
+            }
+            act64(y, act);
+            if (g.Y && rok) {
+                float* dst = g.Y + ((size_t)split * args.R + m) * g.ldy + c0;
+                if ((g.ldy & 3) == 0 && c0 + 64 <= g.nstore) {
 #pragma unroll
-            for (int c = 0; c < T_TN; c += 4) {
-                const int col = nb + c;
-                if (col < g.Nout) {   // Nout is a multiple of 4
-                    if (g.bias) {
-                        const float4 t = ld4(g.bias + col);
-                        y[c] += t.x, y[c + 1] += t.y, y[c + 2] += t.z, y[c + 3] += t.w;
-                    }
-                    if (g.cbias) {
-                        const float4 t = ld4(g.cbias + col);
-                        y[c] += cnt * t.x, y[c + 1] += cnt * t.y, y[c + 2] += cnt * t.z, y[c + 3] += cnt * t.w;
-                    }
-                    if (g.res && rok) {
-                        const float4 t = ld4(g.res + m * g.ldr + col);
-                        y[c] += t.x, y[c + 1] += t.y, y[c + 2] += t.z, y[c + 3] += t.w;
+                    for (int c = 0; c < 64; c += 4)
+                        *reinterpret_cast<float4*>(dst + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c)
+                        if (c0 + c < g.nstore) dst[c] = y[c];
+                }
+            }
+            if (g.p_slot >= 0) {
+                const int slot = g.p_slot + (nb >> 8);
+                store_planes64(y, arena_row(args.arena, unit, slot, 0, r) + cg, arena_row(args.arena, unit, slot, 1, r) + cg,
+                               !rok);
+            }
+            if (g.xplanes && r < g.xrows) {
+                uint16_t* ph = g.xplanes + (((size_t)(g.xunit0 + b) * 2) * g.xrows + r) * 256 + c0;
+                store_planes64(y, ph, ph + (size_t)g.xrows * 256, false);
+            }
+        }
+    } else if (MODE == MODE_DUAL) {
+        // acc0 = dynamic_layer(pooled) (+ count * folded bias), acc1 = input_layer(kernel); kernel_updator.py:58-69
+        float z[64];
+        if (epi) {
+            tmem_ld64(taddr, y);
+            tmem_ld64(taddr + T_TN, z);
+            add_vec64(y, g.bias0 + c0);
+            if (g.cbias0) fma_vec64(y, (g.count && rok) ? __ldg(g.count + m) : 0.f, g.cbias0 + c0);
+            add_vec64(z, g.bias1 + c0);
+        }
+        if (!has_ln) {
+            if (epi) {   // gate_feats = input_in * param_in -> A operand of the gates
+#pragma unroll
+                for (int c = 0; c < 64; ++c) y[c] *= z[c];
+                store_planes64(y, arena_row(args.arena, unit, g.p_slot, 0, r) + c0,
+                               arena_row(args.arena, unit, g.p_slot, 1, r) + c0, !rok);
+            }
+        } else {
+            const int cg = c0 - 256;
+            cluster_wait();
+            if (epi) {
+                float mu, m2;
+                mean_m2_64(y, mu, m2);
+                mail.publish(0, (int)crank * 2 + hsel, r, mu, m2, 2);
+                mean_m2_64(z, mu, m2);
+                mail.publish(1, (int)crank * 2 + hsel, r, mu, m2, 2);
+            }
+            cluster_arrive();
+            cluster_wait();
+            if (epi) {   // param_out = norm_out(.), input_out = input_norm_out(.)   (:78-79)
+                float mean, rstd;
+                mail.combine(0, r, mean, rstd);
+                ln_apply64(y, mean, rstd, g.ln0, cg);
+                mail.combine(1, r, mean, rstd);
+                ln_apply64(z, mean, rstd, g.ln1, cg);
+                if (rok) {
+                    float* d0 = g.Y + m * 256 + cg;
+                    float* d1 = g.Y1 + m * 256 + cg;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 4) {
+                        *reinterpret_cast<float4*>(d0 + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+                        *reinterpret_cast<float4*>(d1 + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
                     }
                 }
             }
         }
-        if (ln) {
-            float s1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < T_TN; ++c) s1 += y[c];
-            s_mail[0][crank][r] = s1;
-            st_cluster_f32(&s_mail[0][crank][r], crank ^ 1u, s1);
+    } else {   // MODE_GATE: columns [0,64) = input_gate, [64,128) = update_gate of features 64*tile .. +63   (:73-88)
+        const int f0 = tile * 64;
+        float* xch = reinterpret_cast<float*>(smem);   // ring stage 0 is free once accfull has fired
+        if (epi) {
+            tmem_ld64(taddr, y);
+            add_vec64(y, g.bias0 + c0);
         }
-    }
-    if (ln) cluster_sync_all();   // every thread of both CTAs
-    if (epi && ln) {
-        mean = (s_mail[0][0][r] + s_mail[0][1][r]) * (1.f / 256.f);
-        float s2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < T_TN; ++c) s2 += (y[c] - mean) * (y[c] - mean);
-        s_mail[1][crank][r] = s2;
-        st_cluster_f32(&s_mail[1][crank][r], crank ^ 1u, s2);
-    }
-    if (ln) cluster_sync_all();
-    if (epi) {
-        if (ln) {
-            rstd = 1.f / sqrtf((s_mail[1][0][r] + s_mail[1][1][r]) * (1.f / 256.f) + U_LN_EPS);
-            const int cg = (tile & 1) * T_TN;   // column inside the 256-wide group
-#pragma unroll
-            for (int c = 0; c < T_TN; c += 4) {
-                const float4 ga = ld4(ln + cg + c), be = ld4(ln + 256 + cg + c);
-                y[c] = (y[c] - mean) * rstd * ga.x + be.x, y[c + 1] = (y[c + 1] - mean) * rstd * ga.y + be.y;
-                y[c + 2] = (y[c + 2] - mean) * rstd * ga.z + be.z, y[c + 3] = (y[c + 3] - mean) * rstd * ga.w + be.w;
-            }
+        cluster_wait();
+        if (epi) {
+            float mu, m2;
+            mean_m2_64(y, mu, m2);
+            mail.publish(hsel, (int)crank, r, mu, m2, 4);
         }
-        const int act = g.act[gi];
-        if (act == ACT_RELU) {
+        cluster_arrive();
+        cluster_wait();
+        if (epi) {
+            float mean, rstd;
+            mail.combine(hsel, r, mean, rstd);
+            ln_apply64(y, mean, rstd, hsel ? g.ln1 : g.ln0, f0);
+            act64(y, ACT_SIGMOID);
+            if (rok) {
+                const float* mul = (hsel ? g.mul1 : g.mul0) + m * 256 + f0;
 #pragma unroll
-            for (int c = 0; c < T_TN; ++c) y[c] = fmaxf(y[c], 0.f);
-        } else if (act == ACT_SIGMOID) {
-#pragma unroll
-            for (int c = 0; c < T_TN; ++c) y[c] = 1.f / (1.f + expf(-y[c]));
-        }
-        if (g.Y && rok) {
-            float* dst = g.Y + ((size_t)split * args.R + m) * g.ldy + nb;
-            if ((g.ldy & 3) == 0 && nb + T_TN <= g.nstore) {
-#pragma unroll
-                for (int c = 0; c < T_TN; c += 4)
-                    *reinterpret_cast<float4*>(dst + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < T_TN; ++c)
-                    if (nb + c < g.nstore) dst[c] = y[c];
-            }
-        }
-        if (g.planes && r < g.plane_rows) {
-            const size_t unit = (size_t)g.plane_unit0 + b;
-            uint16_t* ph = g.planes + ((unit * 2) * g.plane_rows + r) * g.plane_ld + nb;
-            uint16_t* pl = ph + (size_t)g.plane_rows * g.plane_ld;
-#pragma unroll
-            for (int c = 0; c < T_TN; c += 8) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float v0 = rok ? y[c + 2 * i] : 0.f, v1 = rok ? y[c + 2 * i + 1] : 0.f;
-                    const float h0 = bf16_round(v0), h1 = bf16_round(v1);
-                    hi[i] = pack_bf16x2(h0, h1);
-                    lo[i] = pack_bf16x2(v0 - h0, v1 - h1);
+                for (int c = 0; c < 64; c += 4) {
+                    const float4 t = ld4(mul + c);
+                    y[c] *= t.x, y[c + 1] *= t.y, y[c + 2] *= t.z, y[c + 3] *= t.w;
                 }
-                *reinterpret_cast<uint4*>(ph + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(pl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (hsel == 1) {
+#pragma unroll
+                for (int c = 0; c < 64; c += 4)
+                    *reinterpret_cast<float4*>(xch + r * T_XCH_LD + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+            }
+            epi_bar();
+            if (hsel == 0) {   // features = update_gate * param_out + input_gate * input_out
+#pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(xch + r * T_XCH_LD + c);
+                    y[c] += t.x, y[c + 1] += t.y, y[c + 2] += t.z, y[c + 3] += t.w;
+                }
+                store_planes64(y, arena_row(args.arena, unit, g.p_slot, 0, r) + f0,
+                               arena_row(args.arena, unit, g.p_slot, 1, r) + f0, !rok);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<T_TN>(tmem_base);
+    if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep: fp32 rows -> arena planes.
+//   job 0/1: pooled[branch] = sum over the S pooling partials (fixed order) -> SLOT_POOLED (+ count, job 0)
+//   job 2  : proposal_feat -> SLOT_INP of the mask branch
+//   job 3  : depth_proposal + proposal_feat (kernel_update_head.py:250) -> SLOT_INP of the depth branch
+// Also serves pf_kernel_updator (S = 1, two plain copies).  Thread = one float4 of one row.
+struct PrepArgs {
+    const float* src[4];     // job sources: partial base (jobs 0,1) or rows (jobs 2,3)
+    const float* add[4];     // optional second addend
+    int S[4];                // > 0: sum over S partials laid out [unit][S][N][256]
+    int unit0[4], slot[4];
+    const float* cntp;       // [B][S][N] (job 0 only) or null
+    float* count;
+    uint16_t* arena;
+    int B, N, njobs;
+};
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int job = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;   // (b, r, c4) with r < 128
+    const int c4 = idx & 63, r = (idx >> 6) & 127, b = idx >> 13;
+    if (b >= a.B) return;
+    const int N = a.N, S = a.S[job];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < N) {
+        if (S > 0) {
+            const float4* src = reinterpret_cast<const float4*>(a.src[job] + (((size_t)b * S) * N + r) * 256) + c4;
+            const size_t stride4 = (size_t)N * 64;
+            int s = 0;
+            for (; s + 6 <= S; s += 6) {
+                float4 v[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) v[i] = __ldg(src + (size_t)(s + i) * stride4);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc.x += v[i].x, acc.y += v[i].y, acc.z += v[i].z, acc.w += v[i].w;
+            }
+            for (; s < S; ++s) {
+                const float4 v = __ldg(src + (size_t)s * stride4);
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+            }
+            if (c4 == 0 && a.cntp && a.count && job == 0) {
+                float k = 0.f;
+                for (int s2 = 0; s2 < S; ++s2) k += __ldg(a.cntp + ((size_t)b * S + s2) * N + r);
+                a.count[b * N + r] = k;
+            }
+        } else {
+            acc = __ldg(reinterpret_cast<const float4*>(a.src[job] + ((size_t)b * N + r) * 256) + c4);
+            if (a.add[job]) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(a.add[job] + ((size_t)b * N + r) * 256) + c4);
+                acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+            }
+        }
+    }
+    const float h0 = bf16_round(acc.x), h1 = bf16_round(acc.y), h2 = bf16_round(acc.z), h3 = bf16_round(acc.w);
+    const int unit = a.unit0[job] + b;
+    uint16_t* ph = arena_row(a.arena, unit, a.slot[job], 0, r) + c4 * 4;
+    uint16_t* pl = arena_row(a.arena, unit, a.slot[job], 1, r) + c4 * 4;
+    *reinterpret_cast<uint2*>(ph) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    *reinterpret_cast<uint2*>(pl) = make_uint2(pack_bf16x2(acc.x - h0, acc.y - h1), pack_bf16x2(acc.z - h2, acc.w - h3));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ffn_norm(x + ffn2 split-K partials + b2) (kernel_update_head.py:271-272): warp = row, lane owns 8 columns.
+// Writes obj_feat / depth_feat_new (the stage's outputs, fp32) and SLOT_OBJ2 (A operand of the FC heads).
+struct SumLnArgs {
+    const float* part[2];    // [nsplit][R][256]
+    const float* res[2];     // [R][256]
+    const float* bias[2];
+    const float* ln[2];
+    float* out[2];
+    uint16_t* arena;
+    int B, N, R, nsplit;
+};
+__global__ void __launch_bounds__(256) sumln_kernel(const __grid_constant__ SumLnArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int br = blockIdx.y;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // b * 128 + r
+    const int lane = threadIdx.x & 31;
+    const int b = row >> 7, r = row & 127;
+    if (b >= a.B) return;
+    const int k0 = lane * 8;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 0.f;
+    if (r < a.N) {
+        const size_t m = (size_t)b * a.N + r;
+        float4 u[8], v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < a.nsplit) {
+                const float* pp = a.part[br] + ((size_t)s * a.R + m) * 256 + k0;
+                u[s] = ld4(pp), v[s] = ld4(pp + 4);
+            } else {
+                u[s] = v[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const float4 bu = ld4(a.bias[br] + k0), bv = ld4(a.bias[br] + k0 + 4);
+        const float4 ru = ld4(a.res[br] + m * 256 + k0), rv = ld4(a.res[br] + m * 256 + k0 + 4);
+        const float4 gu = ld4(a.ln[br] + k0), gv = ld4(a.ln[br] + k0 + 4);
+        const float4 eu = ld4(a.ln[br] + 256 + k0), ev = ld4(a.ln[br] + 256 + k0 + 4);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            x[0] += u[s].x, x[1] += u[s].y, x[2] += u[s].z, x[3] += u[s].w;
+            x[4] += v[s].x, x[5] += v[s].y, x[6] += v[s].z, x[7] += v[s].w;
+        }
+        x[0] += bu.x + ru.x, x[1] += bu.y + ru.y, x[2] += bu.z + ru.z, x[3] += bu.w + ru.w;
+        x[4] += bv.x + rv.x, x[5] += bv.y + rv.y, x[6] += bv.z + rv.z, x[7] += bv.w + rv.w;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += x[i];
+        const float mean = warp_sum(sum) * (1.f / 256.f);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sq += (x[i] - mean) * (x[i] - mean);
+        const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / 256.f) + U_LN_EPS);
+        const float gam[8] = {gu.x, gu.y, gu.z, gu.w, gv.x, gv.y, gv.z, gv.w};
+        const float bet[8] = {eu.x, eu.y, eu.z, eu.w, ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (x[i] - mean) * rstd * gam[i] + bet[i];
+        *reinterpret_cast<float4*>(a.out[br] + m * 256 + k0) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(a.out[br] + m * 256 + k0 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float h0 = bf16_round(x[2 * i]), h1 = bf16_round(x[2 * i + 1]);
+        hi[i] = pack_bf16x2(h0, h1);
+        lo[i] = pack_bf16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
+    }
+    const int unit = br * a.B + b;
+    *reinterpret_cast<uint4*>(arena_row(a.arena, unit, SLOT_OBJ2, 0, r) + k0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(arena_row(a.arena, unit, SLOT_OBJ2, 1, r) + k0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Inter-kernel self-attention of one (branch, image, head): softmax(q k^T / sqrt(32)) v over the N kernels of the
 // image (mmcv MultiheadAttention -> nn.MultiheadAttention, seq-first; kernel_update_head.py:259-260).
-// qkv [R][768] = [q | k | v]; out [R][256] (heads concatenated), before out_proj.
+// qkv [R][768] = [q | k | v] fp32; output (heads concatenated, before out_proj) -> SLOT_ATT planes.
 // 4 threads per query; keys are dealt to the 4 threads in blocks of 4 consecutive keys so that K^T rows and V rows
 // are read as float4 (4 FMAs per shared-memory load).  Two-pass softmax with the scores kept in registers, quad
 // reduction by shuffles.  Two CTAs per (branch, image, head) split the queries.
@@ -406,31 +610,41 @@ constexpr int ATT_NB = PF_MAX_N / 16;   // key blocks of 4 per thread (8 -> 32 k
 constexpr int ATT_QPC = PF_MAX_N / 2;   // queries per CTA
 __global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __restrict__ qkv0,
                                                                 const float* __restrict__ qkv1,
-                                                                float* __restrict__ out0, float* __restrict__ out1,
-                                                                int N) {
+                                                                uint16_t* __restrict__ arena, int B, int N) {
     __shared__ __align__(16) float s_kt[32][PF_MAX_N + 4];   // K transposed: [d][key]
     __shared__ __align__(16) float s_v[PF_MAX_N][36];
     const int h = blockIdx.x >> 1, half = blockIdx.x & 1, b = blockIdx.y;
     pdl_wait();
     pdl_launch_dependents();
     const float* qkv = (blockIdx.z == 0 ? qkv0 : qkv1) + (size_t)b * N * 768;
-    float* out = (blockIdx.z == 0 ? out0 : out1) + (size_t)b * N * 256;
-    for (int i = threadIdx.x; i < PF_MAX_N * 32; i += ATT_QPC * 4) {
-        const int n = i >> 5, d = i & 31;
-        const bool ok = n < N;
-        s_kt[d][n] = ok ? qkv[(size_t)n * 768 + 256 + h * 32 + d] : 0.f;
-        s_v[n][d] = ok ? qkv[(size_t)n * 768 + 512 + h * 32 + d] : 0.f;
+    {   // K and V of this head: 128 keys x 8 float4 each; all 8 loads of a thread are issued before the first store
+        float4 kk[4], vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + j * (ATT_QPC * 4);   // 0 .. 1023
+            const int n = i >> 3, d4 = i & 7;
+            const bool ok = n < N;
+            kk[j] = ok ? ld4(qkv + (size_t)n * 768 + 256 + h * 32 + d4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vv[j] = ok ? ld4(qkv + (size_t)n * 768 + 512 + h * 32 + d4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = threadIdx.x + j * (ATT_QPC * 4);
+            const int n = i >> 3, d4 = i & 7;
+            s_kt[d4 * 4][n] = kk[j].x, s_kt[d4 * 4 + 1][n] = kk[j].y, s_kt[d4 * 4 + 2][n] = kk[j].z, s_kt[d4 * 4 + 3][n] = kk[j].w;
+            *reinterpret_cast<float4*>(&s_v[n][d4 * 4]) = vv[j];
+        }
     }
-    __syncthreads();
     const int n = half * ATT_QPC + (threadIdx.x >> 2), part = threadIdx.x & 3;
     const int nq = n < N ? n : N - 1;   // keep whole quads alive for the shuffles
     float q[32];
     const float scale = 0.17677669529663687f;  // 1/sqrt(32), applied to q before q k^T as torch does
 #pragma unroll
     for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 t = *reinterpret_cast<const float4*>(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
+        const float4 t = ld4(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
         q[d4 * 4] = t.x * scale, q[d4 * 4 + 1] = t.y * scale, q[d4 * 4 + 2] = t.z * scale, q[d4 * 4 + 3] = t.w * scale;
     }
+    __syncthreads();
     float sc[ATT_NB][4];
     float mx = -INFINITY;
 #pragma unroll
@@ -473,32 +687,35 @@ __global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __r
         o[d] += __shfl_xor_sync(0xffffffffu, o[d], 1);
         o[d] += __shfl_xor_sync(0xffffffffu, o[d], 2);
     }
-    if (n < N) {
-        float* orow = out + (size_t)n * 256 + h * 32;
+    // lane `part` of the quad writes dims [8 part, 8 part + 8) of query row n as bf16 hi / lo (rows >= N: zeros)
+    const int unit = blockIdx.z * B + b;
+    uint16_t* ph = arena_row(arena, unit, SLOT_ATT, 0, n) + h * 32 + part * 8;
+    uint16_t* pl = arena_row(arena, unit, SLOT_ATT, 1, n) + h * 32 + part * 8;
+    uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp)   // lane `part` writes dims [8 part, 8 part + 8)
-            if (part == pp) {
-                *reinterpret_cast<float4*>(orow + pp * 8) =
-                    make_float4(o[pp * 8] * inv, o[pp * 8 + 1] * inv, o[pp * 8 + 2] * inv, o[pp * 8 + 3] * inv);
-                *reinterpret_cast<float4*>(orow + pp * 8 + 4) =
-                    make_float4(o[pp * 8 + 4] * inv, o[pp * 8 + 5] * inv, o[pp * 8 + 6] * inv, o[pp * 8 + 7] * inv);
+    for (int pp = 0; pp < 4; ++pp)
+        if (part == pp) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v0 = n < N ? o[pp * 8 + 2 * i] * inv : 0.f, v1 = n < N ? o[pp * 8 + 2 * i + 1] * inv : 0.f;
+                const float h0 = bf16_round(v0), h1 = bf16_round(v1);
+                hi[i] = pack_bf16x2(h0, h1);
+                lo[i] = pack_bf16x2(v0 - h0, v1 - h1);
             }
-    }
+        }
+    *reinterpret_cast<uint4*>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
-struct UpdateScratch {
-    float *params, *inp, *gate, *obj0, *qkv, *att, *obj1, *head, *part;
-    uint16_t* hid;   // bf16 hi/lo planes [B][2][128][ffn]
-};
 constexpr int kFfnSplit = 8;
 
-// tensor maps over the (long-lived) weight stacks are cached: encoding one costs ~1 us of host time per call otherwise
+// tensor maps over long-lived buffers (weight stacks, workspaces) are cached: encoding one costs ~1 us per call
 static int cached_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols) {
     struct Entry { const void* base; uint64_t rows, cols; CUtensorMap map; };
     static Entry cache[64];
-    static int n = 0;
+    static int n = 0, next = 0;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     for (int i = 0; i < n; ++i)
@@ -507,20 +724,29 @@ static int cached_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uin
             return PF_OK;
         }
     CUtensorMap m;
-    if (int e = make_tmap_bf16_2d(&m, base, rows, cols, cols, T_TN, T_KC)) return e;
-    if (n < 64) cache[n++] = Entry{base, rows, cols, m};
+    if (int e = make_tmap_bf16_2d(&m, base, rows, cols, cols, 128, T_KC)) return e;
+    cache[next] = Entry{base, rows, cols, m};
+    next = (next + 1) % 64;
+    if (n < 64) ++n;
     *out = m;
     return PF_OK;
 }
 
-static int launch_tc(const CUtensorMap& tw, const CUtensorMap& ta, TcArgs a, int max_nout, int nbranch, cudaStream_t st) {
-    const int tiles = (max_nout + T_TN - 1) / T_TN;
-    a.cluster = (tiles % 2 == 0) ? 2 : 1;
-    cudaError_t e = cudaFuncSetAttribute(tcgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "tcgemm smem attribute: %s", cudaGetErrorString(e));
+struct Maps {
+    CUtensorMap w256, wffn, a;
+};
+
+template <int MODE>
+static int launch_tc(const Maps& mp, const TcArgs& a, int tiles, int njobs, int cluster, cudaStream_t st) {
+    static bool attr_done = false;   // per-process; the attribute is a property of the function
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tcgemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+        if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "tcgemm smem attribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(tiles, a.B * a.ksplit, nbranch);
+    cfg.gridDim = dim3(tiles, a.B * a.ksplit, njobs);
     cfg.blockDim = dim3(T_THREADS);
     cfg.dynamicSmemBytes = T_SMEM;
     cfg.stream = st;
@@ -528,17 +754,32 @@ static int launch_tc(const CUtensorMap& tw, const CUtensorMap& ta, TcArgs a, int
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     attrs[1].id = cudaLaunchAttributeClusterDimension;
-    attrs[1].val.clusterDim.x = a.cluster, attrs[1].val.clusterDim.y = 1, attrs[1].val.clusterDim.z = 1;
+    attrs[1].val.clusterDim.x = cluster, attrs[1].val.clusterDim.y = 1, attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 2;
-    e = cudaLaunchKernelEx(&cfg, tcgemm_kernel, tw, ta, a);
-    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "tcgemm_kernel launch: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tcgemm_kernel<MODE>, mp.w256, mp.wffn, mp.a, a);
+    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "tcgemm_kernel<%d> launch: %s", MODE, cudaGetErrorString(e));
     count_launch();
     return PF_OK;
 }
 
-static int launch_attention(const float* q0, const float* q1, float* o0, float* o1, int B, int N, int nbranch,
-                            cudaStream_t st) {
+template <typename Args>
+static int launch_pdl(void (*kern)(Args), dim3 grid, dim3 block, const Args& a, const char* name, cudaStream_t st) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e));
+    count_launch();
+    return PF_OK;
+}
+
+static int launch_attention(const float* q0, const float* q1, uint16_t* arena, int B, int N, int nbranch, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(PF_HEADS * 2, B, nbranch);
@@ -549,30 +790,92 @@ static int launch_attention(const float* q0, const float* q1, float* o0, float* 
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, attention_kernel, q0, q1, o0, o1, N);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, attention_kernel, q0, q1, arena, B, N);
     if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "attention_kernel launch: %s", cudaGetErrorString(e));
     count_launch();
     return PF_OK;
 }
 
-static TcBranch blank() {
-    TcBranch g;
+static TcJob blank_job() {
+    TcJob g;
     memset(&g, 0, sizeof(g));
+    g.npass = 1;
+    g.p_slot = -1;
     return g;
 }
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-static size_t update_ws_bytes(int B, int N, int ffn) {
+static size_t arena_bytes(int units) { return align256((size_t)units * NSLOT * SLOT_ELEMS * 2); }
+static size_t update_ws_bytes(int B, int N) {
     const size_t R = (size_t)B * N;
-    size_t per_branch = R * (512 * 3 + 256 * 3 + 768 + 512) * 4 + (size_t)kFfnSplit * R * 256 * 4;
-    per_branch = align256(per_branch) + align256((size_t)B * 2 * 128 * ffn * 2);
-    return 2 * per_branch + align256(2 * R * 256 * 4) + align256(R * 4) + 256;
+    // per branch: pon, ion, obj0, obj1 [R][256]; qkv [R][768]; part [8][R][256]
+    const size_t per_branch = align256(R * (4 * 256 + 768 + kFfnSplit * 256) * 4);
+    return arena_bytes(2 * B) + 2 * per_branch + align256(R * 4) + 256;
+}
+
+struct BranchScratch {
+    float *pon, *ion, *obj0, *obj1, *qkv, *part;
+};
+
+static int make_maps(Maps* mp, const pf_stage_weights* w, const void* arena, int units) {
+    if (int e = cached_tmap_2d(&mp->w256, w->wstack256, (uint64_t)w->wstack256_rows, 256)) return e;
+    if (w->wstack_ffn) {
+        if (int e = cached_tmap_2d(&mp->wffn, w->wstack_ffn, (uint64_t)w->wstack_ffn_rows, (uint64_t)w->ffn_channels)) return e;
+    } else {
+        mp->wffn = mp->w256;
+    }
+    return cached_tmap_2d(&mp->a, arena, (uint64_t)units * NSLOT * 256, 256);
+}
+
+// KernelUpdator.forward for `nb` branches on arena units [unit0_of_branch(b) ...): launches dyn+inp, gates, fc.
+// fc output: fp32 rows into out[b] (may be null) and/or planes into slot out_slot (or -1).
+static int run_updator(const Maps& mp, const pf_stage_weights* w, uint16_t* arena, BranchScratch* sc, const float* count,
+                       float* const* out, int out_slot, int nbr, int B, int N, cudaStream_t st) {
+    const int R = B * N;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.arena = arena, a.B = B, a.N = N, a.R = R, a.ksplit = 1;
+    // 1. parameters = dynamic_layer(pooled') | input_feats = input_layer(kernel)   (kernel_updator.py:58-69, 78-79)
+    for (int b = 0; b < nbr; ++b) {
+        const pf_branch_weights& bw = w->br[b];
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 4, g.npass = 2;
+        g.pass[0] = TcPass{SLOT_POOLED, 0, bw.dyn_w, 512, 0};
+        g.pass[1] = TcPass{SLOT_INP, 0, bw.inp_w, 512, 0};
+        g.bias0 = bw.dyn_b, g.cbias0 = bw.dyn_cb, g.count = bw.dyn_cb ? count : nullptr, g.bias1 = bw.inp_b;
+        g.ln0 = bw.ln_norm_out, g.ln1 = bw.ln_input_norm_out;
+        g.Y = sc[b].pon, g.Y1 = sc[b].ion, g.p_slot = SLOT_GATEIN;
+        a.job[b] = g;
+    }
+    if (int e = launch_tc<MODE_DUAL>(mp, a, 4, nbr, 2, st)) return e;
+    // 2. gates + mixing   (:69-88)
+    for (int b = 0; b < nbr; ++b) {
+        const pf_branch_weights& bw = w->br[b];
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 4;
+        g.pass[0] = TcPass{SLOT_GATEIN, 0, bw.gate_w, 512, 0};
+        g.bias0 = bw.gate_b, g.ln0 = bw.ln_input_norm_in, g.ln1 = bw.ln_norm_in;
+        g.mul0 = sc[b].ion, g.mul1 = sc[b].pon, g.p_slot = SLOT_MIX;
+        a.job[b] = g;
+    }
+    if (int e = launch_tc<MODE_GATE>(mp, a, 4, nbr, 4, st)) return e;
+    // 3. relu(fc_norm(fc_layer(features)))   (:89-92)
+    for (int b = 0; b < nbr; ++b) {
+        const pf_branch_weights& bw = w->br[b];
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 2;
+        g.pass[0] = TcPass{SLOT_MIX, 0, bw.fc_w, 256, 0};
+        g.bias0 = bw.fc_b, g.ln0 = bw.ln_fc_norm, g.act0 = ACT_RELU;
+        g.Y = out[b], g.ldy = 256, g.nstore = 256, g.p_slot = out_slot;
+        a.job[b] = g;
+    }
+    return launch_tc<MODE_GENERIC>(mp, a, 2, nbr, 2, st);
 }
 
 }  // namespace pf
 
 extern "C" size_t pf_update_workspace_bytes(int B, int N, int ffn_channels) {
     if (B <= 0 || N <= 0 || ffn_channels <= 0) return 0;
-    return pf::update_ws_bytes(B, N, ffn_channels);
+    return pf::update_ws_bytes(B, N);
 }
 
 extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial, const float* cntp, int S,
@@ -588,201 +891,165 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
     PF_REQUIRE(ffn == kFfnSplit * T_K, PF_ERR_ARG, "pf_kernel_update: ffn_channels=%d (this build supports %d)", ffn, kFfnSplit * T_K);
     PF_REQUIRE(w->num_classes > 0 && w->num_classes <= PF_MAX_CLASSES, PF_ERR_ARG, "pf_kernel_update: num_classes=%d", w->num_classes);
     PF_REQUIRE(w->wstack256 && w->wstack_ffn, PF_ERR_ARG, "pf_kernel_update: weight stacks missing");
-    PF_REQUIRE(workspace_bytes >= update_ws_bytes(B, N, ffn), PF_ERR_WORKSPACE, "pf_kernel_update: workspace %zu < %zu",
-               workspace_bytes, update_ws_bytes(B, N, ffn));
+    PF_REQUIRE(workspace_bytes >= update_ws_bytes(B, N), PF_ERR_WORKSPACE, "pf_kernel_update: workspace %zu < %zu",
+               workspace_bytes, update_ws_bytes(B, N));
     PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PF_ERR_ALIGN, "pf_kernel_update: workspace not 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int R = B * N;
 
-    UpdateScratch sc[2];
     char* wp = static_cast<char*>(workspace);
+    uint16_t* arena = reinterpret_cast<uint16_t*>(wp);
+    wp += arena_bytes(2 * B);
+    BranchScratch sc[2];
     for (int b = 0; b < 2; ++b) {
         float* p = reinterpret_cast<float*>(wp);
-        sc[b].params = p, p += (size_t)R * 512;
-        sc[b].inp = p, p += (size_t)R * 512;
-        sc[b].gate = p, p += (size_t)R * 512;
+        sc[b].pon = p, p += (size_t)R * 256;
+        sc[b].ion = p, p += (size_t)R * 256;
         sc[b].obj0 = p, p += (size_t)R * 256;
-        sc[b].qkv = p, p += (size_t)R * 768;
-        sc[b].att = p, p += (size_t)R * 256;
         sc[b].obj1 = p, p += (size_t)R * 256;
-        sc[b].head = p, p += (size_t)R * 512;
+        sc[b].qkv = p, p += (size_t)R * 768;
         sc[b].part = p, p += (size_t)kFfnSplit * R * 256;
         wp += align256(reinterpret_cast<char*>(p) - wp);
-        sc[b].hid = reinterpret_cast<uint16_t*>(wp);
-        wp += align256((size_t)B * 2 * 128 * ffn * 2);
     }
-    float* pooled = reinterpret_cast<float*>(wp);   // [2][R][256]
-    wp += align256((size_t)2 * R * 256 * 4);
     float* count = reinterpret_cast<float*>(wp);    // [R]
-    const float* in_[2] = {obj_in, dep_in};
     float* out_[2] = {obj_out, dep_out};
 
-    CUtensorMap tw, tf, th;
-    if (int e = cached_tmap_2d(&tw, w->wstack256, (uint64_t)w->wstack256_rows, 256)) return e;
-    if (int e = cached_tmap_2d(&tf, w->wstack_ffn, (uint64_t)w->wstack_ffn_rows, (uint64_t)ffn)) return e;
-    // hid planes of both branches are adjacent in the workspace only up to alignment: one map per branch
-    CUtensorMap thid[2];
-    for (int b = 0; b < 2; ++b)
-        if (int e = make_tmap_bf16_3d(&thid[b], sc[b].hid, (uint64_t)B * 2, 128, (uint64_t)ffn, 128, 64)) return e;
-    (void)th;
+    Maps mp;
+    if (int e = make_maps(&mp, w, arena, 2 * B)) return e;
 
-    // 0. deterministic sum of the split-K pooling partials (fixed order)
-    if (int e = pf_pool_reduce(partial, cntp, pooled, count, B, N, 2, S, stream)) return e;
+    // 0. pooled' = sum of the split-K pooling partials (fixed order); kernel operands; depth kernel += mask kernel
+    {
+        PrepArgs p;
+        memset(&p, 0, sizeof(p));
+        p.arena = arena, p.B = B, p.N = N, p.njobs = 4, p.cntp = cntp, p.count = count;
+        p.src[0] = partial, p.S[0] = S, p.unit0[0] = 0, p.slot[0] = SLOT_POOLED;
+        p.src[1] = partial + (size_t)B * S * N * 256, p.S[1] = S, p.unit0[1] = B, p.slot[1] = SLOT_POOLED;
+        p.src[2] = obj_in, p.unit0[2] = 0, p.slot[2] = SLOT_INP;
+        p.src[3] = dep_in, p.add[3] = obj_in, p.unit0[3] = B, p.slot[3] = SLOT_INP;
+        if (int e = launch_pdl(prep_kernel, dim3((B * 128 * 64 + 255) / 256, 4), dim3(256), p, "prep_kernel", st)) return e;
+    }
+    // 1-3. KernelUpdator x2 -> obj0 (fp32 residual + SLOT_OBJ0 planes)
+    float* obj0_[2] = {sc[0].obj0, sc[1].obj0};
+    if (int e = run_updator(mp, w, arena, sc, count, obj0_, SLOT_OBJ0, 2, B, N, st)) return e;
 
     TcArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = B, a.N = N, a.R = R, a.ksplit = 1;
+    a.arena = arena, a.B = B, a.N = N, a.R = R, a.ksplit = 1;
 
-    // 1. parameters = dynamic_layer(pooled W_t^T + count b_t); param_out -> norm_out     (kernel_updator.py:58-62,78)
-    a.pro = PRO_PLAIN;
+    // 4. attention in-projection
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = pooled + (size_t)b * R * 256, g.ldx = 256, g.count = count;
-        g.w_row = bw.dyn_w, g.w_lo_off = 512, g.bias = bw.dyn_b, g.cbias = bw.dyn_cb;
-        g.ln[1] = bw.ln_norm_out;
-        g.Y = sc[b].params, g.ldy = 512, g.Nout = 512, g.nstore = 512;
-        a.br[b] = g;
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 6;
+        g.pass[0] = TcPass{SLOT_OBJ0, 0, bw.qkv_w, 768, 0};
+        g.bias0 = bw.qkv_b, g.Y = sc[b].qkv, g.ldy = 768, g.nstore = 768;
+        a.job[b] = g;
     }
-    if (int e = launch_tc(tw, tw, a, 512, 2, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC>(mp, a, 6, 2, 1, st)) return e;
 
-    // 2. input_feats = input_layer(kernel); depth kernel += mask kernel (kernel_update_head.py:250); input_out -> input_norm_out
-    a.pro = PRO_ADD;
+    // 5. softmax(q k^T) v per (branch, image, head) -> SLOT_ATT
+    if (int e = launch_attention(sc[0].qkv, sc[1].qkv, arena, B, N, 2, st)) return e;
+
+    // 6. attention_norm(x + out_proj(attn))
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = in_[b], g.ldx = 256;
-        if (b == 1) g.X2 = obj_in, g.ldx2 = 256;
-        g.w_row = bw.inp_w, g.w_lo_off = 512, g.bias = bw.inp_b;
-        g.ln[1] = bw.ln_input_norm_out;
-        g.Y = sc[b].inp, g.ldy = 512, g.Nout = 512, g.nstore = 512;
-        a.br[b] = g;
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 2;
+        g.pass[0] = TcPass{SLOT_ATT, 0, bw.out_w, 256, 0};
+        g.bias0 = bw.out_b, g.res = sc[b].obj0, g.ldr = 256, g.ln0 = bw.ln_attn;
+        g.Y = sc[b].obj1, g.ldy = 256, g.nstore = 256, g.p_slot = SLOT_OBJ1;
+        a.job[b] = g;
     }
-    if (int e = launch_tc(tw, tw, a, 512, 2, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC>(mp, a, 2, 2, 2, st)) return e;
 
-    // 3. gate_feats = input_in * param_in; [input_gate | update_gate] = sigmoid(LN(W g + b))   (:69,73-77)
-    a.pro = PRO_MUL;
+    // 7. FFN layer 1 + ReLU -> SLOT_HID0..7 (one slot per 256 hidden channels)
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = sc[b].inp, g.ldx = 512, g.X2 = sc[b].params, g.ldx2 = 512;
-        g.w_row = bw.gate_w, g.w_lo_off = 512, g.bias = bw.gate_b;
-        g.ln[0] = bw.ln_input_norm_in, g.ln[1] = bw.ln_norm_in;
-        g.act[0] = g.act[1] = ACT_SIGMOID;
-        g.Y = sc[b].gate, g.ldy = 512, g.Nout = 512, g.nstore = 512;
-        a.br[b] = g;
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = ffn / T_TN;
+        g.pass[0] = TcPass{SLOT_OBJ1, 0, bw.ffn1_w, ffn, 0};
+        g.bias0 = bw.ffn1_b, g.act0 = g.act1 = ACT_RELU, g.p_slot = SLOT_HID0;
+        a.job[b] = g;
     }
-    if (int e = launch_tc(tw, tw, a, 512, 2, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC>(mp, a, ffn / T_TN, 2, 1, st)) return e;
 
-    // 4. features = update_gate * param_out + input_gate * input_out; relu(fc_norm(fc_layer(.)))   (:86-91)
-    a.pro = PRO_MIX;
+    // 8. FFN layer 2, split-K over the 8 hidden slots -> fp32 partials
+    a.ksplit = kFfnSplit;
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = sc[b].gate + 256, g.ldx = 512, g.X2 = sc[b].params + 256, g.ldx2 = 512;
-        g.X3 = sc[b].gate, g.ldx3 = 512, g.X4 = sc[b].inp + 256, g.ldx4 = 512;
-        g.w_row = bw.fc_w, g.w_lo_off = 256, g.bias = bw.fc_b, g.ln[0] = bw.ln_fc_norm, g.act[0] = ACT_RELU;
-        g.Y = sc[b].obj0, g.ldy = 256, g.Nout = 256, g.nstore = 256;
-        a.br[b] = g;
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 2;
+        g.pass[0] = TcPass{SLOT_HID0, 1, bw.ffn2_w, 256, 0};
+        g.Y = sc[b].part, g.ldy = 256, g.nstore = 256;
+        a.job[b] = g;
     }
-    if (int e = launch_tc(tw, tw, a, 256, 2, st)) return e;
-
-    // 5. attention in-projection
-    a.pro = PRO_PLAIN;
-    for (int b = 0; b < 2; ++b) {
-        const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = sc[b].obj0, g.ldx = 256, g.w_row = bw.qkv_w, g.w_lo_off = 768, g.bias = bw.qkv_b;
-        g.Y = sc[b].qkv, g.ldy = 768, g.Nout = 768, g.nstore = 768;
-        a.br[b] = g;
-    }
-    if (int e = launch_tc(tw, tw, a, 768, 2, st)) return e;
-
-    // 6. softmax(q k^T) v per (branch, image, head)
-    if (int e = launch_attention(sc[0].qkv, sc[1].qkv, sc[0].att, sc[1].att, B, N, 2, st)) return e;
-
-    // 7. attention_norm(x + out_proj(attn))
-    for (int b = 0; b < 2; ++b) {
-        const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = sc[b].att, g.ldx = 256, g.w_row = bw.out_w, g.w_lo_off = 256, g.bias = bw.out_b;
-        g.res = sc[b].obj0, g.ldr = 256, g.ln[0] = bw.ln_attn;
-        g.Y = sc[b].obj1, g.ldy = 256, g.Nout = 256, g.nstore = 256;
-        a.br[b] = g;
-    }
-    if (int e = launch_tc(tw, tw, a, 256, 2, st)) return e;
-
-    // 8. FFN layer 1 + ReLU -> bf16 hi/lo planes (the A operand of layer 2)
-    for (int b = 0; b < 2; ++b) {
-        const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = sc[b].obj1, g.ldx = 256, g.w_row = bw.ffn1_w, g.w_lo_off = ffn, g.bias = bw.ffn1_b;
-        g.act[0] = g.act[1] = ACT_RELU;
-        g.Nout = ffn, g.nstore = ffn;
-        g.planes = sc[b].hid, g.plane_rows = 128, g.plane_ld = ffn, g.plane_unit0 = 0;
-        a.br[b] = g;
-    }
-    if (int e = launch_tc(tw, tw, a, ffn, 2, st)) return e;
-
-    // 9. FFN layer 2, split-K over kFfnSplit slabs of 256 -> fp32 partials.  One launch per branch (its own A map).
-    a.pro = PRO_PLANES, a.ksplit = kFfnSplit;
-    for (int b = 0; b < 2; ++b) {
-        const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.a_unit0 = 0, g.w_row = bw.ffn2_w, g.w_lo_off = 256;
-        g.Y = sc[b].part, g.ldy = 256, g.Nout = 256, g.nstore = 256;
-        a.br[0] = g;
-        if (int e = launch_tc(tf, thid[b], a, 256, 1, st)) return e;
-    }
+    if (int e = launch_tc<MODE_GENERIC>(mp, a, 2, 2, 1, st)) return e;
     a.ksplit = 1;
 
-    // 10. ffn_norm(x + sum of partials + b2) -> obj_feat / depth_feat_new (returned to the caller) in the prologue,
-    //     then cls_fcs / mask_fcs / depth_regs: Linear(no bias) + LN (+ ReLU except depth_regs)
-    a.pro = PRO_SUMLN;
+    // 9. ffn_norm(x + sum of partials + b2) -> obj_feat / depth_feat_new (returned to the caller) + SLOT_OBJ2
+    {
+        SumLnArgs s;
+        memset(&s, 0, sizeof(s));
+        s.arena = arena, s.B = B, s.N = N, s.R = R, s.nsplit = kFfnSplit;
+        for (int b = 0; b < 2; ++b) {
+            s.part[b] = sc[b].part, s.res[b] = sc[b].obj1, s.bias[b] = w->br[b].ffn2_b, s.ln[b] = w->br[b].ln_ffn;
+            s.out[b] = out_[b];
+        }
+        if (int e = launch_pdl(sumln_kernel, dim3(B * 128 / 8, 2), dim3(256), s, "sumln_kernel", st)) return e;
+    }
+
+    // 10. cls_fcs / mask_fcs / depth_regs: Linear(no bias) + LN (+ ReLU except depth_regs) -> SLOT_HEAD0 / SLOT_HEAD1
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.part = sc[b].part, g.nsplit = kFfnSplit, g.pbias = bw.ffn2_b, g.pres = sc[b].obj1, g.pln = bw.ln_ffn;
-        g.xout = out_[b];
-        g.w_row = bw.head_w, g.w_lo_off = (b == 0) ? 512 : 256;
-        g.ln[0] = bw.ln_head_a, g.ln[1] = bw.ln_head_b;
-        g.act[0] = g.act[1] = bw.head_relu ? ACT_RELU : ACT_NONE;
-        g.Nout = (b == 0) ? 512 : 256;
-        g.Y = sc[b].head, g.ldy = 512, g.nstore = g.Nout;
-        a.br[b] = g;
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = (b == 0) ? 4 : 2;
+        g.pass[0] = TcPass{SLOT_OBJ2, 0, bw.head_w, (b == 0) ? 512 : 256, 0};
+        g.ln0 = bw.ln_head_a, g.ln1 = bw.ln_head_b;
+        g.act0 = g.act1 = bw.head_relu ? ACT_RELU : ACT_NONE;
+        g.p_slot = (b == 0) ? SLOT_HEAD0 : SLOT_HEAD1;
+        a.job[b] = g;
     }
-    if (int e = launch_tc(tw, tw, a, 512, 2, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC>(mp, a, 4, 2, 2, st)) return e;
 
     // 11. fc_mask / fc_depth with feat_transform folded in -> dynamic kernels (bf16 hi/lo planes) + their logit bias
-    a.pro = PRO_PLAIN;
+    //     (one extra weight row), fc_cls
+    int nj = 0;
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
-        TcBranch g = blank();
-        g.X = sc[b].head + (b == 0 ? 256 : 0), g.ldx = 512, g.w_row = bw.kern_w, g.w_lo_off = 256, g.bias = bw.kern_b;
-        g.Y = kern ? kern + (size_t)b * R * 256 : nullptr, g.ldy = 256, g.Nout = 256, g.nstore = 256;
-        g.planes = kern_split, g.plane_rows = N, g.plane_ld = 256, g.plane_unit0 = b * B;
-        g.rowdot_w = bw.kb_w, g.rowdot_b = bw.kb_b, g.rowdot_out = kbias + (size_t)b * R;
-        a.br[b] = g;
+        TcJob g = blank_job();
+        g.unit0 = b * B, g.ntiles = 2;
+        g.pass[0] = TcPass{SLOT_HEAD1, 0, bw.kern_w, 256, 0};
+        g.bias0 = bw.kern_b;
+        g.Y = kern ? kern + (size_t)b * R * 256 : nullptr, g.ldy = 256, g.nstore = 256;
+        g.xplanes = kern_split, g.xrows = N, g.xunit0 = b * B;
+        a.job[nj++] = g;
+        TcJob k = blank_job();
+        k.unit0 = b * B, k.ntiles = 1;
+        k.pass[0] = TcPass{SLOT_HEAD1, 0, bw.kbrow_w, 128, 0};
+        k.bias0 = bw.kbrow_b;
+        k.Y = kbias + (size_t)b * R, k.ldy = 1, k.nstore = 1;
+        a.job[nj++] = k;
     }
-    if (int e = launch_tc(tw, tw, a, 256, 2, st)) return e;
-
-    // 12. fc_cls (mask branch only)
     if (cls_out) {
         const pf_branch_weights& bw = w->br[0];
-        TcBranch g = blank();
-        g.X = sc[0].head, g.ldx = 512, g.w_row = bw.cls_w, g.w_lo_off = 128, g.bias = bw.cls_b;
-        g.act[0] = g.act[1] = cls_sigmoid ? ACT_SIGMOID : ACT_NONE;
-        g.Y = cls_out, g.ldy = w->num_classes, g.Nout = PF_MAX_CLASSES, g.nstore = w->num_classes;
-        a.br[0] = g;
-        if (int e = launch_tc(tw, tw, a, PF_MAX_CLASSES, 1, st)) return e;
+        TcJob g = blank_job();
+        g.unit0 = 0, g.ntiles = 1;
+        g.pass[0] = TcPass{SLOT_HEAD0, 0, bw.cls_w, 128, 0};
+        g.bias0 = bw.cls_b, g.act0 = cls_sigmoid ? ACT_SIGMOID : ACT_NONE;
+        g.Y = cls_out, g.ldy = w->num_classes, g.nstore = w->num_classes;
+        a.job[nj++] = g;
     }
-    return PF_OK;
+    return launch_tc<MODE_GENERIC>(mp, a, 2, nj, 1, st);
 }
 
-extern "C" size_t pf_updator_workspace_bytes(int R) { return R > 0 ? (size_t)R * 1536 * sizeof(float) + 256 : 0; }
+extern "C" size_t pf_updator_workspace_bytes(int R) {
+    if (R <= 0) return 0;
+    const int units = (R + 127) / 128;
+    return pf::arena_bytes(units) + pf::align256((size_t)R * 512 * sizeof(float)) + 256;
+}
 
 // KernelUpdator.forward on its own (polyphonic/funcs/kernel_updator.py:55-93): no feat_transform fold, one branch.
-// Rows are processed in groups of <= 128 ("images" of N = 128 rows).
+// Rows are processed in groups of <= 128 ("images" of N = 128 rows); a ragged tail is a second launch set.
 extern "C" int pf_kernel_updator(const pf_stage_weights* w, const float* update_feature, const float* input_feature,
                                  float* out, void* workspace, size_t workspace_bytes, int R, void* stream) {
     using namespace pf;
@@ -791,60 +1058,36 @@ extern "C" int pf_kernel_updator(const pf_stage_weights* w, const float* update_
     PF_REQUIRE(R > 0 && w->wstack256, PF_ERR_ARG, "pf_kernel_updator: R=%d", R);
     PF_REQUIRE(workspace_bytes >= pf_updator_workspace_bytes(R), PF_ERR_WORKSPACE, "pf_kernel_updator: workspace %zu < %zu",
                workspace_bytes, pf_updator_workspace_bytes(R));
-    PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(update_feature) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(input_feature) & 15) == 0,
-               PF_ERR_ALIGN, "pf_kernel_updator: pointers must be 16-byte aligned");
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(update_feature) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(input_feature) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               PF_ERR_ALIGN, "pf_kernel_updator: workspace must be 256-byte, tensors 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const pf_branch_weights* bw = &w->br[0];
-    CUtensorMap tw;
-    if (int e = cached_tmap_2d(&tw, w->wstack256, (uint64_t)w->wstack256_rows, 256)) return e;
-    float* params = static_cast<float*>(workspace);
-    float* inp = params + (size_t)R * 512;
-    float* gate = inp + (size_t)R * 512;
-    // groups of 128 rows; the last group may be ragged: run it as a second launch set with its own N
+    const int units = (R + 127) / 128;
+    uint16_t* arena = static_cast<uint16_t*>(workspace);
+    float* pon = reinterpret_cast<float*>(static_cast<char*>(workspace) + arena_bytes(units));
+    float* ion = pon + (size_t)R * 256;
+    Maps mp;
+    if (int e = make_maps(&mp, w, arena, units)) return e;
     for (int r0 = 0; r0 < R;) {
         const int full_groups = (R - r0) / 128;
         const int Bg = full_groups > 0 ? full_groups : 1;
         const int Ng = full_groups > 0 ? 128 : (R - r0);
-        const int Rg = Bg * Ng;
-        TcArgs a;
-        memset(&a, 0, sizeof(a));
-        a.B = Bg, a.N = Ng, a.R = Rg, a.ksplit = 1;
-        TcBranch g;
-
-        a.pro = PRO_PLAIN;
-        g = blank();
-        g.X = update_feature + (size_t)r0 * 256, g.ldx = 256, g.w_row = bw->dyn_w, g.w_lo_off = 512, g.bias = bw->dyn_b;
-        g.ln[1] = bw->ln_norm_out;
-        g.Y = params + (size_t)r0 * 512, g.ldy = 512, g.Nout = 512, g.nstore = 512;
-        a.br[0] = g;
-        if (int e = launch_tc(tw, tw, a, 512, 1, st)) return e;
-
-        g = blank();
-        g.X = input_feature + (size_t)r0 * 256, g.ldx = 256, g.w_row = bw->inp_w, g.w_lo_off = 512, g.bias = bw->inp_b;
-        g.ln[1] = bw->ln_input_norm_out;
-        g.Y = inp + (size_t)r0 * 512, g.ldy = 512, g.Nout = 512, g.nstore = 512;
-        a.br[0] = g;
-        if (int e = launch_tc(tw, tw, a, 512, 1, st)) return e;
-
-        a.pro = PRO_MUL;
-        g = blank();
-        g.X = inp + (size_t)r0 * 512, g.ldx = 512, g.X2 = params + (size_t)r0 * 512, g.ldx2 = 512;
-        g.w_row = bw->gate_w, g.w_lo_off = 512, g.bias = bw->gate_b;
-        g.ln[0] = bw->ln_input_norm_in, g.ln[1] = bw->ln_norm_in, g.act[0] = g.act[1] = ACT_SIGMOID;
-        g.Y = gate + (size_t)r0 * 512, g.ldy = 512, g.Nout = 512, g.nstore = 512;
-        a.br[0] = g;
-        if (int e = launch_tc(tw, tw, a, 512, 1, st)) return e;
-
-        a.pro = PRO_MIX;
-        g = blank();
-        g.X = gate + (size_t)r0 * 512 + 256, g.ldx = 512, g.X2 = params + (size_t)r0 * 512 + 256, g.ldx2 = 512;
-        g.X3 = gate + (size_t)r0 * 512, g.ldx3 = 512, g.X4 = inp + (size_t)r0 * 512 + 256, g.ldx4 = 512;
-        g.w_row = bw->fc_w, g.w_lo_off = 256, g.bias = bw->fc_b, g.ln[0] = bw->ln_fc_norm, g.act[0] = ACT_RELU;
-        g.Y = out + (size_t)r0 * 256, g.ldy = 256, g.Nout = 256, g.nstore = 256;
-        a.br[0] = g;
-        if (int e = launch_tc(tw, tw, a, 256, 1, st)) return e;
-        r0 += Rg;
+        const int u0 = r0 / 128;
+        uint16_t* ar = arena + (size_t)u0 * NSLOT * SLOT_ELEMS;   // this group's units start at arena unit 0 of `ar`
+        Maps mg = mp;
+        if (int e = cached_tmap_2d(&mg.a, ar, (uint64_t)Bg * NSLOT * 256, 256)) return e;
+        PrepArgs p;
+        memset(&p, 0, sizeof(p));
+        p.arena = ar, p.B = Bg, p.N = Ng, p.njobs = 2;
+        p.src[0] = update_feature + (size_t)r0 * 256, p.slot[0] = SLOT_POOLED;
+        p.src[1] = input_feature + (size_t)r0 * 256, p.slot[1] = SLOT_INP;
+        if (int e = launch_pdl(prep_kernel, dim3((Bg * 128 * 64 + 255) / 256, 2), dim3(256), p, "prep_kernel", st)) return e;
+        BranchScratch sc;
+        memset(&sc, 0, sizeof(sc));
+        sc.pon = pon + (size_t)r0 * 256, sc.ion = ion + (size_t)r0 * 256;
+        float* o = out + (size_t)r0 * 256;
+        if (int e = run_updator(mg, w, ar, &sc, nullptr, &o, -1, 1, Bg, Ng, st)) return e;
+        r0 += Bg * Ng;
     }
     return PF_OK;
 }

@@ -33,6 +33,15 @@ def round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def gate_interleave_index():
+    """Packed row order of the concatenated [input_gate; update_gate] (512 rows): blocks of 64 alternate between the
+    two gates so that one 128-column GEMM tile holds both gates of the same 64 features (pf_decoder.h)."""
+    idx = []
+    for t in range(PF_C // 64):
+        idx += list(range(64 * t, 64 * t + 64)) + list(range(PF_C + 64 * t, PF_C + 64 * t + 64))
+    return torch.tensor(idx, dtype=torch.long)
+
+
 def _split_planes(w64, pad_rows):
     """fp64 [out][in] -> bf16 [2*pad_rows][in]: hi plane (bf16(w)) then lo plane (bf16(w - hi)), rows zero-padded."""
     w32 = w64.to(torch.float32)
@@ -69,7 +78,7 @@ class _Packer:
         return off
 
     def finish(self, device, ffn_channels):
-        flat = torch.zeros(max(self.nvec, 64), dtype=torch.float32)
+        flat = torch.zeros(self.nvec + 128, dtype=torch.float32)   # slack: kernels read whole 64-float groups
         for off, v in self.vecs:
             flat[off:off + v.numel()] = v
         self.flat = flat.to(device)
@@ -86,7 +95,8 @@ class PackedStage:
     (``views``: the folded fp32 parameters, used by the CPU algebra test), then matrices are split into bf16 hi/lo.
     """
 
-    MATS = ('dyn_w', 'inp_w', 'gate_w', 'fc_w', 'qkv_w', 'out_w', 'ffn1_w', 'head_w', 'cls_w', 'kern_w')
+    MATS = ('dyn_w', 'inp_w', 'gate_w', 'fc_w', 'qkv_w', 'out_w', 'ffn1_w', 'head_w', 'cls_w', 'kern_w', 'kbrow_w')
+    PERMUTED = ('gate_w', 'gate_b')     # stored in gate_interleave_index() order; ``views`` keep the logical order
 
     def __init__(self, sd, device, num_classes, ffn_channels):
         f64 = {k: v.detach().to('cpu', torch.float64) for k, v in sd.items()}
@@ -122,6 +132,8 @@ class PackedStage:
                 ln_ffn=ln('ffn_norm%s' % sfx),
                 kern_w=Wt.t() @ Wfc, kern_b=Wt.t() @ bfc, kb_w=Wfc.t() @ bt,
             )
+            p['kbrow_w'] = p['kb_w'].reshape(1, PF_C)
+            p['kbrow_b'] = (bfc @ bt).reshape(1)
             assert p['ffn1_w'].shape == (ffn_channels, PF_C)
             if bi == 0:
                 p['head_w'] = torch.cat([f64['cls_fcs.0.weight'], f64['mask_fcs.0.weight']])
@@ -139,8 +151,11 @@ class PackedStage:
 
         pk = _Packer()
         rows, vecs = {}, {}
+        perm = gate_interleave_index()
         for bi, (p, _) in parts.items():
             for k, v in p.items():
+                if k in self.PERMUTED:
+                    v = v[perm]
                 if k in self.MATS:
                     rows[(bi, k)] = pk.add_matrix(v)
                 elif k == 'ffn2_w':
@@ -166,7 +181,6 @@ class PackedStage:
                 setattr(bw, name, rows.get((bi, name), 0))
             for name in BranchWeights._PTRS:
                 setattr(bw, name, base + 4 * vecs[(bi, name)] if (bi, name) in vecs else None)
-            bw.kb_b = kb_b
             bw.head_relu = 1 if bi == 0 else 0
 
 
@@ -180,11 +194,12 @@ class PackedUpdator:
             return torch.stack([f[name + '.weight'], f[name + '.bias']])
 
         pk = _Packer()
+        perm = gate_interleave_index()
         rows = dict(dyn_w=pk.add_matrix(f['dynamic_layer.weight']), inp_w=pk.add_matrix(f['input_layer.weight']),
-                    gate_w=pk.add_matrix(torch.cat([f['input_gate.weight'], f['update_gate.weight']])),
+                    gate_w=pk.add_matrix(torch.cat([f['input_gate.weight'], f['update_gate.weight']])[perm]),
                     fc_w=pk.add_matrix(f['fc_layer.weight']))
         vecs = dict(dyn_b=pk.add_vector(f['dynamic_layer.bias']), inp_b=pk.add_vector(f['input_layer.bias']),
-                    gate_b=pk.add_vector(torch.cat([f['input_gate.bias'], f['update_gate.bias']])),
+                    gate_b=pk.add_vector(torch.cat([f['input_gate.bias'], f['update_gate.bias']])[perm]),
                     ln_input_norm_in=pk.add_vector(ln('input_norm_in')), ln_norm_in=pk.add_vector(ln('norm_in')),
                     ln_norm_out=pk.add_vector(ln('norm_out')), ln_input_norm_out=pk.add_vector(ln('input_norm_out')),
                     fc_b=pk.add_vector(f['fc_layer.bias']), ln_fc_norm=pk.add_vector(ln('fc_norm')))
