@@ -184,6 +184,10 @@ int pf_decoder_forward(const pf_stage_weights* stages_host, int n_stages, const 
                        float* scaled_out, void* workspace, size_t workspace_bytes, int B, int N, int H, int W, int HWp,
                        int flags, void* stream);
 
+/* debug only: int64 device buffer [16 + 16*capacity], zero-filled by the caller; CTA (0,0,0) of every GEMM launch of
+ * the small-N block appends 16 %globaltimer samples (see scripts/k2_timeline.py).  NULL switches it off. */
+int pf_debug_timeline(long long* device_buffer);
+
 /* number of kernels the last call on this thread launched (for bench.py's gpu_launches) */
 int pf_last_launch_count(void);
 

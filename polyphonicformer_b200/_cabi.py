@@ -49,6 +49,7 @@ _SIGS = {
     'pf_version': (c_int, []),
     'pf_last_error_string': (c_char_p, []),
     'pf_last_launch_count': (c_int, []),
+    'pf_debug_timeline': (c_int, [c_void_p]),
     'pf_cast_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_binarise': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_pool_splits': (c_int, [c_int, c_int, c_int]),

@@ -16,10 +16,11 @@
 //     first stages are issued BEFORE griddepcontrol.wait (programmatic dependent launch), the activation boxes after;
 //   * a CTA runs 1 or 2 "passes" of K = 256 into separate TMEM accumulators (MODE_DUAL: dynamic_layer and
 //     input_layer of the same output columns, so their product is formed in the epilogue);
-//   * epilogue: 8 warps, thread = (row, 64-column half): bias / count-bias / residual, LayerNorm over the 256-wide
-//     group (per-thread (mean, M2) over 64 columns merged across the halves and the CTAs of the cluster through
-//     DSMEM, one cluster barrier), ReLU / sigmoid, gate mixing, then fp32 rows and/or bf16 hi/lo planes.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+//   * epilogue: 16 warps.  Phase 1, thread = (row, 32-column quarter): bias / count-bias, LayerNorm piece statistics
+//     ((mean, M2) over 32 columns, merged across the quarters and the CTAs of the cluster through DSMEM with one
+//     cluster barrier), values staged in shared memory.  Phase 2, warp = 8 rows x 128 columns: normalise, ReLU /
+//     sigmoid, gate mixing, then fp32 rows and/or bf16 hi/lo planes with fully coalesced global accesses.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = epilogue.
 // 12 launches per stage: prep, dyn+inp, gates, fc, qkv, attention, out-proj, ffn1, ffn2 (split-K), sum+LN, heads,
 // kernels+cls.  This block is latency / weight-streaming bound, not roofline bound; see DESIGN.md.
 #include <string.h>
@@ -31,7 +32,7 @@
 
 namespace pf {
 
-constexpr int T_THREADS = 320;
+constexpr int T_THREADS = 576;
 constexpr int T_TN = 128;                       // output columns per CTA (per pass)
 constexpr int T_KC = 64;                        // K per ring stage
 constexpr int T_K = 256;                        // K per pass
@@ -40,10 +41,12 @@ constexpr int T_PLANE = 128 * T_KC * 2;         // 16384: one [128][64] bf16 box
 constexpr int T_STAGE = 4 * T_PLANE;            // A hi | A lo | W hi | W lo
 constexpr int T_BAR_OFF = T_NSTG * T_STAGE;     // 196608
 constexpr int T_MAIL_OFF = T_BAR_OFF + 256;
-constexpr int T_MAIL_BYTES = 2 * 4 * 128 * 8;   // [array][source][row] x (mean, M2)
-constexpr int T_SMEM_USED = T_MAIL_OFF + T_MAIL_BYTES;
+constexpr int T_MAIL_BYTES = 2 * 8 * 128 * 8;   // [array][source][row] x (mean, M2)
+constexpr int T_VEC_OFF = T_MAIL_OFF + T_MAIL_BYTES;   // per-column parameter vectors of this tile: 8 x [128] floats
+enum { V_BIAS0 = 0, V_CBIAS0, V_BIAS1, V_GA0, V_BE0, V_GA1, V_BE1, V_COUNT };
+constexpr int T_SMEM_USED = T_VEC_OFF + V_COUNT * 128 * 4;
 constexpr int T_SMEM = T_SMEM_USED + 1024;      // slack for the 1024-byte alignment of the ring
-constexpr int T_XCH_LD = 68;                    // floats per row of the gate exchange tile (16-byte rows, no conflicts)
+constexpr int T_SLD = 132;                      // floats per row of the epilogue staging tiles (conflict-free float4 rows)
 constexpr float U_LN_EPS = 1e-5f;               // nn.LayerNorm default (mmcv build_norm_layer(dict(type='LN')))
 
 enum { SLOT_POOLED = 0, SLOT_INP, SLOT_GATEIN, SLOT_MIX, SLOT_OBJ0, SLOT_ATT, SLOT_OBJ1, SLOT_HID0,
@@ -105,109 +108,154 @@ __device__ __forceinline__ void st_cluster_f32x2(const void* local_smem_ptr, uin
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps
 
-// 64 fp32 accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&y)[64]) {
-    uint32_t v0[32], v1[32];
-    tmem_ld32(taddr, v0);
-    tmem_ld32(taddr + 32, v1);
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&y)[32]) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v0[i]), y[32 + i] = __uint_as_float(v1[i]);
+    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
 }
-__device__ __forceinline__ void add_vec64(float (&y)[64], const float* __restrict__ v) {   // v: same address in all lanes
+__device__ __forceinline__ void add_vec32(float (&y)[32], const float* v) {   // v: shared memory, same address in all lanes
 #pragma unroll
-    for (int c = 0; c < 64; c += 4) {
-        const float4 t = ld4(v + c);
+    for (int c = 0; c < 32; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(v + c);
         y[c] += t.x, y[c + 1] += t.y, y[c + 2] += t.z, y[c + 3] += t.w;
     }
 }
-__device__ __forceinline__ void fma_vec64(float (&y)[64], float s, const float* __restrict__ v) {
+__device__ __forceinline__ void fma_vec32(float (&y)[32], float s, const float* v) {
 #pragma unroll
-    for (int c = 0; c < 64; c += 4) {
-        const float4 t = ld4(v + c);
+    for (int c = 0; c < 32; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(v + c);
         y[c] += s * t.x, y[c + 1] += s * t.y, y[c + 2] += s * t.z, y[c + 3] += s * t.w;
     }
 }
-__device__ __forceinline__ void mean_m2_64(const float (&y)[64], float& mean, float& m2) {
-    float s = 0.f;
+// (mean, M2) of 32 register values: 8 independent partial sums, two passes
+__device__ __forceinline__ void stats32(const float (&y)[32], float& mean, float& m2) {
+    float p[8];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) s += y[c];
-    mean = s * (1.f / 64.f);
-    float q = 0.f;
+    for (int k = 0; k < 8; ++k) p[k] = y[k];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) q += (y[c] - mean) * (y[c] - mean);
+    for (int c = 8; c < 32; ++c) p[c & 7] += y[c];
+    mean = (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) * (1.f / 32.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[k] = (y[k] - mean) * (y[k] - mean);
+#pragma unroll
+    for (int c = 8; c < 32; ++c) p[c & 7] += (y[c] - mean) * (y[c] - mean);
+    m2 = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+__device__ __forceinline__ void store32(float* d, const float (&y)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(d + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+}
+__device__ __forceinline__ void load32(const float* d, float (&y)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(d + c);
+        y[c] = t.x, y[c + 1] = t.y, y[c + 2] = t.z, y[c + 3] = t.w;
+    }
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+// (mean, M2) of the 4 * LANES values held by a group of LANES lanes (two-pass, in registers)
+template <int LANES>
+__device__ __forceinline__ void stats4(float4 v, float inv_n, float& mean, float& m2) {
+    float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s * inv_n;
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    float q = (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     m2 = q;
 }
-__device__ __forceinline__ void ln_apply64(float (&y)[64], float mean, float rstd, const float* __restrict__ ln, int col) {
-#pragma unroll
-    for (int c = 0; c < 64; c += 4) {
-        const float4 ga = ld4(ln + col + c), be = ld4(ln + 256 + col + c);
-        y[c] = (y[c] - mean) * rstd * ga.x + be.x, y[c + 1] = (y[c + 1] - mean) * rstd * ga.y + be.y;
-        y[c + 2] = (y[c + 2] - mean) * rstd * ga.z + be.z, y[c + 3] = (y[c + 3] - mean) * rstd * ga.w + be.w;
-    }
+__device__ __forceinline__ float4 ln4(float4 v, float mean, float rstd, float4 ga, float4 be) {
+    return make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y,
+                       (v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w);
 }
-__device__ __forceinline__ void act64(float (&y)[64], int act) {
-    if (act == ACT_RELU) {
-#pragma unroll
-        for (int c = 0; c < 64; ++c) y[c] = fmaxf(y[c], 0.f);
-    } else if (act == ACT_SIGMOID) {
-#pragma unroll
-        for (int c = 0; c < 64; ++c) y[c] = 1.f / (1.f + expf(-y[c]));
-    }
+__device__ __forceinline__ float4 act4(float4 v, int act) {
+    if (act == ACT_RELU) return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    if (act == ACT_SIGMOID)
+        return make_float4(1.f / (1.f + expf(-v.x)), 1.f / (1.f + expf(-v.y)), 1.f / (1.f + expf(-v.z)),
+                           1.f / (1.f + expf(-v.w)));
+    return v;
 }
-// 64 values -> bf16 hi / lo, 128 contiguous bytes in each plane
-__device__ __forceinline__ void store_planes64(const float (&y)[64], uint16_t* hi_ptr, uint16_t* lo_ptr, bool zero) {
-#pragma unroll
-    for (int c = 0; c < 64; c += 8) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float v0 = zero ? 0.f : y[c + 2 * i], v1 = zero ? 0.f : y[c + 2 * i + 1];
-            const float h0 = bf16_round(v0), h1 = bf16_round(v1);
-            hi[i] = pack_bf16x2(h0, h1);
-            lo[i] = pack_bf16x2(v0 - h0, v1 - h1);
-        }
-        *reinterpret_cast<uint4*>(hi_ptr + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(lo_ptr + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
+// 4 values -> bf16 hi / lo, 8 contiguous bytes in each plane
+__device__ __forceinline__ void store_planes4(float4 v, uint16_t* hi_ptr, uint16_t* lo_ptr) {
+    const float h0 = bf16_round(v.x), h1 = bf16_round(v.y), h2 = bf16_round(v.z), h3 = bf16_round(v.w);
+    *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    *reinterpret_cast<uint2*>(lo_ptr) = make_uint2(pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
 }
 __device__ __forceinline__ uint16_t* arena_row(uint16_t* arena, int unit, int slot, int plane, int r) {
     return arena + ((size_t)unit * NSLOT + slot) * SLOT_ELEMS + ((size_t)plane * 128 + r) * 256;
 }
 
-// LayerNorm statistics of a 256-wide group held as 4 x 64 columns by (2 halves x 2 CTAs) or (1 half x 4 CTAs):
-// every holder publishes (mean, M2) of its 64 columns into mailbox[arr][src][row] of every CTA of the cluster.
+// LayerNorm statistics of a 256-wide group held as 8 pieces of 32 columns by (4 quarters x 2 CTAs) or (2 quarters x
+// 4 CTAs): every holder publishes (mean, M2) of its piece into mailbox[arr][src][row] of every CTA of the cluster
+// (DSMEM stores); after one cluster barrier each CTA merges the pieces (Chan et al.), which is as stable as a
+// two-pass LayerNorm.
 struct Mail {
-    float2 (*box)[4][128];
+    float2 (*box)[8][128];
     __device__ __forceinline__ void publish(int arr, int src, int r, float mean, float m2, int csize) const {
         for (int k = 0; k < csize; ++k) st_cluster_f32x2(&box[arr][src][r], (uint32_t)k, mean, m2);
     }
     __device__ __forceinline__ void combine(int arr, int r, float& mean, float& rstd) const {
-        const float2 a = box[arr][0][r], b = box[arr][1][r], c = box[arr][2][r], d = box[arr][3][r];
-        mean = (a.x + b.x + c.x + d.x) * 0.25f;
-        const float m2 = a.y + b.y + c.y + d.y +
-                         64.f * ((a.x - mean) * (a.x - mean) + (b.x - mean) * (b.x - mean) + (c.x - mean) * (c.x - mean) +
-                                 (d.x - mean) * (d.x - mean));
-        rstd = 1.f / sqrtf(m2 * (1.f / 256.f) + U_LN_EPS);
+        float2 p[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = box[arr][k][r];
+        mean = (((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x))) * 0.125f;
+        float m2 = 0.f, dv = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m2 += p[k].y, dv += (p[k].x - mean) * (p[k].x - mean);
+        rstd = 1.f / sqrtf((m2 + 32.f * dv) * (1.f / 256.f) + U_LN_EPS);
     }
 };
+
+// Optional in-kernel timeline (pf_debug_timeline): CTA (0,0,0) of every tcgemm launch appends 16 clock samples.
+__device__ long long* g_dbg = nullptr;
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG(i) do { if (dbg) dbg[i] = gtime(); } while (0)
+// block (0,0,0), thread 0 of the helper kernels: claim a record, tag it
+__device__ __forceinline__ long long* dbg_claim(int tag) {
+    if (!g_dbg || blockIdx.x || blockIdx.y || blockIdx.z || threadIdx.x) return nullptr;
+    const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(g_dbg), 1ull);
+    long long* d = g_dbg + 16 + slot * 16;
+    d[0] = gtime();
+    d[15] = tag;
+    return d;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constant__ CUtensorMap tmap_wffn,
               const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ TcArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T_BAR_OFF);
     uint64_t* full = bars;
     uint64_t* empty = bars + T_NSTG;
     uint64_t* accfull = bars + 2 * T_NSTG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_NSTG + 1);
-    Mail mail{reinterpret_cast<float2(*)[4][128]>(smem + T_MAIL_OFF)};
+    Mail mail{reinterpret_cast<float2(*)[8][128]>(smem + T_MAIL_OFF)};
     if (smem + T_SMEM_USED > smem_raw + T_SMEM) __trap();   // dynamic smem base less aligned than assumed
 
+    long long* dbg = nullptr;
+    __shared__ long long* s_dbg;
+    if (g_dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        if (threadIdx.x == 0) {
+            const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(g_dbg), 1ull);
+            s_dbg = g_dbg + 16 + slot * 16;
+            s_dbg[0] = gtime();
+            s_dbg[15] = MODE * 1000 + gridDim.x * 100 + gridDim.z;
+        }
+        __syncthreads();
+        dbg = s_dbg;
+    }
     const TcJob& g = args.job[blockIdx.z];
     const int tile = blockIdx.x, nb = tile * T_TN;
     const int b = blockIdx.y / args.ksplit, split = blockIdx.y % args.ksplit;
@@ -239,7 +287,38 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG(1);
     if (has_ln) cluster_arrive();   // matched by the cluster_wait before the first DSMEM store: peers have started
+    // per-column parameters of this tile (weights: independent of the previous kernel) -> shared memory, now
+    float* vec = reinterpret_cast<float*>(smem + T_VEC_OFF);
+    if (active && warp >= 2 && warp < 2 + V_COUNT) {
+        const int which = warp - 2;
+        const float* src = nullptr;
+        int off = nb;   // column offset inside the source vector
+        if (MODE == MODE_GENERIC) {
+            const float* ln = nb < 256 ? g.ln0 : g.ln1;
+            if (which == V_BIAS0) src = g.bias0;
+            else if (which == V_GA0 && ln) src = ln, off = nb & 255;
+            else if (which == V_BE0 && ln) src = ln + 256, off = nb & 255;
+        } else if (MODE == MODE_DUAL) {
+            if (which == V_BIAS0) src = g.bias0;
+            else if (which == V_CBIAS0) src = g.cbias0;
+            else if (which == V_BIAS1) src = g.bias1;
+            else if (nb >= 256) {
+                off = nb - 256;
+                if (which == V_GA0) src = g.ln0;
+                else if (which == V_BE0) src = g.ln0 + 256;
+                else if (which == V_GA1) src = g.ln1;
+                else if (which == V_BE1) src = g.ln1 + 256;
+            }
+        } else {   // MODE_GATE: tile columns [0,64) -> input_norm_in, [64,128) -> norm_in, both of features 64*tile..
+            if (which == V_BIAS0) src = g.bias0;
+            else if (which == V_GA0) src = (lane < 16 ? g.ln0 : g.ln1), off = tile * 64 - (lane < 16 ? 0 : 64);
+            else if (which == V_BE0) src = (lane < 16 ? g.ln0 : g.ln1) + 256, off = tile * 64 - (lane < 16 ? 0 : 64);
+        }
+        const float4 v = src ? ld4(src + off + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(vec + which * 128 + lane * 4) = v;
+    }
 
     auto issue_w = [&](int it) {
         const TcPass& p = g.pass[it >> 2];
@@ -266,6 +345,32 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         for (int it = 0; it < pre; ++it) issue_w(it);
     pdl_wait();                 // activations written by the previous kernels are visible from here on
     pdl_launch_dependents();    // let the next kernel start prefetching its weights
+    if (threadIdx.x == 0) DBG(2);
+    // operands of the epilogue written by previous kernels: issue their loads now, they land while the MMAs run
+    float4 pref[8];                     // GENERIC: residual, GATE: LN'ed input_out / param_out (phase-2 mapping)
+    float cnt = 0.f;                    // DUAL: mask pixel count of this thread's row (phase-1 mapping)
+    if (active && warp >= 2) {
+        const int ew_ = warp - 2;
+        if (MODE == MODE_GENERIC) {
+            if (g.res && args.ksplit == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = ew_ + 16 * i;
+                    pref[i] = rr < N ? ld4(g.res + ((size_t)b * N + rr) * g.ldr + nb + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else if (MODE == MODE_GATE) {
+            const float* mul = ((lane >> 4) ? g.mul1 : g.mul0) + tile * 64 + (lane & 15) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = ew_ + 16 * i;
+                pref[i] = rr < N ? ld4(mul + ((size_t)b * N + rr) * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            const int r_ = (warp & 3) * 32 + lane;
+            if (g.count && r_ < N) cnt = __ldg(g.count + (size_t)b * N + r_);
+        }
+    }
 
     if (active && warp == 0 && lane == 0) {
         // ================= TMA producer =================
@@ -282,6 +387,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             const int s = it % T_NSTG, kb = it & 3;
             mbar_wait(&full[s], (it / T_NSTG) & 1);
             tc_fence_after();
+            if (it < 4) DBG(3 + it);
             const uint32_t a_hi = smem_u32(smem + s * T_STAGE), a_lo = a_hi + T_PLANE;
             const uint32_t w_hi = a_hi + 2 * T_PLANE, w_lo = a_hi + 3 * T_PLANE;
             const uint32_t d = tmem_base + (uint32_t)(it >> 2) * T_TN;
@@ -301,166 +407,184 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     }
     __syncwarp();
 
-    // ================= epilogue: warps 2..9, thread = (TMEM lane = kernel row, 64-column half) =================
+    // ================= epilogue: warps 2..17 =================
+    // phase 1: thread = (TMEM lane = kernel row, 32-column quarter): accumulator + bias in registers, LayerNorm piece
+    //          statistics straight from the registers (no shuffles), values -> fp32 tile(s) in the (now idle) ring;
+    // phase 2: warp = 8 rows, lane = 4 consecutive columns, so every global access is a contiguous row segment.
     const bool epi = active && warp >= 2;
-    const int q = warp & 3, hsel = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
-    const bool rok = r < N;
-    const size_t m = (size_t)b * N + (rok ? r : 0);
+    const int ew = warp - 2;
     const uint32_t crank = has_ln ? cluster_ctarank() : 0u;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hsel * 64;
-    const int c0 = nb + hsel * 64;          // first output column of this thread
-    float y[64];
-
+    if (has_ln) cluster_wait();   // matches the arrive after setup: every CTA of the cluster is running (DSMEM is valid)
+    float* S0 = reinterpret_cast<float*>(smem);
+    float* S1 = S0 + 128 * T_SLD;
+    const int cl = lane * 4;            // phase 2: column inside the tile
+    const int col = nb + cl;            //          output column
+    const int cg = col & 255;           //          column inside the 256-wide group
     if (epi) {
         mbar_wait(accfull, 0);
         tc_fence_after();
-    }
-
-    if (MODE == MODE_GENERIC) {
-        const float* ln = nb < 256 ? g.ln0 : g.ln1;
-        const int act = nb < 256 ? g.act0 : g.act1;
-        const int cg = c0 & 255;            // column inside the 256-wide group
-        float mean = 0.f, rstd = 1.f;
-        if (epi) {
-            tmem_ld64(taddr, y);
-            if (args.ksplit == 1) {
-                if (g.bias0) add_vec64(y, g.bias0 + c0);
-                if (g.res && rok) add_vec64(y, g.res + m * g.ldr + c0);
+        epi_bar();                      // the staged parameter vectors are visible to all epilogue warps
+        if (threadIdx.x == 64) DBG(8);
+        const int q = warp & 3, qt = ew >> 2;
+        const int r = q * 32 + lane;
+        const int c0 = nb + qt * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)qt * 32;
+        float* d0 = S0 + r * T_SLD + qt * 32;
+        float y[32];
+        float mu, m2;
+        tmem_ld32f(taddr, y);
+        if (MODE == MODE_GENERIC) {
+            const bool res = g.res && args.ksplit == 1;
+            add_vec32(y, vec + V_BIAS0 * 128 + qt * 32);
+            if (has_ln && !res) {
+                stats32(y, mu, m2);
+                mail.publish(0, (int)crank * 4 + qt, r, mu, m2, 2);
             }
-        }
-        if (has_ln) {
-            cluster_wait();
-            if (epi) {
-                float mu, m2;
-                mean_m2_64(y, mu, m2);
-                mail.publish(0, (int)crank * 2 + hsel, r, mu, m2, 2);
-            }
-            cluster_arrive();
-            cluster_wait();
-        }
-        if (epi) {
-            if (has_ln) {
-                mail.combine(0, r, mean, rstd);
-                ln_apply64(y, mean, rstd, ln, cg);
-            }
-            act64(y, act);
-            if (g.Y && rok) {
-                float* dst = g.Y + ((size_t)split * args.R + m) * g.ldy + c0;
-                if ((g.ldy & 3) == 0 && c0 + 64 <= g.nstore) {
+            store32(d0, y);
+            epi_bar();
+            if (res) {   // residual: coalesced add into the tile, then the statistics of the finished rows
 #pragma unroll
-                    for (int c = 0; c < 64; c += 4)
-                        *reinterpret_cast<float4*>(dst + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 64; ++c)
-                        if (c0 + c < g.nstore) dst[c] = y[c];
+                for (int i = 0; i < 8; ++i) {
+                    float4* p4 = reinterpret_cast<float4*>(S0 + (ew + 16 * i) * T_SLD + cl);
+                    *p4 = add4(*p4, pref[i]);
+                }
+                epi_bar();
+                if (has_ln) {
+                    load32(d0, y);
+                    stats32(y, mu, m2);
+                    mail.publish(0, (int)crank * 4 + qt, r, mu, m2, 2);
                 }
             }
-            if (g.p_slot >= 0) {
-                const int slot = g.p_slot + (nb >> 8);
-                store_planes64(y, arena_row(args.arena, unit, slot, 0, r) + cg, arena_row(args.arena, unit, slot, 1, r) + cg,
-                               !rok);
+        } else if (MODE == MODE_DUAL) {
+            // acc0 = dynamic_layer(pooled) (+ count * folded bias), acc1 = input_layer(kernel); kernel_updator.py:58-69
+            float z[32];
+            tmem_ld32f(taddr + T_TN, z);
+            add_vec32(y, vec + V_BIAS0 * 128 + qt * 32);
+            fma_vec32(y, cnt, vec + V_CBIAS0 * 128 + qt * 32);
+            add_vec32(z, vec + V_BIAS1 * 128 + qt * 32);
+            if (!has_ln) {   // gate_feats = input_in * param_in -> A operand of the gates
+#pragma unroll
+                for (int c = 0; c < 32; ++c) y[c] *= z[c];
+                store32(d0, y);
+            } else {
+                stats32(y, mu, m2);
+                mail.publish(0, (int)crank * 4 + qt, r, mu, m2, 2);
+                stats32(z, mu, m2);
+                mail.publish(1, (int)crank * 4 + qt, r, mu, m2, 2);
+                store32(d0, y);
+                store32(S1 + r * T_SLD + qt * 32, z);
             }
-            if (g.xplanes && r < g.xrows) {
-                uint16_t* ph = g.xplanes + (((size_t)(g.xunit0 + b) * 2) * g.xrows + r) * 256 + c0;
-                store_planes64(y, ph, ph + (size_t)g.xrows * 256, false);
+            epi_bar();
+        } else {   // MODE_GATE: columns [0,64) = input_gate, [64,128) = update_gate of features 64*tile .. +63
+            add_vec32(y, vec + V_BIAS0 * 128 + qt * 32);
+            stats32(y, mu, m2);
+            mail.publish(qt >> 1, (int)crank * 2 + (qt & 1), r, mu, m2, 4);
+            store32(d0, y);
+            epi_bar();
+        }
+        if (threadIdx.x == 64) DBG(9);
+    }
+    if (has_ln) {
+        cluster_arrive();
+        cluster_wait();
+    }
+    if (threadIdx.x == 64) DBG(11);
+    // LayerNorm (mean, rstd) of this warp's 8 rows, one row per lane (lanes 8..15: the second array)
+    float pm = 0.f, pr = 1.f;
+    if (epi && has_ln) mail.combine((lane >> 3) & 1, ew + 16 * (lane & 7), pm, pr);
+
+    if (MODE == MODE_GENERIC) {
+        if (epi) {
+            const int act = nb < 256 ? g.act0 : g.act1;
+            const float4 ga = *reinterpret_cast<const float4*>(vec + V_GA0 * 128 + cl);
+            const float4 be = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + cl);
+            const int ldy = g.ldy, nstore = g.nstore, xrows = g.xrows;
+            const bool vec = (ldy & 3) == 0 && col + 4 <= nstore;
+            float* yp = g.Y ? g.Y + ((size_t)split * args.R + (size_t)b * N + ew) * ldy + col : nullptr;
+            uint16_t* pp = g.p_slot >= 0 ? arena_row(args.arena, unit, g.p_slot + (nb >> 8), 0, ew) + cg : nullptr;
+            uint16_t* xp = g.xplanes ? g.xplanes + (((size_t)(g.xunit0 + b) * 2) * xrows + ew) * 256 + col : nullptr;
+            const float* sp = S0 + ew * T_SLD + cl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = ew + 16 * i;
+                const bool rok = rr < N;
+                float4 v = *reinterpret_cast<const float4*>(sp + i * 16 * T_SLD);
+                const float mean = __shfl_sync(0xffffffffu, pm, i), rstd = __shfl_sync(0xffffffffu, pr, i);
+                if (has_ln) v = ln4(v, mean, rstd, ga, be);
+                v = act4(v, act);
+                if (yp && rok) {
+                    float* dst = yp + (size_t)i * 16 * ldy;
+                    if (vec) {
+                        *reinterpret_cast<float4*>(dst) = v;
+                    } else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < nstore) dst[j] = e[j];
+                    }
+                }
+                if (pp) store_planes4(rok ? v : make_float4(0.f, 0.f, 0.f, 0.f), pp + i * 16 * 256, pp + (128 + i * 16) * 256);
+                if (xp && rr < xrows) store_planes4(v, xp + i * 16 * 256, xp + ((size_t)xrows + i * 16) * 256);
             }
         }
     } else if (MODE == MODE_DUAL) {
-        // acc0 = dynamic_layer(pooled) (+ count * folded bias), acc1 = input_layer(kernel); kernel_updator.py:58-69
-        float z[64];
-        if (epi) {
-            tmem_ld64(taddr, y);
-            tmem_ld64(taddr + T_TN, z);
-            add_vec64(y, g.bias0 + c0);
-            if (g.cbias0) fma_vec64(y, (g.count && rok) ? __ldg(g.count + m) : 0.f, g.cbias0 + c0);
-            add_vec64(z, g.bias1 + c0);
-        }
-        if (!has_ln) {
-            if (epi) {   // gate_feats = input_in * param_in -> A operand of the gates
+        if (epi && !has_ln) {
+            uint16_t* pp = arena_row(args.arena, unit, g.p_slot, 0, ew) + col;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) y[c] *= z[c];
-                store_planes64(y, arena_row(args.arena, unit, g.p_slot, 0, r) + c0,
-                               arena_row(args.arena, unit, g.p_slot, 1, r) + c0, !rok);
+            for (int i = 0; i < 8; ++i) {
+                const int rr = ew + 16 * i;
+                const float4 v = rr < N ? *reinterpret_cast<float4*>(S0 + rr * T_SLD + cl) : make_float4(0.f, 0.f, 0.f, 0.f);
+                store_planes4(v, pp + i * 16 * 256, pp + (128 + i * 16) * 256);
             }
-        } else {
-            const int cg = c0 - 256;
-            cluster_wait();
-            if (epi) {
-                float mu, m2;
-                mean_m2_64(y, mu, m2);
-                mail.publish(0, (int)crank * 2 + hsel, r, mu, m2, 2);
-                mean_m2_64(z, mu, m2);
-                mail.publish(1, (int)crank * 2 + hsel, r, mu, m2, 2);
-            }
-            cluster_arrive();
-            cluster_wait();
-            if (epi) {   // param_out = norm_out(.), input_out = input_norm_out(.)   (:78-79)
-                float mean, rstd;
-                mail.combine(0, r, mean, rstd);
-                ln_apply64(y, mean, rstd, g.ln0, cg);
-                mail.combine(1, r, mean, rstd);
-                ln_apply64(z, mean, rstd, g.ln1, cg);
-                if (rok) {
-                    float* d0 = g.Y + m * 256 + cg;
-                    float* d1 = g.Y1 + m * 256 + cg;
+        } else if (epi) {   // param_out = norm_out(.), input_out = input_norm_out(.)   (:78-79)
+            const int c2 = col - 256;
+            const float4 ga0 = *reinterpret_cast<const float4*>(vec + V_GA0 * 128 + cl);
+            const float4 be0 = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + cl);
+            const float4 ga1 = *reinterpret_cast<const float4*>(vec + V_GA1 * 128 + cl);
+            const float4 be1 = *reinterpret_cast<const float4*>(vec + V_BE1 * 128 + cl);
+            float* y0 = g.Y + ((size_t)b * N + ew) * 256 + c2;
+            float* y1 = g.Y1 + ((size_t)b * N + ew) * 256 + c2;
 #pragma unroll
-                    for (int c = 0; c < 64; c += 4) {
-                        *reinterpret_cast<float4*>(d0 + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
-                        *reinterpret_cast<float4*>(d1 + c) = make_float4(z[c], z[c + 1], z[c + 2], z[c + 3]);
-                    }
+            for (int i = 0; i < 8; ++i) {
+                const int rr = ew + 16 * i;
+                const float mean0 = __shfl_sync(0xffffffffu, pm, i), rstd0 = __shfl_sync(0xffffffffu, pr, i);
+                const float mean1 = __shfl_sync(0xffffffffu, pm, i + 8), rstd1 = __shfl_sync(0xffffffffu, pr, i + 8);
+                if (rr < N) {
+                    *reinterpret_cast<float4*>(y0 + i * 16 * 256) =
+                        ln4(*reinterpret_cast<float4*>(S0 + rr * T_SLD + cl), mean0, rstd0, ga0, be0);
+                    *reinterpret_cast<float4*>(y1 + i * 16 * 256) =
+                        ln4(*reinterpret_cast<float4*>(S1 + rr * T_SLD + cl), mean1, rstd1, ga1, be1);
                 }
             }
         }
-    } else {   // MODE_GATE: columns [0,64) = input_gate, [64,128) = update_gate of features 64*tile .. +63   (:73-88)
-        const int f0 = tile * 64;
-        float* xch = reinterpret_cast<float*>(smem);   // ring stage 0 is free once accfull has fired
+    } else {   // MODE_GATE   (:73-88)
         if (epi) {
-            tmem_ld64(taddr, y);
-            add_vec64(y, g.bias0 + c0);
-        }
-        cluster_wait();
-        if (epi) {
-            float mu, m2;
-            mean_m2_64(y, mu, m2);
-            mail.publish(hsel, (int)crank, r, mu, m2, 4);
-        }
-        cluster_arrive();
-        cluster_wait();
-        if (epi) {
-            float mean, rstd;
-            mail.combine(hsel, r, mean, rstd);
-            ln_apply64(y, mean, rstd, hsel ? g.ln1 : g.ln0, f0);
-            act64(y, ACT_SIGMOID);
-            if (rok) {
-                const float* mul = (hsel ? g.mul1 : g.mul0) + m * 256 + f0;
+            const int half = lane >> 4;
+            const int f = tile * 64 + (lane & 15) * 4;   // feature column of this lane
+            const float4 ga = *reinterpret_cast<const float4*>(vec + V_GA0 * 128 + cl);
+            const float4 be = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + cl);
+            uint16_t* pp = arena_row(args.arena, unit, g.p_slot, 0, ew) + f;
 #pragma unroll
-                for (int c = 0; c < 64; c += 4) {
-                    const float4 t = ld4(mul + c);
-                    y[c] *= t.x, y[c + 1] *= t.y, y[c + 2] *= t.z, y[c + 3] *= t.w;
-                }
-            }
-            if (hsel == 1) {
-#pragma unroll
-                for (int c = 0; c < 64; c += 4)
-                    *reinterpret_cast<float4*>(xch + r * T_XCH_LD + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
-            }
-            epi_bar();
-            if (hsel == 0) {   // features = update_gate * param_out + input_gate * input_out
-#pragma unroll
-                for (int c = 0; c < 64; c += 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(xch + r * T_XCH_LD + c);
-                    y[c] += t.x, y[c + 1] += t.y, y[c + 2] += t.z, y[c + 3] += t.w;
-                }
-                store_planes64(y, arena_row(args.arena, unit, g.p_slot, 0, r) + f0,
-                               arena_row(args.arena, unit, g.p_slot, 1, r) + f0, !rok);
+            for (int i = 0; i < 8; ++i) {
+                const int rr = ew + 16 * i;
+                const float mean = __shfl_sync(0xffffffffu, pm, i + 8 * half);
+                const float rstd = __shfl_sync(0xffffffffu, pr, i + 8 * half);
+                float4 v = ln4(*reinterpret_cast<float4*>(S0 + rr * T_SLD + cl), mean, rstd, ga, be);
+                v = act4(v, ACT_SIGMOID);
+                const float4 t = pref[i];
+                v = make_float4(v.x * t.x, v.y * t.y, v.z * t.z, v.w * t.w);
+                // features = update_gate * param_out + input_gate * input_out: lanes l and l + 16 hold the same feature
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, 16), v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, 16), v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+                if (half == 0) store_planes4(v, pp + i * 16 * 256, pp + (128 + i * 16) * 256);
             }
         }
     }
+    if (threadIdx.x == 64) DBG(12);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<256>(tmem_base);
+    if (threadIdx.x == 0) DBG(13);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -480,8 +604,10 @@ struct PrepArgs {
     int B, N, njobs;
 };
 __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepArgs a) {
+    long long* dbg = dbg_claim(1);
     pdl_wait();
     pdl_launch_dependents();
+    DBG(2);
     const int job = blockIdx.y;
     const int idx = blockIdx.x * 256 + threadIdx.x;   // (b, r, c4) with r < 128
     const int c4 = idx & 63, r = (idx >> 6) & 127, b = idx >> 13;
@@ -523,6 +649,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepA
     uint16_t* pl = arena_row(a.arena, unit, a.slot[job], 1, r) + c4 * 4;
     *reinterpret_cast<uint2*>(ph) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
     *reinterpret_cast<uint2*>(pl) = make_uint2(pack_bf16x2(acc.x - h0, acc.y - h1), pack_bf16x2(acc.z - h2, acc.w - h3));
+    DBG(13);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -538,8 +665,10 @@ struct SumLnArgs {
     int B, N, R, nsplit;
 };
 __global__ void __launch_bounds__(256) sumln_kernel(const __grid_constant__ SumLnArgs a) {
+    long long* dbg = dbg_claim(2);
     pdl_wait();
     pdl_launch_dependents();
+    DBG(2);
     const int br = blockIdx.y;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);   // b * 128 + r
     const int lane = threadIdx.x & 31;
@@ -597,31 +726,37 @@ __global__ void __launch_bounds__(256) sumln_kernel(const __grid_constant__ SumL
     const int unit = br * a.B + b;
     *reinterpret_cast<uint4*>(arena_row(a.arena, unit, SLOT_OBJ2, 0, r) + k0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(arena_row(a.arena, unit, SLOT_OBJ2, 1, r) + k0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    DBG(13);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Inter-kernel self-attention of one (branch, image, head): softmax(q k^T / sqrt(32)) v over the N kernels of the
 // image (mmcv MultiheadAttention -> nn.MultiheadAttention, seq-first; kernel_update_head.py:259-260).
 // qkv [R][768] = [q | k | v] fp32; output (heads concatenated, before out_proj) -> SLOT_ATT planes.
-// 4 threads per query; keys are dealt to the 4 threads in blocks of 4 consecutive keys so that K^T rows and V rows
-// are read as float4 (4 FMAs per shared-memory load).  Two-pass softmax with the scores kept in registers, quad
-// reduction by shuffles.  Two CTAs per (branch, image, head) split the queries.
-constexpr int ATT_NB = PF_MAX_N / 16;   // key blocks of 4 per thread (8 -> 32 keys per thread, 128 per quad)
-constexpr int ATT_QPC = PF_MAX_N / 2;   // queries per CTA
-__global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __restrict__ qkv0,
-                                                                const float* __restrict__ qkv1,
-                                                                uint16_t* __restrict__ arena, int B, int N) {
+// 8 threads per query; keys are dealt to the 8 threads in blocks of 4 consecutive keys so that K^T rows and V rows
+// are read as float4 (4 FMAs per shared-memory load; V chunks XOR-swizzled by key block: conflict-free).  Two-pass
+// softmax with the scores kept in registers, octet reduction by shuffles.  Four CTAs per (branch, image, head)
+// split the queries, so the 64 (image, head) pairs of a batch of 4 spread over 512 CTAs.
+constexpr int ATT_TPQ = 8;                        // threads per query
+constexpr int ATT_NB = PF_MAX_N / (4 * ATT_TPQ);  // key blocks of 4 per thread (4 -> 16 keys per thread)
+constexpr int ATT_QPC = 32;                       // queries per CTA
+constexpr int ATT_CPH = PF_MAX_N / ATT_QPC;       // CTAs per (branch, image, head)
+__global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const float* __restrict__ qkv0,
+                                                                      const float* __restrict__ qkv1,
+                                                                      uint16_t* __restrict__ arena, int B, int N) {
     __shared__ __align__(16) float s_kt[32][PF_MAX_N + 4];   // K transposed: [d][key]
-    __shared__ __align__(16) float s_v[PF_MAX_N][36];
-    const int h = blockIdx.x >> 1, half = blockIdx.x & 1, b = blockIdx.y;
+    __shared__ __align__(16) float s_v[PF_MAX_N][32];        // V: 16-byte chunk c of key j stored at chunk c ^ ((j >> 2) & 7)
+    const int h = blockIdx.x / ATT_CPH, qblk = blockIdx.x % ATT_CPH, b = blockIdx.y;
+    long long* dbg = dbg_claim(3);
     pdl_wait();
     pdl_launch_dependents();
+    DBG(2);
     const float* qkv = (blockIdx.z == 0 ? qkv0 : qkv1) + (size_t)b * N * 768;
     {   // K and V of this head: 128 keys x 8 float4 each; all 8 loads of a thread are issued before the first store
         float4 kk[4], vv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = threadIdx.x + j * (ATT_QPC * 4);   // 0 .. 1023
+            const int i = threadIdx.x + j * (ATT_QPC * ATT_TPQ);   // 0 .. 1023
             const int n = i >> 3, d4 = i & 7;
             const bool ok = n < N;
             kk[j] = ok ? ld4(qkv + (size_t)n * 768 + 256 + h * 32 + d4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -629,14 +764,14 @@ __global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __r
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = threadIdx.x + j * (ATT_QPC * 4);
+            const int i = threadIdx.x + j * (ATT_QPC * ATT_TPQ);
             const int n = i >> 3, d4 = i & 7;
             s_kt[d4 * 4][n] = kk[j].x, s_kt[d4 * 4 + 1][n] = kk[j].y, s_kt[d4 * 4 + 2][n] = kk[j].z, s_kt[d4 * 4 + 3][n] = kk[j].w;
-            *reinterpret_cast<float4*>(&s_v[n][d4 * 4]) = vv[j];
+            *reinterpret_cast<float4*>(&s_v[n][(d4 ^ ((n >> 2) & 7)) * 4]) = vv[j];
         }
     }
-    const int n = half * ATT_QPC + (threadIdx.x >> 2), part = threadIdx.x & 3;
-    const int nq = n < N ? n : N - 1;   // keep whole quads alive for the shuffles
+    const int n = qblk * ATT_QPC + threadIdx.x / ATT_TPQ, part = threadIdx.x % ATT_TPQ;
+    const int nq = n < N ? n : N - 1;   // keep whole octets alive for the shuffles
     float q[32];
     const float scale = 0.17677669529663687f;  // 1/sqrt(32), applied to q before q k^T as torch does
 #pragma unroll
@@ -645,11 +780,12 @@ __global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __r
         q[d4 * 4] = t.x * scale, q[d4 * 4 + 1] = t.y * scale, q[d4 * 4 + 2] = t.z * scale, q[d4 * 4 + 3] = t.w * scale;
     }
     __syncthreads();
+    DBG(3);
     float sc[ATT_NB][4];
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < ATT_NB; ++i) {
-        const int j0 = 4 * (part + 4 * i);
+        const int j0 = 4 * (part + ATT_TPQ * i);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int d = 0; d < 32; ++d) {
@@ -660,51 +796,56 @@ __global__ void __launch_bounds__(ATT_QPC * 4) attention_kernel(const float* __r
         sc[i][2] = j0 + 2 < N ? a.z : -INFINITY, sc[i][3] = j0 + 3 < N ? a.w : -INFINITY;
         mx = fmaxf(fmaxf(mx, fmaxf(sc[i][0], sc[i][1])), fmaxf(sc[i][2], sc[i][3]));
     }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#pragma unroll
+    for (int o = 1; o < ATT_TPQ; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    DBG(4);
     float o[32], den = 0.f;
 #pragma unroll
     for (int d = 0; d < 32; ++d) o[d] = 0.f;
 #pragma unroll
     for (int i = 0; i < ATT_NB; ++i) {
-        const int j0 = 4 * (part + 4 * i);
+        const int j0 = 4 * (part + ATT_TPQ * i);   // (j0 >> 2) & 7 == part
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float pj = expf(sc[i][e] - mx);   // exp(-inf) = 0 for padded keys (their V rows are zero)
             den += pj;
 #pragma unroll
             for (int d4 = 0; d4 < 8; ++d4) {
-                const float4 vv = *reinterpret_cast<const float4*>(&s_v[j0 + e][d4 * 4]);
+                const float4 vv = *reinterpret_cast<const float4*>(&s_v[j0 + e][(d4 ^ part) * 4]);
                 o[d4 * 4] += pj * vv.x, o[d4 * 4 + 1] += pj * vv.y, o[d4 * 4 + 2] += pj * vv.z, o[d4 * 4 + 3] += pj * vv.w;
             }
         }
     }
-    den += __shfl_xor_sync(0xffffffffu, den, 1);
-    den += __shfl_xor_sync(0xffffffffu, den, 2);
+#pragma unroll
+    for (int s2 = 1; s2 < ATT_TPQ; s2 <<= 1) den += __shfl_xor_sync(0xffffffffu, den, s2);
     const float inv = 1.f / den;
+    // octet reduce-scatter: after 3 halving steps lane `part` holds the full sums of dims [4 part, 4 part + 4)
+    float r16[16], r8[8], r4[4];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) {
-        o[d] += __shfl_xor_sync(0xffffffffu, o[d], 1);
-        o[d] += __shfl_xor_sync(0xffffffffu, o[d], 2);
+    for (int k = 0; k < 16; ++k) {
+        const float send = (part & 4) ? o[k] : o[16 + k];
+        const float keep = (part & 4) ? o[16 + k] : o[k];
+        r16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
-    // lane `part` of the quad writes dims [8 part, 8 part + 8) of query row n as bf16 hi / lo (rows >= N: zeros)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float send = (part & 2) ? r16[k] : r16[8 + k];
+        const float keep = (part & 2) ? r16[8 + k] : r16[k];
+        r8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float send = (part & 1) ? r8[k] : r8[4 + k];
+        const float keep = (part & 1) ? r8[4 + k] : r8[k];
+        r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    // lane `part` writes dims [4 part, 4 part + 4) of query row n as bf16 hi / lo (rows >= N: zeros)
+    const bool ok = n < N;
     const int unit = blockIdx.z * B + b;
-    uint16_t* ph = arena_row(arena, unit, SLOT_ATT, 0, n) + h * 32 + part * 8;
-    uint16_t* pl = arena_row(arena, unit, SLOT_ATT, 1, n) + h * 32 + part * 8;
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp)
-        if (part == pp) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float v0 = n < N ? o[pp * 8 + 2 * i] * inv : 0.f, v1 = n < N ? o[pp * 8 + 2 * i + 1] * inv : 0.f;
-                const float h0 = bf16_round(v0), h1 = bf16_round(v1);
-                hi[i] = pack_bf16x2(h0, h1);
-                lo[i] = pack_bf16x2(v0 - h0, v1 - h1);
-            }
-        }
-    *reinterpret_cast<uint4*>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    store_planes4(ok ? make_float4(r4[0] * inv, r4[1] * inv, r4[2] * inv, r4[3] * inv) : make_float4(0.f, 0.f, 0.f, 0.f),
+                  arena_row(arena, unit, SLOT_ATT, 0, n) + h * 32 + part * 4,
+                  arena_row(arena, unit, SLOT_ATT, 1, n) + h * 32 + part * 4);
+    DBG(13);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -782,8 +923,8 @@ static int launch_pdl(void (*kern)(Args), dim3 grid, dim3 block, const Args& a, 
 static int launch_attention(const float* q0, const float* q1, uint16_t* arena, int B, int N, int nbranch, cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(PF_HEADS * 2, B, nbranch);
-    cfg.blockDim = dim3(ATT_QPC * 4);
+    cfg.gridDim = dim3(PF_HEADS * ATT_CPH, B, nbranch);
+    cfg.blockDim = dim3(ATT_QPC * ATT_TPQ);
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -872,6 +1013,13 @@ static int run_updator(const Maps& mp, const pf_stage_weights* w, uint16_t* aren
 }
 
 }  // namespace pf
+
+// Debug: device buffer of int64 [16 + 16 * capacity] (zeroed by the caller) receiving the in-kernel timeline of CTA
+// (0,0,0) of every tcgemm launch; pass NULL to switch it off.  Not part of the product path.
+extern "C" int pf_debug_timeline(long long* device_buffer) {
+    cudaError_t e = cudaMemcpyToSymbol(pf::g_dbg, &device_buffer, sizeof(device_buffer));
+    return e == cudaSuccess ? PF_OK : pf::set_error(PF_ERR_CUDA, "pf_debug_timeline: %s", cudaGetErrorString(e));
+}
 
 extern "C" size_t pf_update_workspace_bytes(int B, int N, int ffn_channels) {
     if (B <= 0 || N <= 0 || ffn_channels <= 0) return 0;
