@@ -34,7 +34,7 @@ C, N_KERNELS, STAGES, NUM_CLASSES = 256, 111, 3, 19
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=4)
@@ -130,7 +130,7 @@ def working_set_mb(args, B):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+    Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
         'clocks_event_reasons.sw_power_cap'
 
@@ -139,15 +139,17 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) host time.time() bounds of the busy region: only samples inside it are used."""
+        import datetime
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
@@ -156,6 +158,10 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
+                if window is not None:
+                    ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                    if not (window[0] <= ts <= window[1]):
+                        continue
                 sm.append(float(r[1])), mx.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
@@ -204,11 +210,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # samples span the warm-up and the timed steps
+    if sampler:
+        time.sleep(0.25)                                       # let nvidia-smi start before the GPU gets busy
+    t_busy0 = time.time()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches_per_step = lib.pf_last_launch_count() + 2      # + the two 57 KB proposal copies (torch memcpy kernels)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
@@ -218,7 +227,7 @@ def run_ours(args, rank, world, local_rank):
         step()
         ev[i][1].record()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop((t_busy0, time.time())) if sampler else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -339,47 +348,38 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
 
 
 def run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier):
-    """Public API with pinned host buffers: per step H2D of (x_feats, depth_feats) bf16 + mask logits + proposal
-    kernels, decode, D2H of cls scores and the x2-upsampled mask / depth logits."""
+    """Public host-buffer API (polyphonicformer_b200.decoder.HostPipeline): every step copies its inputs (x_feats,
+    depth_feats bf16, mask logits, proposal kernels) from pinned HOST memory to the device, decodes, and copies
+    cls scores + the x2-upsampled mask / depth logits back into pinned HOST memory.  Steps are submitted back to
+    back; the three streams overlap the copies of neighbouring steps with the decode.  Timed with CUDA events from
+    the first H2D to the last D2H, max over ranks."""
     import torch.distributed as dist
-    pin = {k: v.pin_memory() for k, v in hin.items()}
-    out_cls = torch.empty((B, N, NUM_CLASSES), dtype=torch.float32).pin_memory()
-    out_scaled = torch.empty((2, B, N, 2 * H, 2 * W), dtype=torch.float32).pin_memory()
-    d_x = torch.empty_like(hin['x'], device=dev)
-    d_d = torch.empty_like(hin['d'], device=dev)
-    d_mask = torch.empty_like(hin['mask'], device=dev)
-    d_prop = torch.empty_like(hin['prop'], device=dev)
-    d_dprop = torch.empty_like(hin['dprop'], device=dev)
-    buf = eng.alloc_decode_buffers(B, N, H, W, upsample=True)
-    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ('x', 'd', 'mask', 'prop', 'dprop'))
-    d2h = out_cls.numel() * 4 + out_scaled.numel() * 4
-
-    def step():
-        d_x.copy_(pin['x'], non_blocking=True), d_d.copy_(pin['d'], non_blocking=True)
-        d_mask.copy_(pin['mask'], non_blocking=True)
-        d_prop.copy_(pin['prop'], non_blocking=True), d_dprop.copy_(pin['dprop'], non_blocking=True)
-        feats = eng.prepare_feats(d_x, d_d)
-        out = eng.decode(feats, d_mask, d_prop, d_dprop, H, W, upsample=True, buffers=buf,
-                         all_stage_outputs=args.all_stage_outputs)
-        out_cls.copy_(out['cls_score'], non_blocking=True)
-        out_scaled.copy_(buf['scaled'], non_blocking=True)
-
-    steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step()
+    from polyphonicformer_b200.decoder import HostPipeline
+    depth = 2
+    pin_in = [{k: v.clone().pin_memory() for k, v in hin.items()} for _ in range(depth)]
+    pin_out = [dict(cls=torch.empty((B, N, NUM_CLASSES), dtype=torch.float32).pin_memory(),
+                    scaled=torch.empty((2, B, N, 2 * H, 2 * W), dtype=torch.float32).pin_memory())
+               for _ in range(depth)]
+    pipe = HostPipeline(eng, B, N, H, W, upsample=True, depth=depth)
+    steps = max(4, min(args.steps, 12))
+    for i in range(3):
+        pipe.submit(pin_in[i % depth], pin_out[i % depth])
+    pipe.drain()
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        step()
-    b.record()
+    a.record(pipe.s_in)
+    for i in range(steps):
+        ev = pipe.submit(pin_in[i % depth], pin_out[i % depth])
+    b.record(pipe.s_out)
+    pipe.drain()
     barrier()
     t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return dict(value=world * B * steps / (t.item() / 1e3), unit='frames/s', h2d_bytes_per_step=h2d,
-                d2h_bytes_per_step=d2h, steps=steps, ms_per_step=t.item() / steps,
-                note='serial H2D -> decode -> D2H per step on one stream; PCIe-bound')
+    return dict(value=world * B * steps / (t.item() / 1e3), unit='frames/s', h2d_bytes_per_step=pipe.h2d_bytes(),
+                d2h_bytes_per_step=pipe.d2h_bytes(), steps=steps, ms_per_step=t.item() / steps,
+                note='HostPipeline: pinned host buffers, H2D | decode | D2H of neighbouring steps overlapped on 3 '
+                     'streams, 2 device slots; bound by the PCIe read-back of the fp32 logits')
 
 
 def cpu_baseline(args):

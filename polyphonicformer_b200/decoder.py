@@ -352,3 +352,79 @@ class DecoderEngine:
                    _ptr(buf['obj']), _ptr(buf['dep']), _ptr(buf['cls']), _ptr(buf['logits']), _ptr(buf['scaled']),
                    _ptr(buf['ws']), buf['ws_bytes'], B, N, H, W, feats.shape[-1],
                    _cabi.PF_FWD_ALL_STAGE_OUTPUTS if all_stage_outputs else 0, _stream_ptr())
+
+
+class HostPipeline:
+    """Decoder over HOST buffers: the call a user of the C ABI makes when feature maps and proposals live in pinned
+    host memory (e.g. handed over by another process).  ``submit`` enqueues, on three streams, the host->device copy of
+    one batch, the 3-stage decode and the device->host copy of its results; consecutive submissions overlap (copy of
+    batch i+1 | decode of batch i | read-back of batch i-1) using ``depth`` device slots.  Nothing here computes: it
+    is stream/event plumbing around ``DecoderEngine.decode_inplace``.
+
+    host_in : dict of pinned tensors  x, d [B,256,H,W] bf16; mask [B,N,H,W] f32; prop, dprop [B,N,256] f32
+    host_out: dict of pinned tensors  cls [B,N,classes] f32; scaled [2,B,N,2H,2W] f32 (or logits [2,B,N,H,W])
+    """
+
+    def __init__(self, engine, B, N, H, W, upsample=True, depth=2):
+        self.eng, self.B, self.N, self.H, self.W, self.upsample = engine, B, N, H, W, upsample
+        dev = engine.device
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.slots = []
+        HWp = engine.pitch(H * W)
+        self.direct = HWp == H * W      # the host maps can be copied straight into the library's [2,B,256,HWp] layout
+        for _ in range(depth):
+            feats = torch.empty((2, B, PF_C, HWp), dtype=torch.bfloat16, device=dev)
+            if self.direct:
+                x, d = feats[0].view(B, PF_C, H, W), feats[1].view(B, PF_C, H, W)
+            else:
+                feats.zero_()
+                x = torch.empty((B, PF_C, H, W), dtype=torch.bfloat16, device=dev)
+                d = torch.empty_like(x)
+            self.slots.append(dict(
+                x=x, d=d, feats=feats, mask=torch.empty((B, N, H, W), dtype=torch.float32, device=dev),
+                buf=engine.alloc_decode_buffers(B, N, H, W, upsample),
+                ev_in=torch.cuda.Event(), ev_run=torch.cuda.Event(), ev_out=torch.cuda.Event()))
+        self.n = 0
+
+    def h2d_bytes(self):
+        s = self.slots[0]
+        return sum(t.numel() * t.element_size() for t in (s['x'], s['d'], s['mask'], s['buf']['obj'], s['buf']['dep']))
+
+    def d2h_bytes(self):
+        b = self.slots[0]['buf']
+        out = b['scaled'] if self.upsample else b['logits']
+        return b['cls'].numel() * 4 + out.numel() * 4
+
+    def submit(self, host_in, host_out):
+        """Enqueue one batch; returns the event that fires when ``host_out`` holds its results."""
+        s = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        B, H, W = self.B, self.H, self.W
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(s['ev_run'])        # the slot's previous decode has consumed its inputs
+            s['x'].copy_(host_in['x'], non_blocking=True), s['d'].copy_(host_in['d'], non_blocking=True)
+            s['mask'].copy_(host_in['mask'], non_blocking=True)
+            self.s_in.wait_event(s['ev_out'])        # ... and its previous results have left the output buffers
+            s['buf']['obj'].copy_(host_in['prop'].reshape(B, self.N, PF_C), non_blocking=True)
+            s['buf']['dep'].copy_(host_in['dprop'].reshape(B, self.N, PF_C), non_blocking=True)
+            s['ev_in'].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(s['ev_in'])
+            self.s_run.wait_event(s['ev_out'])
+            if not self.direct:                      # ragged row pitch: one strided device copy into the layout
+                HW = H * W
+                s['feats'][0, :, :, :HW].copy_(s['x'].reshape(B, PF_C, HW))
+                s['feats'][1, :, :, :HW].copy_(s['d'].reshape(B, PF_C, HW))
+            self.eng.decode_inplace(s['feats'], s['mask'], s['buf'], H, W)
+            s['ev_run'].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(s['ev_run'])
+            host_out['cls'].copy_(s['buf']['cls'], non_blocking=True)
+            src = s['buf']['scaled'] if self.upsample else s['buf']['logits']
+            host_out['scaled' if self.upsample else 'logits'].copy_(src, non_blocking=True)
+            s['ev_out'].record(self.s_out)
+        return s['ev_out']
+
+    def drain(self):
+        for st in (self.s_in, self.s_run, self.s_out):
+            st.synchronize()

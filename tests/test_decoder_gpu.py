@@ -136,3 +136,33 @@ def test_decode_is_deterministic_and_graph_capturable(dev):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(buf['scaled'], outs[0][0])
+
+
+@pytest.mark.parametrize('H,W', [(16, 24), (10, 12)])     # HW % 8 == 0 (direct layout) and a ragged row pitch
+def test_host_pipeline_matches_resident_decode(dev, H, W):
+    """HostPipeline (pinned host buffers, 3 streams, 2 slots) returns bit-identical results to the resident path,
+    for every one of several overlapped submissions with different inputs."""
+    from polyphonicformer_b200.decoder import HostPipeline
+    B = 2
+    eng, _ = make_engine(0, dev)
+    pipe = HostPipeline(eng, B, synth.N_KERNELS, H, W, upsample=True, depth=2)
+    ins, outs, want = [], [], []
+    for seed in range(5):
+        inp = synth.synth_decoder_inputs(B, H, W, seed)
+        feats = eng.prepare_feats(inp['x_feats'].to(dev), inp['depth_feats'].to(dev))
+        o = eng.decode(feats, inp['mask_preds'].to(dev), inp['proposal_feats'].to(dev), inp['depth_proposal'].to(dev),
+                       H, W, upsample=True)
+        torch.cuda.synchronize()
+        want.append((o['cls_score'].cpu().clone(), torch.stack([o['scaled_mask_preds'], o['scaled_depth_preds']]).cpu()))
+        ins.append(dict(x=inp['x_feats'].to(torch.bfloat16).pin_memory(), d=inp['depth_feats'].to(torch.bfloat16).pin_memory(),
+                        mask=inp['mask_preds'].pin_memory(), prop=inp['proposal_feats'].reshape(B, -1, 256).pin_memory(),
+                        dprop=inp['depth_proposal'].reshape(B, -1, 256).contiguous().pin_memory()))
+        outs.append(dict(cls=torch.empty((B, synth.N_KERNELS, 19)).pin_memory(),
+                         scaled=torch.empty((2, B, synth.N_KERNELS, 2 * H, 2 * W)).pin_memory()))
+    for i in range(5):
+        pipe.submit(ins[i], outs[i])
+    pipe.drain()
+    for i in range(5):
+        assert torch.equal(outs[i]['cls'], want[i][0]), i
+        assert torch.equal(outs[i]['scaled'], want[i][1]), i
+    assert pipe.h2d_bytes() > 0 and pipe.d2h_bytes() == outs[0]['cls'].numel() * 4 + outs[0]['scaled'].numel() * 4
