@@ -44,6 +44,8 @@ def parse():
                     help='also materialise the (unobservable) fp32 logits + depth einsum of stages 0..S-2')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every step from the host instead of replaying a CUDA graph')
+    ap.add_argument('--splits', type=int, default=None, help='batch windows decoded concurrently (default: 1)')
     return ap.parse_args()
 
 
@@ -120,7 +122,9 @@ def workload_config(args, B):
                 parallelism='dp%d (batch-sharded frames, no collective)' % args.gpus,
                 l2='per-step working set %.0f MB > 126 MB L2 (no flush needed)' % working_set_mb(args, B)
                 if working_set_mb(args, B) > 126 else 'L2 flushed between timed iterations',
-                stage_outputs='all' if args.all_stage_outputs else 'observable-only')
+                stage_outputs='all' if args.all_stage_outputs else 'observable-only',
+                batch_windows=args.splits if args.splits else 1,
+                launch='eager' if args.no_graph else 'cuda-graph replay')
 
 
 def working_set_mb(args, B):
@@ -196,13 +200,27 @@ def run_ours(args, rank, world, local_rank):
     feats = eng.prepare_feats(hin['x'].to(dev), hin['d'].to(dev))
     mask = hin['mask'].to(dev)
     prop, dprop = hin['prop'].to(dev), hin['dprop'].to(dev)
-    buf = eng.alloc_decode_buffers(B, N, H, W, upsample=True)
+    buf = eng.alloc_decode_buffers(B, N, H, W, upsample=True, splits=args.splits)
     need_flush = working_set_mb(args, B) <= 126
     l2buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if need_flush else None
 
-    def step():
+    def step_eager():
         buf['obj'].copy_(prop), buf['dep'].copy_(dprop)
         eng.decode_inplace(feats, mask, buf, H, W, args.all_stage_outputs)
+
+    step = step_eager
+    if not args.no_graph:
+        # the step is launch-only (no allocation, no sync): capture it once, replay it per step
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(dev)
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            step_eager()
+            cap.synchronize()
+            with torch.cuda.graph(graph, stream=cap):
+                step_eager()
+        torch.cuda.current_stream().wait_stream(cap)
+        step = graph.replay
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    launches_per_step = lib.pf_last_launch_count() + 2      # + the two 57 KB proposal copies (torch memcpy kernels)
+    launches_per_step = eng.last_launches + 2               # + the two 57 KB proposal copies (torch memcpy kernels)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):

@@ -184,6 +184,16 @@ int pf_decoder_forward(const pf_stage_weights* stages_host, int n_stages, const 
                        float* scaled_out, void* workspace, size_t workspace_bytes, int B, int N, int H, int W, int HWp,
                        int flags, void* stream);
 
+/* The same loop over the batch window [b0, b0+B) of full-batch tensors: feats [2][B_total][256][HWp], mask_logits /
+ * obj / dep / cls_out [B_total][...], logits_out / scaled_out [2][B_total][N][..]; `workspace` sized for B images
+ * (pf_decoder_workspace_bytes(B, ...)) and private to the call.  Lets the host decode disjoint windows of one batch
+ * concurrently on several streams: the latency-bound small-N block of one window overlaps the HBM-bound pooling /
+ * einsum of another (DecoderEngine.decode_inplace(splits=...)). */
+int pf_decoder_forward_slice(const pf_stage_weights* stages_host, int n_stages, const uint16_t* feats,
+                             const float* mask_logits, float* obj, float* dep, float* cls_out, float* logits_out,
+                             float* scaled_out, void* workspace, size_t workspace_bytes, int B_total, int b0, int B,
+                             int N, int H, int W, int HWp, int flags, void* stream);
+
 /* debug only: int64 device buffer [16 + 16*capacity], zero-filled by the caller; CTA (0,0,0) of every GEMM launch of
  * the small-N block appends 16 %globaltimer samples (see scripts/k2_timeline.py).  NULL switches it off. */
 int pf_debug_timeline(long long* device_buffer);

@@ -68,6 +68,9 @@ _SIGS = {
                                c_void_p]),
     'pf_upsample2x': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_decoder_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'pf_decoder_forward_slice': (c_int, [POINTER(StageWeights), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_void_p]),
     'pf_decoder_forward': (c_int, [POINTER(StageWeights), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p]),

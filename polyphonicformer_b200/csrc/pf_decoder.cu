@@ -45,36 +45,52 @@ extern "C" int pf_decoder_forward(const pf_stage_weights* stages, int n_stages, 
                                   const float* mask_logits, float* obj, float* dep, float* cls_out, float* logits_out,
                                   float* scaled_out, void* workspace, size_t workspace_bytes, int B, int N, int H, int W,
                                   int HWp, int flags, void* stream) {
+    return pf_decoder_forward_slice(stages, n_stages, feats, mask_logits, obj, dep, cls_out, logits_out, scaled_out,
+                                    workspace, workspace_bytes, B, 0, B, N, H, W, HWp, flags, stream);
+}
+
+extern "C" int pf_decoder_forward_slice(const pf_stage_weights* stages, int n_stages, const uint16_t* feats,
+                                        const float* mask_logits, float* obj, float* dep, float* cls_out,
+                                        float* logits_out, float* scaled_out, void* workspace, size_t workspace_bytes,
+                                        int B_total, int b0, int B, int N, int H, int W, int HWp, int flags, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
     reset_launch_count();
     PF_REQUIRE(stages && n_stages > 0 && feats && mask_logits && obj && dep && cls_out && logits_out && workspace,
                PF_ERR_ARG, "pf_decoder_forward: null pointer");
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && H > 0 && W > 0, PF_ERR_ARG, "pf_decoder_forward: bad shape");
+    PF_REQUIRE(b0 >= 0 && b0 + B <= B_total, PF_ERR_ARG, "pf_decoder_forward: bad batch window %d+%d of %d", b0, B, B_total);
     PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PF_ERR_ALIGN, "pf_decoder_forward: workspace not 256-byte aligned");
     const int HW = H * W;
     const int ffn = stages[0].ffn_channels;
+    const int ncls = stages[0].num_classes;
     const DecoderScratch s = carve(workspace, B, N, HW, ffn);
     PF_REQUIRE(workspace_bytes >= s.total, PF_ERR_WORKSPACE, "pf_decoder_forward: workspace %zu < %zu", workspace_bytes, s.total);
     const int S = pf_pool_splits(B, 2, HW);
+    // batch-major tensors: plain offsets; [2][B_total] tensors (feats, logits, scaled): addressed through the window
+    mask_logits += (size_t)b0 * N * HW;
+    obj += (size_t)b0 * N * PF_C, dep += (size_t)b0 * N * PF_C, cls_out += (size_t)b0 * N * ncls;
 
     if (int e = pf_binarise(mask_logits, s.bits, B, N, HW, stream)) return e;
     for (int st = 0; st < n_stages; ++st) {
         const bool last = st == n_stages - 1;
-        if (int e = pf_mask_pool(feats, s.bits, s.partial, s.cntp, B, N, HW, HWp, 2, S, stream)) return e;
+        if (int e = mask_pool_window(feats, s.bits, s.partial, s.cntp, B_total, b0, B, N, HW, HWp, 2, S, stream)) return e;
         if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, nullptr, s.kern, s.kbias,
                                      s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
             return e;
         int e;
         if (last)
-            e = pf_mask_einsum(feats, s.kern, s.kbias, logits_out, nullptr, B, N, HW, HWp, 2 * B, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, nullptr, B_total, b0, B, N, HW, HWp, 2 * B, stream);
         else if (flags & PF_FWD_ALL_STAGE_OUTPUTS)
-            e = pf_mask_einsum(feats, s.kern, s.kbias, logits_out, s.bits, B, N, HW, HWp, 2 * B, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, s.bits, B_total, b0, B, N, HW, HWp, 2 * B, stream);
         else  // only the sign of the next mask is observable (kernel_update_head.py:236-238)
-            e = pf_mask_einsum(feats, s.kern, s.kbias, nullptr, s.bits, B, N, HW, HWp, B, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, nullptr, s.bits, B_total, b0, B, N, HW, HWp, B, stream);
         if (e) return e;
     }
     if (scaled_out)
-        if (int e = pf_upsample2x(logits_out, scaled_out, 2 * B * N, H, W, stream)) return e;
+        for (int br = 0; br < 2; ++br) {
+            const size_t u0 = ((size_t)br * B_total + b0) * N;
+            if (int e = pf_upsample2x(logits_out + u0 * HW, scaled_out + u0 * 4 * HW, B * N, H, W, stream)) return e;
+        }
     return PF_OK;
 }

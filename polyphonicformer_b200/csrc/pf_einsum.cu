@@ -32,6 +32,7 @@ struct EinsumParams {
     uint32_t* bits;      // [B][WORDS][128] or null
     int N, HW, words, B;
     int tiles_per_unit, ctas_per_unit;
+    int Btot, b0;        // batch window inside the [2][Btot] feature / logits tensors
 };
 
 __global__ void __launch_bounds__(E_THREADS, 1)
@@ -56,6 +57,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     const int tile_begin = (int)((long long)j * p.tiles_per_unit / p.ctas_per_unit);
     const int tile_end = (int)((long long)(j + 1) * p.tiles_per_unit / p.ctas_per_unit);
     const int ntiles = tile_end - tile_begin;
+    const int gunit = (unit / p.B) * p.Btot + p.b0 + unit % p.B;   // unit inside the full-batch feature / logits tensors
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
@@ -94,7 +96,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 const uint32_t ph = (i / E_STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full[s], E_B_BYTES);
-                tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, unit * E_C,
+                tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, gunit * E_C,
                             kEvictFirst);
             }
         }
@@ -130,7 +132,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
         const int n = q * 32 + lane;
         const bool row_ok = n < p.N;
         const float bias = row_ok ? __ldg(p.kbias + (size_t)unit * p.N + n) : 0.f;
-        float* orow = p.logits ? p.logits + ((size_t)unit * p.N + (row_ok ? n : 0)) * p.HW : nullptr;
+        float* orow = p.logits ? p.logits + ((size_t)gunit * p.N + (row_ok ? n : 0)) * p.HW : nullptr;
         const bool vec_ok = (p.HW & 3) == 0;
         uint32_t* brow = (p.bits && unit < p.B) ? p.bits + (size_t)unit * p.words * 128 + n : nullptr;
         for (int i = 0; i < ntiles; ++i) {
@@ -213,10 +215,21 @@ extern "C" int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_u
     return PF_OK;
 }
 
+namespace pf {
+int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits, uint32_t* bits_out,
+                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, void* stream);
+}
 extern "C" int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
                               uint32_t* bits_out, int B, int N, int HW, int HWp, int n_units, void* stream) {
+    return pf::mask_einsum_window(feats, kern, kbias, logits, bits_out, B, 0, B, N, HW, HWp, n_units, stream);
+}
+
+// feats / logits: the FULL [2][Btot][..] tensors; kern / kbias / bits_out: buffers of the window's B images
+int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
+                           uint32_t* bits_out, int Btot, int b0, int B, int N, int HW, int HWp, int n_units, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
+    PF_REQUIRE(Btot >= B && b0 >= 0 && b0 + B <= Btot, PF_ERR_ARG, "pf_mask_einsum: bad batch window %d+%d of %d", b0, B, Btot);
     PF_REQUIRE(feats && kern && kbias, PF_ERR_ARG, "pf_mask_einsum: null input");
     PF_REQUIRE(logits || bits_out, PF_ERR_ARG, "pf_mask_einsum: no output requested");
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_mask_einsum: bad shape B=%d N=%d HW=%d", B, N, HW);
@@ -226,7 +239,7 @@ extern "C" int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern, const
     PF_REQUIRE(!logits || (reinterpret_cast<uintptr_t>(logits) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: logits not 16-byte aligned");
 
     CUtensorMap tmap;
-    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_units * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
+    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)(n_units / B) * Btot * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
 
     CUtensorMap tmap_k;
     if (int e = make_tmap_bf16_3d(&tmap_k, kern, (uint64_t)n_units * 2, (uint64_t)N, E_C, 128, 64)) return e;
@@ -234,6 +247,7 @@ extern "C" int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern, const
     EinsumParams p;
     p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
+    p.Btot = Btot, p.b0 = b0;
     p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
     int cpu = num_sms() / n_units;
     if (cpu < 1) cpu = 1;

@@ -24,6 +24,12 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
                       uint32_t box0);
 
+// batch-window variants of the streaming kernels (pf_decoder_forward_slice): feats / logits are full-batch tensors
+int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
+                     int N, int HW, int HWp, int n_branch, int S, void* stream);
+int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits, uint32_t* bits_out,
+                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, void* stream);
+
 #define PF_CHECK_LAUNCH(name)                                                          \
     do {                                                                               \
         cudaError_t e__ = cudaGetLastError();                                          \

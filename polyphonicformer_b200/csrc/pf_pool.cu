@@ -31,6 +31,7 @@ struct PoolParams {
     float* partial;        // [G][S][N][256]
     float* cntp;           // [G][S][N]
     int N, HW, words, B, S, tiles_per_unit;
+    int Btot, b0;          // batch window: this launch covers images b0 .. b0+B-1 of a [n_branch][Btot] feature tensor
 };
 
 // 8 mask bits -> 8 bf16 {0,1} packed in 4 u32 (element 2i in the low half)
@@ -84,7 +85,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
                 mbar_wait(&empty[s], ((i / P_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(&fullB[s], P_B_BYTES);
                 tma_load_2d(smem + s * P_STAGE_BYTES + P_A_BYTES, &tmap_feats, &fullB[s], (tile_begin + i) * P_BHW,
-                            unit * P_C, kEvictFirst);
+                            ((unit / p.B) * p.Btot + p.b0 + b) * P_C, kEvictFirst);
             }
         }
     } else if (warp == 1) {
@@ -202,10 +203,21 @@ extern "C" int pf_pool_splits(int B, int n_branch, int HW) {
     return S;
 }
 
+namespace pf {
+int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
+                     int N, int HW, int HWp, int n_branch, int S, void* stream);
+}
 extern "C" int pf_mask_pool(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int B, int N,
                             int HW, int HWp, int n_branch, int S, void* stream) {
+    return pf::mask_pool_window(feats, bits, partial, cntp, B, 0, B, N, HW, HWp, n_branch, S, stream);
+}
+
+// feats: the FULL [n_branch][Btot][256][HWp] tensor; bits / partial / cntp: buffers of the window's B images
+int pf::mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
+                         int N, int HW, int HWp, int n_branch, int S, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
+    PF_REQUIRE(Btot >= B && b0 >= 0 && b0 + B <= Btot, PF_ERR_ARG, "pf_mask_pool: bad batch window %d+%d of %d", b0, B, Btot);
     PF_REQUIRE(feats && bits && partial && cntp, PF_ERR_ARG, "pf_mask_pool: null pointer");
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0 && (n_branch == 1 || n_branch == 2), PF_ERR_ARG,
                "pf_mask_pool: bad shape B=%d N=%d HW=%d n_branch=%d", B, N, HW, n_branch);
@@ -215,8 +227,9 @@ extern "C" int pf_mask_pool(const uint16_t* feats, const uint32_t* bits, float* 
     PF_REQUIRE((reinterpret_cast<uintptr_t>(partial) & 15) == 0, PF_ERR_ALIGN, "pf_mask_pool: partial not 16-byte aligned");
 
     CUtensorMap tmap;
-    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_branch * B * P_C, (uint64_t)HW, (uint64_t)HWp, P_C, P_BHW)) return e;
+    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_branch * Btot * P_C, (uint64_t)HW, (uint64_t)HWp, P_C, P_BHW)) return e;
     PoolParams p;
+    p.Btot = Btot, p.b0 = b0;
     p.bits = bits, p.partial = partial, p.cntp = cntp;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B, p.S = S, p.tiles_per_unit = tiles;
     cudaError_t e = cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);

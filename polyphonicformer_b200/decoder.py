@@ -318,12 +318,31 @@ class DecoderEngine:
         return out
 
     # ------------------------------------------------------------------ the whole stage loop
-    def alloc_decode_buffers(self, B, N, H, W, upsample=True):
+    @staticmethod
+    def default_splits(B):
+        """Batch windows decoded concurrently (see decode_inplace).  Measured at B=4, 1024x2048: 1 window 0.663 ms,
+        2 windows 0.660 ms, 4 windows 0.741 ms per step -- the small-N block is latency-bound, so a half batch costs
+        as much as a full one and concurrency buys nothing; one window is the default."""
+        return 1
+
+    @staticmethod
+    def windows(B, splits):
+        """[(b0, Bsub)] -- contiguous, near-equal batch windows."""
+        splits = max(1, min(splits, B))
+        edges = [B * i // splits for i in range(splits + 1)]
+        return [(edges[i], edges[i + 1] - edges[i]) for i in range(splits)]
+
+    def alloc_decode_buffers(self, B, N, H, W, upsample=True, splits=None):
         HW = H * W
         lib = _cabi.load()
-        nbytes = lib.pf_decoder_workspace_bytes(B, N, HW, self.ffn_channels)
+        splits = self.default_splits(B) if splits is None else splits
+        wins = self.windows(B, splits)
+        ws = []
+        for _, bs in wins:
+            nbytes = lib.pf_decoder_workspace_bytes(bs, N, HW, self.ffn_channels)
+            ws.append((torch.empty(nbytes, dtype=torch.uint8, device=self.device), nbytes))
         return dict(
-            ws=torch.empty(nbytes, dtype=torch.uint8, device=self.device), ws_bytes=nbytes,
+            ws=ws, windows=wins,
             obj=torch.empty((B, N, PF_C), dtype=torch.float32, device=self.device),
             dep=torch.empty((B, N, PF_C), dtype=torch.float32, device=self.device),
             cls=torch.empty((B, N, self.num_classes), dtype=torch.float32, device=self.device),
@@ -346,13 +365,42 @@ class DecoderEngine:
                     object_feats=buf['obj'], depth_proposal=buf['dep'])
 
     def decode_inplace(self, feats, mask_logits, buf, H, W, all_stage_outputs=False):
-        """Launch-only variant (graph-capturable): obj/dep in ``buf`` are updated in place."""
-        B, N = buf['obj'].shape[:2]
-        _cabi.call('pf_decoder_forward', self.stage_array, len(self.stages), _ptr(feats), _ptr(mask_logits),
-                   _ptr(buf['obj']), _ptr(buf['dep']), _ptr(buf['cls']), _ptr(buf['logits']), _ptr(buf['scaled']),
-                   _ptr(buf['ws']), buf['ws_bytes'], B, N, H, W, feats.shape[-1],
-                   _cabi.PF_FWD_ALL_STAGE_OUTPUTS if all_stage_outputs else 0, _stream_ptr())
+        """Launch-only variant (graph-capturable): obj/dep in ``buf`` are updated in place.
 
+        The batch is decoded as ``len(buf['windows'])`` disjoint windows, each through ``pf_decoder_forward_slice`` on
+        its own stream (window 0 on the current stream, the others on side streams forked from / joined to it with
+        events).  Frames are independent, so this changes no result; it lets the latency-bound small-N block of one
+        window run under the HBM-bound pooling / einsum of another."""
+        B, N = buf['obj'].shape[:2]
+        flags = _cabi.PF_FWD_ALL_STAGE_OUTPUTS if all_stage_outputs else 0
+        cur = torch.cuda.current_stream()
+        wins = buf['windows']
+        side = self._side_streams(len(wins) - 1)
+        fork = None
+        if side:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+        launches = 0
+        for i, ((b0, bs), (ws, ws_bytes)) in enumerate(zip(wins, buf['ws'])):
+            st = cur if i == 0 else side[i - 1]
+            if i > 0:
+                st.wait_event(fork)
+            _cabi.call('pf_decoder_forward_slice', self.stage_array, len(self.stages), _ptr(feats), _ptr(mask_logits),
+                       _ptr(buf['obj']), _ptr(buf['dep']), _ptr(buf['cls']), _ptr(buf['logits']), _ptr(buf['scaled']),
+                       _ptr(ws), ws_bytes, B, b0, bs, N, H, W, feats.shape[-1], flags,
+                       ctypes.c_void_p(st.cuda_stream))
+            launches += _cabi.load().pf_last_launch_count()
+            if i > 0:
+                join = torch.cuda.Event()
+                join.record(st)
+                cur.wait_event(join)
+        self.last_launches = launches
+
+    def _side_streams(self, n):
+        pool = self.__dict__.setdefault('_streams', [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(self.device))
+        return pool[:n]
 
 class HostPipeline:
     """Decoder over HOST buffers: the call a user of the C ABI makes when feature maps and proposals live in pinned

@@ -166,3 +166,27 @@ def test_host_pipeline_matches_resident_decode(dev, H, W):
         assert torch.equal(outs[i]['cls'], want[i][0]), i
         assert torch.equal(outs[i]['scaled'], want[i][1]), i
     assert pipe.h2d_bytes() > 0 and pipe.d2h_bytes() == outs[0]['cls'].numel() * 4 + outs[0]['scaled'].numel() * 4
+
+
+def test_batch_windows_agree(dev):
+    """decode_inplace over 1, 2 and 3 concurrent batch windows (ragged: 3 images) gives the same results up to the
+    pooling summation order (the split-K slab count depends on the window size)."""
+    B, H, W, seed = 3, 16, 24, 1
+    eng, _ = make_engine(seed, dev)
+    inp = synth.synth_decoder_inputs(B, H, W, seed)
+    feats = eng.prepare_feats(inp['x_feats'].to(dev), inp['depth_feats'].to(dev))
+    mask = inp['mask_preds'].to(dev)
+    obj0 = inp['proposal_feats'].reshape(B, -1, 256).to(dev)
+    dep0 = inp['depth_proposal'].reshape(B, -1, 256).to(dev)
+    outs = []
+    for splits in (1, 2, 3):
+        buf = eng.alloc_decode_buffers(B, obj0.shape[1], H, W, splits=splits)
+        assert [w[1] for w in buf['windows']] == {1: [3], 2: [1, 2], 3: [1, 1, 1]}[splits]
+        buf['obj'].copy_(obj0), buf['dep'].copy_(dep0)
+        eng.decode_inplace(feats, mask, buf, H, W)
+        torch.cuda.synchronize()
+        outs.append({k: buf[k].clone() for k in ('scaled', 'logits', 'cls', 'obj', 'dep')})
+    for o in outs[1:]:
+        for k, v in o.items():
+            l2, mx = rel_err(v.cpu(), outs[0][k].cpu())
+            assert l2 < 2e-5 and mx < 1e-4, (k, l2, mx)
