@@ -6,8 +6,11 @@
 //        accumulate), TMA-loaded once per CTA, K-major, resident in shared memory (2 x 64 KB, 128-byte swizzle);
 //   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 3-stage ring;
 //   D  = [128 lanes][64 columns] fp32 in TMEM, 4 accumulator buffers so the epilogue overlaps the next tiles;
-//   epilogue: tcgen05.ld -> + bias -> fp32 logits (128-bit stores) and/or the packed sign bits consumed by the next
-//             stage's pooling (thread = kernel row n, 32 consecutive pixels = one u32 word).
+//   epilogue: tcgen05.ld -> + bias -> the packed sign bits consumed by the next stage's pooling (thread = kernel row
+//             n, 32 consecutive pixels = one u32 word) and/or fp32 logits.  Logits leave through shared memory:
+//             each thread writes its 32 pixels into a 128-byte-swizzled [128 rows][32 px] tile, one thread issues a
+//             TMA tensor store of the tile (rows >= N are clipped by the tensor map), two tiles in flight.  (Direct
+//             per-thread stores touch 32 different 128-byte lines per warp instruction and were LSU-bound.)
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // The kernel is HBM-bound (59 FLOP/B against a ridge of ~213): see DESIGN.md for the roofline.
@@ -18,13 +21,16 @@ namespace pf {
 
 constexpr int E_C = PF_C;            // 256 = K of the GEMM
 constexpr int E_BHW = 64;            // pixels per tile (= N of the MMA, one 128-byte swizzle atom of bf16)
-constexpr int E_STAGES = 3;
+constexpr int E_STAGES = 3;          // feature ring depth without the logits staging tiles
+constexpr int E_STAGES_TMA = 2;      // ... with them (the output traffic halves the load rate a CTA must sustain)
+constexpr int E_OUT_BYTES = 128 * 32 * 4;   // one staged half tile: [128 rows][32 px] fp32
 constexpr int E_ACC = 4;             // TMEM accumulator buffers
 constexpr int E_TMEM_COLS = E_ACC * E_BHW;  // 256
 constexpr int E_A_BYTES = 128 * E_C * 2;    // 65536 per (hi | lo)
 constexpr int E_B_BYTES = E_C * E_BHW * 2;  // 32768 per stage
 constexpr int E_THREADS = 192;
 constexpr int E_SMEM = 2 * E_A_BYTES + E_STAGES * E_B_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+static_assert(E_STAGES_TMA * E_B_BYTES + 2 * E_OUT_BYTES <= E_STAGES * E_B_BYTES, "staging tiles must fit in the ring");
 
 struct EinsumParams {
     const float* kbias;  // [G][N]
@@ -35,14 +41,27 @@ struct EinsumParams {
     int Btot, b0;        // batch window inside the [2][Btot] feature / logits tensors
 };
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void epi_bar4() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
+// TMA_OUT: fp32 logits leave as TMA tensor stores of staged tiles (tmap_out over [units][N][HW]); the feature ring
+// then has STAGES = 2 and the two staging tiles live behind it.
+template <bool TMA_OUT>
 __global__ void __launch_bounds__(E_THREADS, 1)
 einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_kern,
-              const EinsumParams p) {
+              const __grid_constant__ CUtensorMap tmap_out, const EinsumParams p) {
+    constexpr int STAGES = TMA_OUT ? E_STAGES_TMA : E_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA_hi = smem;
     uint8_t* sA_lo = smem + E_A_BYTES;
     uint8_t* sB = smem + 2 * E_A_BYTES;
+    uint8_t* sOut = sB + E_STAGES_TMA * E_B_BYTES;   // TMA_OUT only: 2 x [128][32] fp32, 1024-byte aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + E_STAGES * E_B_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + E_STAGES;
@@ -62,8 +81,9 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
         tma_prefetch_desc(&tmap_kern);
+        if (TMA_OUT) tma_prefetch_desc(&tmap_out);
         mbar_init(abar, 1);
-        for (int i = 0; i < E_STAGES; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
@@ -92,8 +112,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                     tma_load_3d(sA_hi + h * E_A_BYTES + kb * (128 * 128), &tmap_kern, abar, kb * 64, 0, unit * 2 + h,
                                 kEvictLast);
             for (int i = 0; i < ntiles; ++i) {
-                const int s = i % E_STAGES;
-                const uint32_t ph = (i / E_STAGES) & 1;
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&full[s], E_B_BYTES);
                 tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, gunit * E_C,
@@ -107,9 +127,9 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
             mbar_wait(abar, 0);
             for (int i = 0; i < ntiles; ++i) {
-                const int s = i % E_STAGES, a = i % E_ACC;
+                const int s = i % STAGES, a = i % E_ACC;
                 mbar_wait(&tempty[a], ((i / E_ACC) & 1) ^ 1);
-                mbar_wait(&full[s], (i / E_STAGES) & 1);
+                mbar_wait(&full[s], (i / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + a * E_BHW;
                 const uint32_t b_base = smem_u32(sB + s * E_B_BYTES);
@@ -163,7 +183,22 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 const int valid = p.HW - hwb;  // > 0
                 if (valid < 32) word &= (1u << valid) - 1u;
                 if (brow) brow[(size_t)(hwb >> 5) * 128] = word;
-                if (orow && row_ok) {
+                if (TMA_OUT) {
+                    // staged tile (2*i + h) & 1: wait until the store issued two half tiles ago has read it
+                    uint8_t* tile = sOut + ((2 * i + h) & 1) * E_OUT_BYTES;
+                    if (threadIdx.x == 64) tma_store_wait_read<1>();
+                    epi_bar4();
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(tile + sw128_offset(n, c)) =
+                            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    fence_proxy_async_smem();
+                    epi_bar4();
+                    if (threadIdx.x == 64) {
+                        tma_store_3d(&tmap_out, tile, hwb, 0, gunit);
+                        tma_store_commit();
+                    }
+                } else if (orow && row_ok) {
                     float* dst = orow + hwb;
                     if (vec_ok && valid >= 32) {
 #pragma unroll
@@ -180,6 +215,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             }
         }
     }
+    if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read<0>();   // shared memory must outlive the last store's read
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<E_TMEM_COLS>(tmem_base);
@@ -254,9 +290,15 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     if (cpu > p.tiles_per_unit) cpu = p.tiles_per_unit;
     p.ctas_per_unit = cpu;
 
-    cudaError_t ea = cudaFuncSetAttribute(einsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
+    // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
+    const bool tma_out = logits && (HW % 4) == 0;
+    CUtensorMap tmap_o = tmap_k;
+    if (tma_out)
+        if (int e = make_tmap_f32_3d(&tmap_o, logits, (uint64_t)(n_units / B) * Btot, (uint64_t)N, (uint64_t)HW, 128, 32)) return e;
+    auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
+    cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
-    einsum_kernel<<<n_units * cpu, E_THREADS, E_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, tmap_k, p);
+    kern_fn<<<n_units * cpu, E_THREADS, E_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, tmap_k, tmap_o, p);
     PF_CHECK_LAUNCH("einsum_kernel");
     return PF_OK;
 }

@@ -98,6 +98,23 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t 
     return PF_OK;
 }
 
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
+                     uint32_t box0) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(PF_ERR_ALIGN, "TMA base not 16-byte aligned");
+    if ((d0 * 4) % 16 != 0) return set_error(PF_ERR_ALIGN, "TMA row pitch not a 16-byte multiple");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled(f32 3d) failed with CUresult %d", (int)r);
+    return PF_OK;
+}
+
 }  // namespace pf
 
 extern "C" int pf_version(void) { return 100; }

@@ -24,6 +24,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
                       uint32_t box0);
 
+// 3-D fp32 tensor [d2][d1][d0] (dense); box = [1][box1][box0], 128-byte swizzle (box0 * 4 bytes must be 128)
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
+                     uint32_t box0);
+
 // batch-window variants of the streaming kernels (pf_decoder_forward_slice): feats / logits are full-batch tensors
 int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
                      int N, int HW, int HWp, int n_branch, int S, void* stream);
