@@ -71,20 +71,23 @@ extern "C" int pf_decoder_forward_slice(const pf_stage_weights* stages, int n_st
     mask_logits += (size_t)b0 * N * HW;
     obj += (size_t)b0 * N * PF_C, dep += (size_t)b0 * N * PF_C, cls_out += (size_t)b0 * N * ncls;
 
+    // Every kernel of the loop is launched with programmatic stream serialization.  binarise waits for everything
+    // before this call (the producers of feats / mask_logits / obj / dep) BEFORE it releases its dependents, so the
+    // pooling and einsum kernels may stream the feature maps ahead of their own grid dependency (early_feats = 1).
     if (int e = pf_binarise(mask_logits, s.bits, B, N, HW, stream)) return e;
     for (int st = 0; st < n_stages; ++st) {
         const bool last = st == n_stages - 1;
-        if (int e = mask_pool_window(feats, s.bits, s.partial, s.cntp, B_total, b0, B, N, HW, HWp, 2, S, stream)) return e;
+        if (int e = mask_pool_window(feats, s.bits, s.partial, s.cntp, B_total, b0, B, N, HW, HWp, 2, S, 1, stream)) return e;
         if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, nullptr, s.kern, s.kbias,
                                      s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
             return e;
         int e;
         if (last)
-            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, nullptr, B_total, b0, B, N, HW, HWp, 2 * B, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, nullptr, B_total, b0, B, N, HW, HWp, 2 * B, 1, stream);
         else if (flags & PF_FWD_ALL_STAGE_OUTPUTS)
-            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, s.bits, B_total, b0, B, N, HW, HWp, 2 * B, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, s.bits, B_total, b0, B, N, HW, HWp, 2 * B, 1, stream);
         else  // only the sign of the next mask is observable (kernel_update_head.py:236-238)
-            e = mask_einsum_window(feats, s.kern, s.kbias, nullptr, s.bits, B_total, b0, B, N, HW, HWp, B, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, nullptr, s.bits, B_total, b0, B, N, HW, HWp, B, 1, stream);
         if (e) return e;
     }
     if (scaled_out)

@@ -16,6 +16,7 @@
 // The kernel is HBM-bound (59 FLOP/B against a ridge of ~213): see DESIGN.md for the roofline.
 #include "pf_internal.h"
 #include "pf_sm100.cuh"
+#include "pf_debug.cuh"
 
 namespace pf {
 
@@ -39,6 +40,7 @@ struct EinsumParams {
     int N, HW, words, B;
     int tiles_per_unit, ctas_per_unit;
     int Btot, b0;        // batch window inside the [2][Btot] feature / logits tensors
+    int early_feats;     // the feature maps were complete before the PREVIOUS kernel started: prefetch them before pdl_wait
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
@@ -77,6 +79,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     const int tile_end = (int)((long long)(j + 1) * p.tiles_per_unit / p.ctas_per_unit);
     const int ntiles = tile_end - tile_begin;
     const int gunit = (unit / p.B) * p.Btot + p.b0 + unit % p.B;   // unit inside the full-batch feature / logits tensors
+    long long* dbg = dbg_claim_all(TMA_OUT ? 21 : 20);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
@@ -99,10 +102,21 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    DBG(1);
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            // inside the decode loop the feature tiles are long-complete inputs: fill the ring before the grid
+            // dependency resolves
+            if (!p.early_feats) pdl_wait();
+            const int pre = ntiles < STAGES ? ntiles : STAGES;
+            for (int i = 0; i < pre; ++i) {
+                mbar_arrive_expect_tx(&full[i], E_B_BYTES);
+                tma_load_2d(sB + i * E_B_BYTES, &tmap_feats, &full[i], (tile_begin + i) * E_BHW, gunit * E_C, kEvictFirst);
+            }
+            pdl_wait();   // the dynamic kernels come from the previous kernel
             // A operand: [hi | lo] x 4 K-blocks of [128 rows][64 k]; rows >= N are out of bounds -> zero filled
             mbar_arrive_expect_tx(abar, 2 * E_A_BYTES);
 #pragma unroll
@@ -111,10 +125,12 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 for (int kb = 0; kb < 4; ++kb)
                     tma_load_3d(sA_hi + h * E_A_BYTES + kb * (128 * 128), &tmap_kern, abar, kb * 64, 0, unit * 2 + h,
                                 kEvictLast);
-            for (int i = 0; i < ntiles; ++i) {
+            for (int i = pre; i < ntiles; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                if (i == 3) DBG(2);
+                if (i == ntiles - 1) DBG(3);
                 mbar_arrive_expect_tx(&full[s], E_B_BYTES);
                 tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, gunit * E_C,
                             kEvictFirst);
@@ -148,6 +164,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
         }
     } else {
         // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
+        pdl_wait();   // kbias is read and bits / logits are written only after the previous kernels have completed
         const int q = warp & 3;
         const int n = q * 32 + lane;
         const bool row_ok = n < p.N;
@@ -218,10 +235,12 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read<0>();   // shared memory must outlive the last store's read
     tc_fence_before();
     __syncthreads();
+    DBG(13);
     if (warp == 1) tmem_dealloc<E_TMEM_COLS>(tmem_base);
 }
 
 }  // namespace pf
+PF_DEFINE_DBG_SETTER(set_dbg_einsum)
 
 // fp32 kernels [G][N][256] -> bf16 hi / lo [G][2][N][256] (hi = bf16(x), lo = bf16(x - hi))
 namespace pf {
@@ -253,16 +272,17 @@ extern "C" int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_u
 
 namespace pf {
 int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits, uint32_t* bits_out,
-                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, void* stream);
+                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int early_feats, void* stream);
 }
 extern "C" int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
                               uint32_t* bits_out, int B, int N, int HW, int HWp, int n_units, void* stream) {
-    return pf::mask_einsum_window(feats, kern, kbias, logits, bits_out, B, 0, B, N, HW, HWp, n_units, stream);
+    return pf::mask_einsum_window(feats, kern, kbias, logits, bits_out, B, 0, B, N, HW, HWp, n_units, 0, stream);
 }
 
 // feats / logits: the FULL [2][Btot][..] tensors; kern / kbias / bits_out: buffers of the window's B images
 int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
-                           uint32_t* bits_out, int Btot, int b0, int B, int N, int HW, int HWp, int n_units, void* stream) {
+                           uint32_t* bits_out, int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int early_feats,
+                           void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(Btot >= B && b0 >= 0 && b0 + B <= Btot, PF_ERR_ARG, "pf_mask_einsum: bad batch window %d+%d of %d", b0, B, Btot);
@@ -283,7 +303,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     EinsumParams p;
     p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
-    p.Btot = Btot, p.b0 = b0;
+    p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats;
     p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
     int cpu = num_sms() / n_units;
     if (cpu < 1) cpu = 1;
@@ -298,7 +318,6 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
     cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
-    kern_fn<<<n_units * cpu, E_THREADS, E_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, tmap_k, tmap_o, p);
-    PF_CHECK_LAUNCH("einsum_kernel");
-    return PF_OK;
+    return launch_pdl("einsum_kernel", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,
+                      static_cast<cudaStream_t>(stream), tmap, tmap_k, tmap_o, p);
 }

@@ -34,6 +34,10 @@ constexpr int BIN_WARPS = 16;
 __global__ void __launch_bounds__(BIN_WARPS * 32) binarise_kernel(const float* __restrict__ logits,
                                                                   uint32_t* __restrict__ bits, int N, int HW, int words) {
     __shared__ uint32_t s_bits[BIN_WORDS][128];
+    // wait FIRST, then release the dependents: the pooling kernel that follows starts streaming the feature maps
+    // without waiting, which is only safe once everything before this kernel (their producer) has completed
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int w0 = blockIdx.x * BIN_WORDS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +80,8 @@ __global__ void __launch_bounds__(BIN_WARPS * 32) binarise_kernel(const float* _
 // Thread = 1 input pixel column pair -> 4 output columns x 2 output rows (the 2x2 outputs of input pixels x, x+1).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
                                                          int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int map = blockIdx.z;
     const int y = blockIdx.y;  // input row; produces output rows 2y, 2y+1
     const float* src = in + (size_t)map * H * W;
@@ -154,9 +160,8 @@ extern "C" int pf_binarise(const float* mask_logits, uint32_t* bits, int B, int 
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_binarise: bad shape B=%d N=%d HW=%d", B, N, HW);
     const int words = (HW + 31) / 32;
     dim3 grid((words + BIN_WORDS - 1) / BIN_WORDS, B);
-    binarise_kernel<<<grid, BIN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(mask_logits, bits, N, HW, words);
-    PF_CHECK_LAUNCH("binarise_kernel");
-    return PF_OK;
+    return launch_pdl("binarise_kernel", binarise_kernel, grid, dim3(BIN_WARPS * 32), 0, static_cast<cudaStream_t>(stream),
+                      mask_logits, bits, N, HW, words);
 }
 
 extern "C" int pf_upsample2x(const float* in, float* out, int maps, int H, int W, void* stream) {
@@ -169,7 +174,6 @@ extern "C" int pf_upsample2x(const float* in, float* out, int maps, int H, int W
     int threads = 256;
     while (threads > 32 && threads / 2 >= pairs) threads /= 2;
     dim3 grid((pairs + threads - 1) / threads, H, maps);
-    upsample2x_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, H, W);
-    PF_CHECK_LAUNCH("upsample2x_kernel");
-    return PF_OK;
+    return launch_pdl("upsample2x_kernel", upsample2x_kernel, grid, dim3(threads), 0, static_cast<cudaStream_t>(stream), in,
+                      out, H, W);
 }

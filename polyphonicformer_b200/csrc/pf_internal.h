@@ -30,9 +30,25 @@ int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d
 
 // batch-window variants of the streaming kernels (pf_decoder_forward_slice): feats / logits are full-batch tensors
 int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
-                     int N, int HW, int HWp, int n_branch, int S, void* stream);
+                     int N, int HW, int HWp, int n_branch, int S, int early_feats, void* stream);
 int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits, uint32_t* bits_out,
-                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, void* stream);
+                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int early_feats, void* stream);
+
+// Launch with programmatic stream serialization (PDL): the kernel may begin before its predecessor in the stream has
+// finished; it must execute griddepcontrol.wait (pdl_wait) before touching anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+int launch_pdl(const char* name, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e));
+    count_launch();
+    return PF_OK;
+}
 
 #define PF_CHECK_LAUNCH(name)                                                          \
     do {                                                                               \

@@ -13,6 +13,7 @@
 // warps 2..5 = bit expanders, then epilogue.  HBM-bound: 2*C*HW*2 bytes of features per image dominate.
 #include "pf_internal.h"
 #include "pf_sm100.cuh"
+#include "pf_debug.cuh"
 
 namespace pf {
 
@@ -32,6 +33,7 @@ struct PoolParams {
     float* cntp;           // [G][S][N]
     int N, HW, words, B, S, tiles_per_unit;
     int Btot, b0;          // batch window: this launch covers images b0 .. b0+B-1 of a [n_branch][Btot] feature tensor
+    int early_feats;       // the feature maps were complete before the PREVIOUS kernel started: stream them before pdl_wait
 };
 
 // 8 mask bits -> 8 bf16 {0,1} packed in 4 u32 (element 2i in the low half)
@@ -61,6 +63,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
     const int tile_begin = (int)((long long)split * p.tiles_per_unit / p.S);
     const int tile_end = (int)((long long)(split + 1) * p.tiles_per_unit / p.S);
     const int ntiles = tile_end - tile_begin;
+    long long* dbg = dbg_claim_all(10);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
@@ -77,12 +80,20 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    DBG(1);
+    pdl_launch_dependents();
+    // Inside the decode loop the feature tiles are long-complete inputs (early_feats): the producer streams them
+    // without waiting for the previous kernel.  Only the mask bits come from it, so the expander warps (which also do
+    // every global write of this CTA) wait on the grid dependency.
 
     if (warp == 0) {
         if (lane == 0) {
+            if (!p.early_feats) pdl_wait();
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % P_STAGES;
                 mbar_wait(&empty[s], ((i / P_STAGES) & 1) ^ 1);
+                if (i == 4) DBG(2);
+                if (i == ntiles - 1) DBG(3);
                 mbar_arrive_expect_tx(&fullB[s], P_B_BYTES);
                 tma_load_2d(smem + s * P_STAGE_BYTES + P_A_BYTES, &tmap_feats, &fullB[s], (tile_begin + i) * P_BHW,
                             ((unit / p.B) * p.Btot + p.b0 + b) * P_C, kEvictFirst);
@@ -109,6 +120,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
         }
     } else {
         // ---- expanders: thread = mask row r (TMEM lane r later in the epilogue)
+        pdl_wait();
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t* brow = p.bits + (size_t)b * p.words * 128 + r;
@@ -156,8 +168,12 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
     }
     tc_fence_before();
     __syncthreads();
+    DBG(13);
     if (warp == 1) tmem_dealloc<P_TMEM_COLS>(tmem_base);
 }
+}  // namespace pf
+PF_DEFINE_DBG_SETTER(set_dbg_pool)
+namespace pf {
 
 // sum over splits in a fixed order: pooled[g][n][c], count[b][n].  64 threads x float4 per row, 4 rows per block.
 __global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restrict__ partial,
@@ -205,16 +221,16 @@ extern "C" int pf_pool_splits(int B, int n_branch, int HW) {
 
 namespace pf {
 int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
-                     int N, int HW, int HWp, int n_branch, int S, void* stream);
+                     int N, int HW, int HWp, int n_branch, int S, int early_feats, void* stream);
 }
 extern "C" int pf_mask_pool(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int B, int N,
                             int HW, int HWp, int n_branch, int S, void* stream) {
-    return pf::mask_pool_window(feats, bits, partial, cntp, B, 0, B, N, HW, HWp, n_branch, S, stream);
+    return pf::mask_pool_window(feats, bits, partial, cntp, B, 0, B, N, HW, HWp, n_branch, S, 0, stream);
 }
 
 // feats: the FULL [n_branch][Btot][256][HWp] tensor; bits / partial / cntp: buffers of the window's B images
 int pf::mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
-                         int N, int HW, int HWp, int n_branch, int S, void* stream) {
+                         int N, int HW, int HWp, int n_branch, int S, int early_feats, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(Btot >= B && b0 >= 0 && b0 + B <= Btot, PF_ERR_ARG, "pf_mask_pool: bad batch window %d+%d of %d", b0, B, Btot);
@@ -229,14 +245,13 @@ int pf::mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* par
     CUtensorMap tmap;
     if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)n_branch * Btot * P_C, (uint64_t)HW, (uint64_t)HWp, P_C, P_BHW)) return e;
     PoolParams p;
-    p.Btot = Btot, p.b0 = b0;
+    p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats;
     p.bits = bits, p.partial = partial, p.cntp = cntp;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B, p.S = S, p.tiles_per_unit = tiles;
     cudaError_t e = cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "pool smem attribute: %s", cudaGetErrorString(e));
-    pool_kernel<<<n_branch * B * S, P_THREADS, P_SMEM, static_cast<cudaStream_t>(stream)>>>(tmap, p);
-    PF_CHECK_LAUNCH("pool_kernel");
-    return PF_OK;
+    return launch_pdl("pool_kernel", pool_kernel, dim3(n_branch * B * S), dim3(P_THREADS), P_SMEM,
+                      static_cast<cudaStream_t>(stream), tmap, p);
 }
 
 extern "C" int pf_pool_reduce(const float* partial, const float* cntp, float* pooled, float* count, int B, int N,

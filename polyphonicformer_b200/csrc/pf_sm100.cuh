@@ -58,6 +58,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Everything a kernel does before pdl_wait() may overlap the tail of the previous kernel of the stream (when both
+// were launched with cudaLaunchAttributeProgrammaticStreamSerialization); after it, all memory written by the
+// previous kernels is visible.  pdl_launch_dependents() lets the next kernel start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -29,6 +29,7 @@
 
 #include "pf_internal.h"
 #include "pf_sm100.cuh"
+#include "pf_debug.cuh"
 
 namespace pf {
 
@@ -92,9 +93,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// programmatic dependent launch: everything before pdl_wait() may overlap the previous kernel of the stream
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -211,24 +209,6 @@ struct Mail {
         rstd = 1.f / sqrtf((m2 + 32.f * dv) * (1.f / 256.f) + U_LN_EPS);
     }
 };
-
-// Optional in-kernel timeline (pf_debug_timeline): CTA (0,0,0) of every tcgemm launch appends 16 clock samples.
-__device__ long long* g_dbg = nullptr;
-__device__ __forceinline__ long long gtime() {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define DBG(i) do { if (dbg) dbg[i] = gtime(); } while (0)
-// block (0,0,0), thread 0 of the helper kernels: claim a record, tag it
-__device__ __forceinline__ long long* dbg_claim(int tag) {
-    if (!g_dbg || blockIdx.x || blockIdx.y || blockIdx.z || threadIdx.x) return nullptr;
-    const unsigned long long slot = atomicAdd(reinterpret_cast<unsigned long long*>(g_dbg), 1ull);
-    long long* d = g_dbg + 16 + slot * 16;
-    d[0] = gtime();
-    d[15] = tag;
-    return d;
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(T_THREADS, 1)
@@ -1016,9 +996,14 @@ static int run_updator(const Maps& mp, const pf_stage_weights* w, uint16_t* aren
 
 // Debug: device buffer of int64 [16 + 16 * capacity] (zeroed by the caller) receiving the in-kernel timeline of CTA
 // (0,0,0) of every tcgemm launch; pass NULL to switch it off.  Not part of the product path.
+PF_DEFINE_DBG_SETTER(set_dbg_update)
+namespace pf {
+int set_dbg_pool(long long* p);
+int set_dbg_einsum(long long* p);
+}
 extern "C" int pf_debug_timeline(long long* device_buffer) {
-    cudaError_t e = cudaMemcpyToSymbol(pf::g_dbg, &device_buffer, sizeof(device_buffer));
-    return e == cudaSuccess ? PF_OK : pf::set_error(PF_ERR_CUDA, "pf_debug_timeline: %s", cudaGetErrorString(e));
+    const int e = pf::set_dbg_update(device_buffer) | pf::set_dbg_pool(device_buffer) | pf::set_dbg_einsum(device_buffer);
+    return e == 0 ? PF_OK : pf::set_error(PF_ERR_CUDA, "pf_debug_timeline: cudaMemcpyToSymbol failed (%d)", e);
 }
 
 extern "C" size_t pf_update_workspace_bytes(int B, int N, int ffn_channels) {
