@@ -77,61 +77,61 @@ __global__ void __launch_bounds__(BIN_WARPS * 32) binarise_kernel(const float* _
 // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on [maps][H][W] planes
 // (polyphonic/kernel_update.py:133-143).  src = (dst + 0.5)/2 - 0.5 clamped at 0; weights follow ATen's
 // upsample_bilinear2d: h0l*(w0l*a + w1l*b) + h1l*(w0l*c + w1l*d).
-// Thread = 1 input pixel column pair -> 4 output columns x 2 output rows (the 2x2 outputs of input pixels x, x+1).
-__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+// Thread = 1 input pixel column pair (x, x+1) -> 4 output columns, walking down a strip of UP_ROWS input rows with a
+// rolling window of horizontally interpolated rows: every input row is interpolated horizontally once per strip and
+// used by the (up to) three output rows that depend on it.
+constexpr int UP_ROWS = 8;
+
+// horizontal pass: output columns 2x .. 2x+3 of one input row
+__device__ __forceinline__ void up_hrow(const float* __restrict__ row, int x, int W, float (&h)[4]) {
+    const int c0 = max(x - 1, 0), c2 = min(x + 1, W - 1), c3 = min(x + 2, W - 1);
+    const float a0 = __ldg(row + c0), a1 = __ldg(row + x), a2 = __ldg(row + c2), a3 = __ldg(row + c3);
+    // out col 2x   : src = x - 0.25 -> (x-1, x) weights (0.25, 0.75); at x == 0 the source clamps to column 0
+    h[0] = (x == 0) ? (1.f * a1 + 0.f * a2) : (0.25f * a0 + 0.75f * a1);
+    h[1] = 0.75f * a1 + 0.25f * a2;   // src = x + 0.25
+    h[2] = 0.25f * a1 + 0.75f * a2;   // src = x + 0.75
+    h[3] = 0.75f * a2 + 0.25f * a3;   // src = x + 1.25 -> (x+1, x+2)
+}
+
+__global__ void __launch_bounds__(128) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
                                                          int W) {
     pdl_launch_dependents();
     pdl_wait();
     const int map = blockIdx.z;
-    const int y = blockIdx.y;  // input row; produces output rows 2y, 2y+1
+    const int y0 = blockIdx.y * UP_ROWS;
+    const int y1 = min(y0 + UP_ROWS, H);
     const float* src = in + (size_t)map * H * W;
     float* dst = out + (size_t)map * (4 * (size_t)H * W);
     const int W2 = 2 * W;
-    const int ym = max(y - 1, 0), yp = min(y + 1, H - 1);
-    const float* r0 = src + (size_t)ym * W;
-    const float* r1 = src + (size_t)y * W;
-    const float* r2 = src + (size_t)yp * W;
-    // output row 2y   : src_y = y - 0.25 -> rows (y-1, y) weights (0.25, 0.75); at y = 0 clamps to row 0 weight 1
-    // output row 2y+1 : src_y = y + 0.25 -> rows (y, y+1) weights (0.75, 0.25); at y = H-1 both rows are H-1
-    const float t0 = (y == 0) ? 0.f : 0.25f;   // weight of r0 in the top output row (h0lambda) else
-    for (int xp = blockIdx.x * blockDim.x + threadIdx.x; xp * 2 < W; xp += gridDim.x * blockDim.x) {
-        const int x = xp * 2;
-        // input columns x-1 .. x+2 (clamped)
-        const int c0 = max(x - 1, 0), c1 = x, c2 = min(x + 1, W - 1), c3 = min(x + 2, W - 1);
-        float a[3][4];
-        a[0][0] = __ldg(r0 + c0), a[0][1] = __ldg(r0 + c1), a[0][2] = __ldg(r0 + c2), a[0][3] = __ldg(r0 + c3);
-        a[1][0] = __ldg(r1 + c0), a[1][1] = __ldg(r1 + c1), a[1][2] = __ldg(r1 + c2), a[1][3] = __ldg(r1 + c3);
-        a[2][0] = __ldg(r2 + c0), a[2][1] = __ldg(r2 + c1), a[2][2] = __ldg(r2 + c2), a[2][3] = __ldg(r2 + c3);
-        // horizontal pass for the 4 output columns 2x .. 2x+3 of each of the 3 input rows
-        float hrow[3][4];
-        const float l0 = (x == 0) ? 0.f : 0.25f;  // weight of column x-1 for output column 2x
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            // out col 2x   : (x-1, x) with lambdas (w0 = 1 - w1, w1): src = x - 0.25 -> x0 = x-1, w1 = 0.75
-            //               at x == 0: src clamps to 0 -> x0 = 0, w1 = 0 -> value a[r][1] (c0 == c1 == 0)
-            hrow[r][0] = (x == 0) ? (1.f * a[r][1] + 0.f * a[r][2]) : (l0 * a[r][0] + 0.75f * a[r][1]);
-            // out col 2x+1 : src = x + 0.25 -> (x, x+1) weights (0.75, 0.25)
-            hrow[r][1] = 0.75f * a[r][1] + 0.25f * a[r][2];
-            // out col 2x+2 : src = x + 0.75 -> (x, x+1) weights (0.25, 0.75)
-            hrow[r][2] = 0.25f * a[r][1] + 0.75f * a[r][2];
-            // out col 2x+3 : src = x + 1.25 -> (x+1, x+2) weights (0.75, 0.25)
-            hrow[r][3] = 0.75f * a[r][2] + 0.25f * a[r][3];
-        }
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = xp * 2;
+    if (x >= W) return;
+    const bool vec = x + 1 < W && (W2 & 3) == 0;
+    float hA[4], hB[4], hC[4];
+    up_hrow(src + (size_t)max(y0 - 1, 0) * W, x, W, hA);
+    up_hrow(src + (size_t)y0 * W, x, W, hB);
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y) {
+        up_hrow(src + (size_t)min(y + 1, H - 1) * W, x, W, hC);
+        // output row 2y   : src_y = y - 0.25 -> rows (y-1, y) weights (0.25, 0.75); at y == 0 it clamps to row 0
+        // output row 2y+1 : src_y = y + 0.25 -> rows (y, y+1) weights (0.75, 0.25); at y == H-1 both rows are H-1
         float o0[4], o1[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            o0[k] = (y == 0) ? (1.f * hrow[1][k] + 0.f * hrow[2][k]) : (t0 * hrow[0][k] + 0.75f * hrow[1][k]);
-            o1[k] = 0.75f * hrow[1][k] + 0.25f * hrow[2][k];
+            o0[k] = (y == 0) ? (1.f * hB[k] + 0.f * hC[k]) : (0.25f * hA[k] + 0.75f * hB[k]);
+            o1[k] = 0.75f * hB[k] + 0.25f * hC[k];
         }
         float* d0 = dst + (size_t)(2 * y) * W2 + 2 * x;
         float* d1 = d0 + W2;
-        if (x + 1 < W && (W2 & 3) == 0) {
+        if (vec) {
             __stcs(reinterpret_cast<float4*>(d0), make_float4(o0[0], o0[1], o0[2], o0[3]));
             __stcs(reinterpret_cast<float4*>(d1), make_float4(o1[0], o1[1], o1[2], o1[3]));
         } else {
             const int nout = (x + 1 < W) ? 4 : 2;
             for (int k = 0; k < nout; ++k) d0[k] = o0[k], d1[k] = o1[k];
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hA[k] = hB[k], hB[k] = hC[k];
     }
 }
 
@@ -171,9 +171,9 @@ extern "C" int pf_upsample2x(const float* in, float* out, int maps, int H, int W
     PF_REQUIRE(maps > 0 && H > 0 && W > 0 && maps <= 65535 && H <= 65535, PF_ERR_ARG, "pf_upsample2x: bad shape maps=%d H=%d W=%d", maps, H, W);
     PF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, PF_ERR_ALIGN, "pf_upsample2x: out not 16-byte aligned");
     const int pairs = (W + 1) / 2;
-    int threads = 256;
+    int threads = 128;
     while (threads > 32 && threads / 2 >= pairs) threads /= 2;
-    dim3 grid((pairs + threads - 1) / threads, H, maps);
+    dim3 grid((pairs + threads - 1) / threads, (H + UP_ROWS - 1) / UP_ROWS, maps);
     return launch_pdl("upsample2x_kernel", upsample2x_kernel, grid, dim3(threads), 0, static_cast<cudaStream_t>(stream), in,
                       out, H, W);
 }

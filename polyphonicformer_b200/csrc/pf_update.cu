@@ -206,7 +206,7 @@ struct Mail {
         float m2 = 0.f, dv = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) m2 += p[k].y, dv += (p[k].x - mean) * (p[k].x - mean);
-        rstd = 1.f / sqrtf((m2 + 32.f * dv) * (1.f / 256.f) + U_LN_EPS);
+        rstd = rsqrtf((m2 + 32.f * dv) * (1.f / 256.f) + U_LN_EPS);   // MUFU.RSQ, <= 2 ulp; no slow-path call
     }
 };
 
@@ -471,7 +471,8 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     if (threadIdx.x == 64) DBG(11);
     // LayerNorm (mean, rstd) of this warp's 8 rows, one row per lane (lanes 8..15: the second array)
     float pm = 0.f, pr = 1.f;
-    if (epi && has_ln) mail.combine((lane >> 3) & 1, ew + 16 * (lane & 7), pm, pr);
+    if (epi && has_ln && lane < (MODE == MODE_GENERIC ? 8 : 16)) mail.combine((lane >> 3) & 1, ew + 16 * (lane & 7), pm, pr);
+    if (threadIdx.x == 64) DBG(10);
 
     if (MODE == MODE_GENERIC) {
         if (epi) {

@@ -1,0 +1,22 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): ncu evidence for profiles/.  Usage: bash scripts/capture_profiles.sh <tag>
+# Keeps what it writes well under gpurun's 64 MiB merge limit: raw CSV pages are exported here, reports are deleted.
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+# 1. every launch of the bench command with its device time (cold-cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 330 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $OUT/${TAG}_launches_bench.log 2>&1
+# 2. full captures, one launch of each kind, from the second decode step of a 3-step run
+cap() {  # name, kernel regex, skip, count
+    ncu --set full --clock-control none -k regex:"$2" -s $3 -c $4 -o $OUT/${TAG}_$1 \
+        python scripts/run_stage.py 4 128 256 3 > $OUT/${TAG}_$1.log 2>&1
+    ncu -i $OUT/${TAG}_$1.ncu-rep --page raw --csv > $OUT/${TAG}_$1.raw.csv 2>/dev/null
+    rm -f $OUT/${TAG}_$1.ncu-rep
+    tail -1 $OUT/${TAG}_$1.log
+}
+cap stream "pool_kernel|einsum_kernel|upsample2x|binarise" 9 9
+cap tcgemm "tcgemm" 27 9
+cap helpers "prep_kernel|sumln_kernel|attention_kernel" 9 3
+ls -la $OUT

@@ -16,7 +16,9 @@ torch.cuda.synchronize()
 _cabi.call('pf_debug_timeline', None)
 n = int(tbuf[0].item())
 rec = tbuf[16:16 + 16 * n].reshape(n, 16).cpu()
-last = rec[-(36 + 6):]     # the last step (12 K2 launches + pool + einsum per stage)
+rec = rec[(rec[:, 15] < 10) | (rec[:, 15] >= 100)]   # small-N block only (pool / einsum record every CTA)
+rec = rec[rec[:, 0].argsort()]
+last = rec[-36:]           # the last step: 12 launches per stage
 t0 = int(last[0, 0])
 names = ['start', 'setup', 'pdlwait', 'full0', 'full1', 'full2', 'full3', '-', 'accfull', 'phase1', 'stats', 'cbar', 'done', 'exit']
 print('tag    ' + ' '.join(n.rjust(8) for n in names))
