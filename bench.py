@@ -268,14 +268,16 @@ def run_ours(args, rank, world, local_rank):
         if k['bound'] == 'hbm':
             k['achieved'] = k['alg_bytes'] / (k['ms'] * 1e-3) / 1e9
             k['peak'], k['unit'] = pk['hbm'], 'GB/s'
-        else:
-            k['achieved'] = k['alg_flops'] / (k['ms'] * 1e-3) / 1e12
-            k['peak'], k['unit'] = pk['tf'], 'TFLOP/s'
-        k['frac'] = k['achieved'] / k['peak']
+            k['frac'] = k['achieved'] / k['peak']
+    # the dominant ROOFLINE-bound kernel of the step (the small-N block is latency-bound and listed in ms only)
     dom = max((k for k in kernels if k['bound'] == 'hbm'), key=lambda k: k['ms'] * k['calls_per_step'])
     roofline = dict(kernel=dom['name'], bound=dom['bound'], achieved=dom['achieved'], peak=dom['peak'],
-                    unit=dom['unit'], frac=dom['frac'], traffic=None, peak_source=pk['source'],
-                    alg_bytes_per_launch=dom['alg_bytes'], ms_per_launch=dom['ms'])
+                    unit=dom['unit'], frac=dom['frac'], traffic=dom['traffic'], peak_source=pk['source'],
+                    alg_bytes_per_launch=dom['alg_bytes'], ms_per_launch=dom['ms'],
+                    timing='CUDA events around a single launch, L2 flushed before it (cold); inside the step the '
+                           'same kernel runs faster because part of the feature map is still L2-resident',
+                    traffic_source='profiles/r1_traffic.json (ncu --set full, dram__bytes_read.sum + '
+                                   'dram__bytes_write.sum per launch)' if dom['traffic'] else None)
     line = dict(metric='decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)', value=value,
                 unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -308,6 +310,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
     st = _stream_ptr()
     reps = max(5, min(args.steps, 20))
     sx = 2   # bytes / feature element (bf16)
+    # (name, launches per step, bound, algorithmic bytes, algorithmic flops, launcher)
     specs = [
         ('binarise', 1, 'hbm', B * N * HW * 4 + B * words * 128 * 4, 0,
          lambda: _cabi.call('pf_binarise', _ptr(mask), _ptr(bits), B, N, HW, st)),
@@ -315,7 +318,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
          2 * 2 * B * N * C * HW,
          lambda: _cabi.call('pf_mask_pool', _ptr(feats), _ptr(bits), _ptr(partial), _ptr(cntp), B, N, HW, HWp, 2, S,
                             st)),
-        ('kernel_update (12 launches)', STAGES, 'latency', 0, 0,
+        ('kernel_update (small-N block, 12 launches)', STAGES, 'latency', 0, 0,
          lambda: _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[0].struct), _ptr(partial), _ptr(cntp), S,
                             _ptr(obj), _ptr(dep), _ptr(obj_o), _ptr(dep_o), _ptr(cls), None, _ptr(kern), _ptr(kbias),
                             _ptr(ws), wsb, B, N, 0, st)),
@@ -352,17 +355,23 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
         if bound == 'latency':
             k.update(bound='latency')
         out.append(k)
-    res = []
+    # measured DRAM traffic per launch from the committed ncu --set full capture of the same shapes (profiles/)
+    ncu_name = {'binarise': ('binarise_kernel', 1), 'mask_pool': ('pool_kernel', 1),
+                'mask_einsum (bits only, mask branch)': ('einsum_kernel<0>', 1),
+                'mask_einsum (fp32 logits, both branches)': ('einsum_kernel<1>', 1),
+                'upsample2x': ('upsample2x_kernel', 2)}     # the step launches it once per branch
+    traffic = {}
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tpath) and (B, H, W) == (4, 128, 256):
+        traffic = json.load(open(tpath))['kernels']
     for k in out:
+        nm = ncu_name.get(k['name'])
+        t = traffic.get(nm[0]) if nm else None
+        k['traffic'] = (t['dram_read_bytes'] + t['dram_write_bytes']) * nm[1] if t else None
         if k['bound'] == 'latency':
-            k2 = dict(k)
-            k2['bound'] = 'hbm'
-            k2['alg_bytes'] = 3 * 4.02e6 * 4 / 3   # one stage's fp32 weights, for scale only
-            k2['note'] = 'latency / weight-streaming bound; fraction shown is weights bytes / time, for scale only'
-            res.append(k2)
-        else:
-            res.append(k)
-    return res
+            k['note'] = ('latency / weight-streaming bound (0.88 GFLOP and 16 MB of bf16 hi+lo weights per image-stage '
+                         'over 12 dependent launches): reported in ms only, no roofline fraction')
+    return out
 
 
 def run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier):
