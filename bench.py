@@ -111,7 +111,7 @@ def run_reference(args, rank, world):
                 config=workload_config(args, 1),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, B):
@@ -288,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
         line['e2e'] = e2e
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(args)
-    print(json.dumps(line))
+    emit(line)
 
 
 def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, dev):
@@ -430,7 +430,21 @@ def cpu_baseline(args):
                        (n, args.height, args.width, cores))
 
 
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout (see main: fd 1 is pointed at stderr meanwhile)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL prints its version banner on stdout when NCCL_DEBUG is set on the box) must not pollute the
+    # single JSON line: keep a private copy of stdout, point fd 1 at stderr for everything else
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
