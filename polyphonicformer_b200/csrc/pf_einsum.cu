@@ -3,8 +3,12 @@
 // as a batched [128 x 256] x [256 x HW] GEMM on the tcgen05 tensor cores.
 //
 //   A  = kern[g] as bf16 hi + bf16 lo (the fp32 kernel split in two by its producer; two MMAs per K step, fp32
-//        accumulate), TMA-loaded once per CTA, K-major, resident in shared memory (2 x 64 KB, 128-byte swizzle);
-//   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 3-stage ring;
+//        accumulate), resident in TENSOR MEMORY for the whole CTA (2 x 128 columns: row n in lane n, K packed two
+//        bf16 per 32-bit column), written once by the epilogue warps with tcgen05.st.  With A in shared memory
+//        (SS mode) every MMA re-read 4 KB of A and the kernel was paced by those reads (~87 cycles per
+//        128x64x16 MMA, in-kernel timeline), not by HBM; TS mode reads only the 2 KB feature slice per MMA;
+//   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 6-stage ring
+//        (192 KB in flight per SM);
 //   D  = [128 lanes][64 columns] fp32 in TMEM, 4 accumulator buffers so the epilogue overlaps the next tiles;
 //   epilogue: tcgen05.ld -> + bias -> the packed sign bits consumed by the next stage's pooling (thread = kernel row
 //             n, 32 consecutive pixels = one u32 word) and/or fp32 logits.  Logits leave through shared memory:
@@ -22,18 +26,20 @@ namespace pf {
 
 constexpr int E_C = PF_C;            // 256 = K of the GEMM
 constexpr int E_BHW = 64;            // pixels per tile (= N of the MMA, one 128-byte swizzle atom of bf16)
-constexpr int E_STAGES = 3;          // feature ring depth without the logits staging tiles
-constexpr int E_STAGES_TMA = 2;      // ... with them (the output traffic halves the load rate a CTA must sustain)
+constexpr int E_STAGES = 6;          // feature ring depth without the logits staging tiles
+constexpr int E_STAGES_TMA = 5;      // ... with them
 constexpr int E_OUT_BYTES = 128 * 32 * 4;   // one staged half tile: [128 rows][32 px] fp32
-constexpr int E_ACC = 4;             // TMEM accumulator buffers
-constexpr int E_TMEM_COLS = E_ACC * E_BHW;  // 256
-constexpr int E_A_BYTES = 128 * E_C * 2;    // 65536 per (hi | lo)
+constexpr int E_ACC = 2;             // TMEM accumulator buffers; each = a hi and a lo accumulator of 64 columns (the
+                                     // two MMA chains of a tile are independent, so they overlap in the tensor pipe)
+constexpr int E_TMEM_A = 2 * E_ACC * E_BHW; // first TMEM column of A hi; A lo follows 128 columns later
+constexpr int E_TMEM_COLS = 512;            // 256 accumulator + 2 x 128 A columns: the whole tensor memory
 constexpr int E_B_BYTES = E_C * E_BHW * 2;  // 32768 per stage
 constexpr int E_THREADS = 192;
-constexpr int E_SMEM = 2 * E_A_BYTES + E_STAGES * E_B_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int E_SMEM = E_STAGES * E_B_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 static_assert(E_STAGES_TMA * E_B_BYTES + 2 * E_OUT_BYTES <= E_STAGES * E_B_BYTES, "staging tiles must fit in the ring");
 
 struct EinsumParams {
+    const uint16_t* kern;   // [G][2][N][256] bf16 hi / lo planes
     const float* kbias;  // [G][N]
     float* logits;       // [G][N][HW] or null
     uint32_t* bits;      // [B][WORDS][128] or null
@@ -55,14 +61,12 @@ __device__ __forceinline__ void epi_bar4() { asm volatile("bar.sync 1, 128;" :::
 // then has STAGES = 2 and the two staging tiles live behind it.
 template <bool TMA_OUT>
 __global__ void __launch_bounds__(E_THREADS, 1)
-einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_kern,
-              const __grid_constant__ CUtensorMap tmap_out, const EinsumParams p) {
+einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_out,
+              const EinsumParams p) {
     constexpr int STAGES = TMA_OUT ? E_STAGES_TMA : E_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA_hi = smem;
-    uint8_t* sA_lo = smem + E_A_BYTES;
-    uint8_t* sB = smem + 2 * E_A_BYTES;
+    uint8_t* sB = smem;
     uint8_t* sOut = sB + E_STAGES_TMA * E_B_BYTES;   // TMA_OUT only: 2 x [128][32] fp32, 1024-byte aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + E_STAGES * E_B_BYTES);
     uint64_t* full = bars;
@@ -80,12 +84,12 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     const int ntiles = tile_end - tile_begin;
     const int gunit = (unit / p.B) * p.Btot + p.b0 + unit % p.B;   // unit inside the full-batch feature / logits tensors
     long long* dbg = dbg_claim_all(TMA_OUT ? 21 : 20);
+    __shared__ long long s_dbg2[8];
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
-        tma_prefetch_desc(&tmap_kern);
         if (TMA_OUT) tma_prefetch_desc(&tmap_out);
-        mbar_init(abar, 1);
+        mbar_init(abar, 128);   // every epilogue thread arrives once its row of A is in tensor memory
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
@@ -101,7 +105,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // warp-uniform (REDUX -> uniform register): tcgen05 operands need no per-instruction R2UR
     DBG(1);
     pdl_launch_dependents();
 
@@ -116,15 +120,6 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 mbar_arrive_expect_tx(&full[i], E_B_BYTES);
                 tma_load_2d(sB + i * E_B_BYTES, &tmap_feats, &full[i], (tile_begin + i) * E_BHW, gunit * E_C, kEvictFirst);
             }
-            pdl_wait();   // the dynamic kernels come from the previous kernel
-            // A operand: [hi | lo] x 4 K-blocks of [128 rows][64 k]; rows >= N are out of bounds -> zero filled
-            mbar_arrive_expect_tx(abar, 2 * E_A_BYTES);
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb)
-                    tma_load_3d(sA_hi + h * E_A_BYTES + kb * (128 * 128), &tmap_kern, abar, kb * 64, 0, unit * 2 + h,
-                                kEvictLast);
             for (int i = pre; i < ntiles; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -137,37 +132,55 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, E_BHW, /*a_mn=*/0, /*b_mn=*/1);
-            const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
-            mbar_wait(abar, 0);
-            for (int i = 0; i < ntiles; ++i) {
-                const int s = i % STAGES, a = i % E_ACC;
-                mbar_wait(&tempty[a], ((i / E_ACC) & 1) ^ 1);
-                mbar_wait(&full[s], (i / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + a * E_BHW;
-                const uint32_t b_base = smem_u32(sB + s * E_B_BYTES);
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+        constexpr uint32_t idesc = make_idesc_bf16(128, E_BHW, /*a_mn=*/0, /*b_mn=*/1);
+        const uint32_t a_hi = tmem_base + E_TMEM_A, a_lo = a_hi + 128;
+        mbar_wait(abar, 0);
+        tc_fence_after();
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i % STAGES, a = i % E_ACC;
+            mbar_wait(&tempty[a], ((i / E_ACC) & 1) ^ 1);
+            if (blockIdx.x == 0 && g_dbg && lane == 0 && i >= 4 && i < 8) s_dbg2[2 * (i - 4)] = gtime();
+            mbar_wait(&full[s], (i / STAGES) & 1);
+            if (blockIdx.x == 0 && g_dbg && lane == 0 && i >= 4 && i < 8) s_dbg2[2 * (i - 4) + 1] = gtime();
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + a * (2 * E_BHW);
+            // B (MN-major): 16 K-rows of 128 bytes per K step -> the start-address field advances by 2048 >> 4
+            const uint64_t db0 = make_smem_desc_sw128(smem_u32(sB + s * E_B_BYTES), 32768, 1024);
 #pragma unroll
-                for (int kb = 0; kb < E_C / 16; ++kb) {
-                    // A: K-block kb/4 (16 KB each), 32 bytes per K=16 step inside the 128-byte row
-                    const uint32_t a_off = (kb >> 2) * (128 * 128) + (kb & 3) * 32;
-                    // B (MN-major): 16 K-rows of 128 bytes per step
-                    const uint64_t db = make_smem_desc_sw128(b_base + kb * 2048, 32768, 1024);
-                    umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_hi + a_off, 16, 1024), db, idesc, kb > 0);
-                    umma_bf16_ss(d_tmem, make_smem_desc_sw128(a_lo + a_off, 16, 1024), db, idesc, 1);
-                }
-                umma_commit(&empty[s]);
-                umma_commit(&tfull[a]);
+            for (int kb = 0; kb < E_C / 16; ++kb) {
+                // A (tensor memory): 16 K values = 8 columns per step
+                umma_bf16_ts_warp(d_tmem, a_hi + kb * 8, db0 + (uint64_t)(kb * 128), idesc, kb > 0);
+                umma_bf16_ts_warp(d_tmem + E_BHW, a_lo + kb * 8, db0 + (uint64_t)(kb * 128), idesc, kb > 0);
             }
+            umma_commit_warp(&empty[s]);
+            umma_commit_warp(&tfull[a]);
         }
     } else {
         // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
-        pdl_wait();   // kbias is read and bits / logits are written only after the previous kernels have completed
+        pdl_wait();   // kern / kbias are read and bits / logits written only after the previous kernels have completed
         const int q = warp & 3;
         const int n = q * 32 + lane;
         const bool row_ok = n < p.N;
+        {   // A operand -> tensor memory: this thread's kernel row, hi plane then lo plane (rows >= N: zeros)
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.kern + (((size_t)unit * 2 + h) * p.N + (row_ok ? n : 0)) * E_C);
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 t = row_ok ? __ldg(src + c0 / 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+                        v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+                    }
+                    tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + E_TMEM_A + h * 128 + c0, v);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(abar);
+        }
         const float bias = row_ok ? __ldg(p.kbias + (size_t)unit * p.N + n) : 0.f;
         float* orow = p.logits ? p.logits + ((size_t)gunit * p.N + (row_ok ? n : 0)) * p.HW : nullptr;
         const bool vec_ok = (p.HW & 3) == 0;
@@ -177,10 +190,20 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             mbar_wait(&tfull[a], (i / E_ACC) & 1);
             tc_fence_after();
             uint32_t v0[32], v1[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * E_BHW;
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
-            tmem_ld_wait();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (2 * E_BHW);
+            {
+                uint32_t w0[32], w1[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld32(taddr + E_BHW, w0);
+                tmem_ld32(taddr + E_BHW + 32, w1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {   // hi chain + lo chain
+                    v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(w0[c]));
+                    v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(w1[c]));
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[a]);
@@ -235,6 +258,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read<0>();   // shared memory must outlive the last store's read
     tc_fence_before();
     __syncthreads();
+    if (dbg) for (int k = 0; k < 8; ++k) dbg[4 + k] = s_dbg2[k];
     DBG(13);
     if (warp == 1) tmem_dealloc<E_TMEM_COLS>(tmem_base);
 }
@@ -297,11 +321,8 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     CUtensorMap tmap;
     if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)(n_units / B) * Btot * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
 
-    CUtensorMap tmap_k;
-    if (int e = make_tmap_bf16_3d(&tmap_k, kern, (uint64_t)n_units * 2, (uint64_t)N, E_C, 128, 64)) return e;
-
     EinsumParams p;
-    p.kbias = kbias, p.logits = logits, p.bits = bits_out;
+    p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
     p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats;
     p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
@@ -312,12 +333,12 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
 
     // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
     const bool tma_out = logits && (HW % 4) == 0;
-    CUtensorMap tmap_o = tmap_k;
+    CUtensorMap tmap_o = tmap;
     if (tma_out)
         if (int e = make_tmap_f32_3d(&tmap_o, logits, (uint64_t)(n_units / B) * Btot, (uint64_t)N, (uint64_t)HW, 128, 32)) return e;
     auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
     cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
     return launch_pdl("einsum_kernel", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,
-                      static_cast<cudaStream_t>(stream), tmap, tmap_k, tmap_o, p);
+                      static_cast<cudaStream_t>(stream), tmap, tmap_o, p);
 }

@@ -79,7 +79,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // warp-uniform (REDUX -> uniform register): tcgen05 operands need no per-instruction R2UR
     DBG(1);
     pdl_launch_dependents();
     // Inside the decode loop the feature tiles are long-complete inputs (early_feats): the producer streams them
@@ -100,24 +100,22 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, P_C, 0, 0);
-            for (int i = 0; i < ntiles; ++i) {
-                const int s = i % P_STAGES;
-                const uint32_t ph = (i / P_STAGES) & 1;
-                mbar_wait(&fullA[s], ph);
-                mbar_wait(&fullB[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + s * P_STAGE_BYTES);
-                const uint32_t b_base = a_base + P_A_BYTES;
+        // MMA issuer: the whole warp runs the loop, one lane elected inside the PTX block issues
+        constexpr uint32_t idesc = make_idesc_bf16(128, P_C, 0, 0);
+        for (int i = 0; i < ntiles; ++i) {
+            const int s = i % P_STAGES;
+            const uint32_t ph = (i / P_STAGES) & 1;
+            mbar_wait(&fullA[s], ph);
+            mbar_wait(&fullB[s], ph);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + s * P_STAGE_BYTES);
+            const uint64_t da = make_smem_desc_sw128(a_base, 16, 1024), db = make_smem_desc_sw128(a_base + P_A_BYTES, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < P_BHW / 16; ++k)
-                    umma_bf16_ss(tmem_base, make_smem_desc_sw128(a_base + k * 32, 16, 1024),
-                                 make_smem_desc_sw128(b_base + k * 32, 16, 1024), idesc, (i | k) != 0);
-                umma_commit(&empty[s]);
-            }
-            umma_commit(accfull);
+            for (int k = 0; k < P_BHW / 16; ++k)
+                umma_bf16_ss_warp(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (i | k) != 0);
+            umma_commit_warp(&empty[s]);
         }
+        umma_commit_warp(accfull);
     } else {
         // ---- expanders: thread = mask row r (TMEM lane r later in the epilogue)
         pdl_wait();

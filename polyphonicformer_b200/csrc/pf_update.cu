@@ -266,7 +266,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // warp-uniform (REDUX -> uniform register): tcgen05 operands need no per-instruction R2UR
     if (threadIdx.x == 0) DBG(1);
     if (has_ln) cluster_arrive();   // matched by the cluster_wait before the first DSMEM store: peers have started
     // per-column parameters of this tile (weights: independent of the previous kernel) -> shared memory, now
@@ -360,30 +360,31 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             issue_w(it);
             issue_a(it);
         }
-    } else if (active && warp == 1 && lane == 0) {
+    } else if (active && warp == 1) {
         // ================= MMA issuer: D = Al*Wh + Ah*Wl + Ah*Wh =================
+        // the whole warp runs the loop with warp-uniform operands, one lane elected inside the PTX block issues
         constexpr uint32_t idesc = make_idesc_bf16(128, T_TN, 0, 0);
         for (int it = 0; it < total_it; ++it) {
             const int s = it % T_NSTG, kb = it & 3;
             mbar_wait(&full[s], (it / T_NSTG) & 1);
             tc_fence_after();
-            if (it < 4) DBG(3 + it);
-            const uint32_t a_hi = smem_u32(smem + s * T_STAGE), a_lo = a_hi + T_PLANE;
-            const uint32_t w_hi = a_hi + 2 * T_PLANE, w_lo = a_hi + 3 * T_PLANE;
+            if (it < 4 && lane == 0) DBG(3 + it);
+            const uint32_t st = smem_u32(smem + s * T_STAGE);
+            // K-major operands: the start-address field advances by 32 bytes >> 4 per K = 16 step
+            const uint64_t dah = make_smem_desc_sw128(st, 16, 1024), dal = make_smem_desc_sw128(st + T_PLANE, 16, 1024);
+            const uint64_t dwh = make_smem_desc_sw128(st + 2 * T_PLANE, 16, 1024);
+            const uint64_t dwl = make_smem_desc_sw128(st + 3 * T_PLANE, 16, 1024);
             const uint32_t d = tmem_base + (uint32_t)(it >> 2) * T_TN;
 #pragma unroll
             for (int k16 = 0; k16 < T_KC / 16; ++k16) {
-                const uint64_t dah = make_smem_desc_sw128(a_hi + k16 * 32, 16, 1024);
-                const uint64_t dal = make_smem_desc_sw128(a_lo + k16 * 32, 16, 1024);
-                const uint64_t dwh = make_smem_desc_sw128(w_hi + k16 * 32, 16, 1024);
-                const uint64_t dwl = make_smem_desc_sw128(w_lo + k16 * 32, 16, 1024);
-                umma_bf16_ss(d, dal, dwh, idesc, (kb | k16) != 0);
-                umma_bf16_ss(d, dah, dwl, idesc, 1);
-                umma_bf16_ss(d, dah, dwh, idesc, 1);
+                const uint64_t o = (uint64_t)(k16 * 2);
+                umma_bf16_ss_warp(d, dal + o, dwh + o, idesc, (kb | k16) != 0);
+                umma_bf16_ss_warp(d, dah + o, dwl + o, idesc, 1);
+                umma_bf16_ss_warp(d, dah + o, dwh + o, idesc, 1);
             }
-            umma_commit(&empty[s]);
+            umma_commit_warp(&empty[s]);
         }
-        umma_commit(accfull);
+        umma_commit_warp(accfull);
     }
     __syncwarp();
 
