@@ -181,8 +181,11 @@ __device__ __forceinline__ float4 act4(float4 v, int act) {
 }
 // 4 values -> bf16 hi / lo, 8 contiguous bytes in each plane
 __device__ __forceinline__ void store_planes4(float4 v, uint16_t* hi_ptr, uint16_t* lo_ptr) {
-    const float h0 = bf16_round(v.x), h1 = bf16_round(v.y), h2 = bf16_round(v.z), h3 = bf16_round(v.w);
-    *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    // two packed conversions give the four hi halves; widening a bf16 back to fp32 is a shift / a mask
+    const uint32_t p01 = pack_bf16x2(v.x, v.y), p23 = pack_bf16x2(v.z, v.w);
+    const float h0 = __uint_as_float(p01 << 16), h1 = __uint_as_float(p01 & 0xFFFF0000u);
+    const float h2 = __uint_as_float(p23 << 16), h3 = __uint_as_float(p23 & 0xFFFF0000u);
+    *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(p01, p23);
     *reinterpret_cast<uint2*>(lo_ptr) = make_uint2(pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
 }
 __device__ __forceinline__ uint16_t* arena_row(uint16_t* arena, int unit, int slot, int plane, int r) {
@@ -300,28 +303,29 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         *reinterpret_cast<float4*>(vec + which * 128 + lane * 4) = v;
     }
 
+    // (both run by the WHOLE producer warp; one lane elected inside each PTX block issues)
     auto issue_w = [&](int it) {
         const TcPass& p = g.pass[it >> 2];
         const int kb = it & 3, s = it % T_NSTG;
         uint8_t* st = smem + s * T_STAGE;
         const CUtensorMap* wm = p.w_ffn ? &tmap_wffn : &tmap_w256;
         const int k = p.w_k0 + (p.w_ffn ? split * T_K : 0) + kb * T_KC;
-        mbar_arrive_expect_tx(&full[s], T_STAGE);
-        tma_load_2d(st + 2 * T_PLANE, wm, &full[s], k, p.w_row + nb, kEvictLast);
-        tma_load_2d(st + 3 * T_PLANE, wm, &full[s], k, p.w_row + p.w_lo + nb, kEvictLast);
+        mbar_arrive_expect_tx_warp(&full[s], T_STAGE);
+        tma_load_2d_warp(st + 2 * T_PLANE, wm, &full[s], k, p.w_row + nb, kEvictLast);
+        tma_load_2d_warp(st + 3 * T_PLANE, wm, &full[s], k, p.w_row + p.w_lo + nb, kEvictLast);
     };
     auto issue_a = [&](int it) {
         const TcPass& p = g.pass[it >> 2];
         const int kb = it & 3, s = it % T_NSTG;
         uint8_t* st = smem + s * T_STAGE;
         const int row = ((unit * NSLOT + p.a_slot + (args.ksplit > 1 ? split : 0)) * 2) * 128;
-        tma_load_2d(st, &tmap_a, &full[s], kb * T_KC, row, kEvictFirst);
-        tma_load_2d(st + T_PLANE, &tmap_a, &full[s], kb * T_KC, row + 128, kEvictFirst);
+        tma_load_2d_warp(st, &tmap_a, &full[s], kb * T_KC, row, kEvictFirst);
+        tma_load_2d_warp(st + T_PLANE, &tmap_a, &full[s], kb * T_KC, row + 128, kEvictFirst);
     };
 
     // weights do not depend on the previous kernel: start the ring before the grid dependency is resolved
     const int pre = total_it < T_NSTG ? total_it : T_NSTG;
-    if (active && threadIdx.x == 0)
+    if (active && warp == 0)
         for (int it = 0; it < pre; ++it) issue_w(it);
     pdl_wait();                 // activations written by the previous kernels are visible from here on
     pdl_launch_dependents();    // let the next kernel start prefetching its weights
@@ -352,7 +356,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         }
     }
 
-    if (active && warp == 0 && lane == 0) {
+    if (active && warp == 0) {
         // ================= TMA producer =================
         for (int it = 0; it < pre; ++it) issue_a(it);
         for (int it = pre; it < total_it; ++it) {
