@@ -194,6 +194,28 @@ int pf_decoder_forward_slice(const pf_stage_weights* stages_host, int n_stages, 
                              float* scaled_out, void* workspace, size_t workspace_bytes, int B_total, int b0, int B,
                              int N, int H, int W, int HWp, int flags, void* stream);
 
+/* ---- post-processing of one image ------------------------------------------------
+ * KernelUpdateIterHead.get_panoptic + merge_stuff_thing_stuff_joint (polyphonic/kernel_update.py:421-535) with
+ * rescale_masks / rescale_depth (polyphonic/kernel_update_head.py:593-626) and depth_act
+ * (polyphonic/funcs/depth_utils.py:1-19) fused in: nothing full-resolution is materialised except the three results.
+ *   cls_scores   [N][num_classes]  sigmoid class scores of the last stage
+ *   mask_logits  [N][h][w]         scaled_mask_preds (1/4 of the padded network input)
+ *   depth_logits [N][h][w]         scaled_depth_preds
+ *   depth_init   [h][w]            the initial depth prediction at the same resolution (kernel_update.py:302-307)
+ *   H0, W0                         img_shape = ori_shape: the top-left crop of the x4 up-sampled maps that is returned
+ *   panoptic [H0][W0] int32, depth_final / depth_basic [H0][W0] fp32, segments [max_per_img + stuff] records in
+ *   painting order, *n_segments their count (all DEVICE pointers).  depth_mode: 0 = 'monodepth', 1 = 'sigmoid'. */
+typedef struct pf_segment {
+    int id, isthing, category_id, instance_id, area;
+    float score;
+} pf_segment;
+size_t pf_panoptic_workspace_bytes(int H0, int W0);
+int pf_panoptic(const float* cls_scores, const float* mask_logits, const float* depth_logits, const float* depth_init,
+                int N, int num_proposals, int num_thing_classes, int num_classes, int h, int w, int H0, int W0,
+                int max_per_img, float instance_score_thr, float overlap_thr, int depth_mode, int32_t* panoptic,
+                float* depth_final, float* depth_basic, pf_segment* segments, int* n_segments, void* workspace,
+                size_t workspace_bytes, void* stream);
+
 /* debug only: int64 device buffer [16 + 16*capacity], zero-filled by the caller; CTA (0,0,0) of every GEMM launch of
  * the small-N block appends 16 %globaltimer samples (see scripts/k2_timeline.py).  NULL switches it off. */
 int pf_debug_timeline(long long* device_buffer);

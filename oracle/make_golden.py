@@ -93,6 +93,28 @@ def run_updator_case(head, seed=0, rows=37):
     return dict(update_feature=update.numpy(), input_feature=inputf.numpy(), out=y.numpy())
 
 
+PANOPTIC_CASES = [
+    # name, h, w (scaled predictions = 1/4 of the padded input), img_shape (crop of the padded input), seed
+    ('panoptic_h32_w64_s0', 32, 64, (128, 256), 0),
+    ('panoptic_h24_w40_crop_s1', 24, 40, (94, 157), 1),     # KITTI-like: padded 96x160, image 94x157
+]
+
+
+def run_panoptic_case(head, h, w, img_hw, seed):
+    """kernel_update.py:421-535 -- the reference's own get_panoptic on hand-constructed predictions."""
+    inp = synth.synth_panoptic_inputs(h, w, seed)
+    meta = dict(img_shape=(img_hw[0], img_hw[1], 3), ori_shape=(img_hw[0], img_hw[1], 3), pad_shape=(4 * h, 4 * w, 3),
+                scale_factor=1.0, flip=False, batch_input_shape=(4 * h, 4 * w))
+    with torch.no_grad():
+        _, _, (pan, segs), dbasic, dfinal = head.get_panoptic(
+            inp['cls_scores'], inp['mask_preds'], head.test_cfg, meta, inp['depth_preds'], inp['depth_init'], None)
+    seg = np.array([[s['id'], int(s['isthing']), s['category_id'], s.get('instance_id', -1), s.get('area', -1)]
+                    for s in segs], dtype=np.int64)
+    score = np.array([s.get('score', -1.0) for s in segs], dtype=np.float64)
+    return dict(panoptic=pan, seg=seg, seg_score=score, depth_basic=dbasic, depth_final=dfinal,
+                img_hw=np.array(img_hw))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -104,6 +126,10 @@ def main():
         np.savez_compressed(path, B=B, H=H, W=W, seed=seed, margin=margin, **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith('s2') or 'scaled' in k},
               f'{os.path.getsize(path) / 1e6:.2f} MB')
+    for name, h, w, img_hw, seed in PANOPTIC_CASES:
+        out = run_panoptic_case(head, h, w, img_hw, seed)
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), h=h, w=w, seed=seed, **out)
+        print(name, out['panoptic'].shape, 'segments', len(out['seg']), np.unique(out['panoptic']))
     u = run_updator_case(head)
     np.savez_compressed(os.path.join(GOLD, 'updator_r37_s0.npz'), **u)
     print('updator', u['out'].shape)

@@ -128,3 +128,32 @@ def synth_decoder_inputs(B, H, W, seed=0, n_kernels=N_KERNELS):
     dpred = r(B, 1, H, W)
     return dict(x_feats=x, depth_feats=d, mask_preds=mask.contiguous(), proposal_feats=prop,
                 depth_proposal=dprop, depth_pred=dpred)
+
+
+def synth_panoptic_inputs(h, w, seed=0, n_kernels=N_KERNELS):
+    """Hand-constructed inputs of ``KernelUpdateIterHead.get_panoptic`` (kernel_update.py:421-469): with random
+    weights the decoder's own outputs merge into ~1 segment, so parity of the post-processing is pinned on these
+    instead.  Thing masks are blobs, stuff masks are bands; a dozen things and most stuff classes score high; no two
+    scores are equal.  Returns cls_scores [N,19] (already sigmoid), mask / depth logits [N,h,w], depth_init [1,h,w]."""
+    g = _gen(f'panoptic.{h}.{w}', seed)
+    r = lambda *shape: torch.rand(*shape, generator=g)
+    ys = torch.arange(h, dtype=torch.float32).view(1, h, 1)
+    xs = torch.arange(w, dtype=torch.float32).view(1, 1, w)
+    cy, cx = r(N_PROPOSALS, 1, 1) * h, r(N_PROPOSALS, 1, 1) * w
+    rad = 2.0 + r(N_PROPOSALS, 1, 1) * (h / 4)
+    thing = 5.0 - 7.0 * ((ys - cy) ** 2 + (xs - cx) ** 2) / rad ** 2
+    band0 = torch.linspace(0, h, NUM_STUFF + 1)
+    stuff = torch.stack([2.5 - 2.0 * ((ys[0] - (band0[i] + band0[i + 1]) / 2).abs() / (h / NUM_STUFF)).expand(h, w)
+                         for i in range(NUM_STUFF)])
+    mask = torch.cat([thing, stuff])[:n_kernels] + 0.05 * torch.randn(n_kernels, h, w, generator=g)
+    cls = 0.01 + 0.08 * r(n_kernels, NUM_CLASSES)
+    strong = torch.randperm(N_PROPOSALS, generator=g)[:14]
+    for j, n in enumerate(strong.tolist()):
+        cls[n, j % NUM_THING] = 0.35 + 0.6 * r(1).item() if j != 3 else 0.2      # one below instance_score_thr
+    for i in range(NUM_STUFF):
+        cls[N_PROPOSALS + i, NUM_THING + i] = 0.15 + 0.8 * r(1).item()
+    coarse = torch.randn(n_kernels, max(h // 8, 1), max(w // 8, 1), generator=g)
+    depth = torch.nn.functional.interpolate(coarse[None], size=(h, w), mode='bilinear', align_corners=False)[0]
+    dinit = torch.nn.functional.interpolate(torch.randn(1, 1, max(h // 8, 1), max(w // 8, 1), generator=g), size=(h, w),
+                                            mode='bilinear', align_corners=False)[0]
+    return dict(cls_scores=cls, mask_preds=mask.contiguous(), depth_preds=depth.contiguous(), depth_init=dinit.contiguous())

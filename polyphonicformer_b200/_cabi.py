@@ -49,6 +49,10 @@ _SIGS = {
     'pf_version': (c_int, []),
     'pf_last_error_string': (c_char_p, []),
     'pf_last_launch_count': (c_int, []),
+    'pf_panoptic_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'pf_panoptic': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_size_t, c_void_p]),
     'pf_debug_timeline': (c_int, [c_void_p]),
     'pf_cast_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_binarise': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

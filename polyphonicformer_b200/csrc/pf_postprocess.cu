@@ -1,0 +1,311 @@
+// Panoptic + depth post-processing of one image, replacing
+//   KernelUpdateIterHead.get_panoptic / merge_stuff_thing_stuff_joint   polyphonic/kernel_update.py:421-535
+//   KernelUpdateHead.rescale_masks / rescale_depth                      polyphonic/kernel_update_head.py:593-626
+//   depth_act                                                           polyphonic/funcs/depth_utils.py:1-19
+//
+// The reference materialises 111 sigmoid masks and 111 depth maps at full resolution twice (1.9 GB of fp32 per
+// 1024x2048 frame and pass) and then walks the segments in a Python loop with ~300 host synchronisations.  Here the
+// x4 bilinear up-sampling is fused into the consumers and nothing full-resolution is ever materialised except the
+// three result maps:
+//   pp_select  (1 CTA)    top-k of the 100x8 thing scores (bitonic sort), stuff scores sorted, one "champion" entry
+//                         per proposal: of all (mask, label) entries that share a mask only the best-scoring one can
+//                         win the per-pixel argmax of score * mask, the others end with area 0 and are skipped by the
+//                         reference's loop as well (kernel_update.py:505-507);
+//   pp_argmax  (tiles)    per output pixel: up-sampled sigmoid of every proposal's mask from a shared-memory patch of
+//                         the low-resolution logits, argmax of score * mask -> winner id (u8), per-proposal winner
+//                         area and per-proposal count of mask >= 0.5 (integer atomics: deterministic);
+//   pp_merge   (1 thread) the reference's sequential loop over entries by descending score (score / overlap
+//                         thresholds, running segment id) -> segment id per proposal + the segments_info records;
+//   pp_paint   (pixels)   panoptic id, depth_basic (up-sampled initial depth) and depth_final (the winner's depth map
+//                         where a segment was painted), depth_act applied before the interpolation as the reference.
+// Supported geometry: predictions at 1/4 of the padded input (Hb = 4h, Wb = 4w -- fixed by the model), output = the
+// top-left H0 x W0 crop of the padded input, ori_shape == img_shape (the second F.interpolate is then the identity).
+#include <math.h>
+
+#include "pf_internal.h"
+#include "pf_sm100.cuh"
+
+namespace pf {
+
+constexpr int PP_MAXN = PF_MAX_N;       // proposals (masks)
+constexpr int PP_MAXE = 128;            // entries: max_per_img things + stuff
+constexpr int PP_TY = 16, PP_TX = 64;   // output tile
+constexpr int PP_PR = PP_TY / 4 + 2, PP_PC = PP_TX / 4 + 2;   // low-resolution patch incl. the bilinear halo
+constexpr int PP_THREADS = 256;
+
+struct PpTables {                       // lives in the workspace
+    int entry_mask[PP_MAXE];            // proposal index of entry e
+    int entry_label[PP_MAXE];
+    float entry_score[PP_MAXE];
+    int n_entries, n_thing_entries;
+    int champ_entry[PP_MAXN];           // best entry of proposal n, or -1
+    float champ_score[PP_MAXN];
+    int area[PP_MAXN];                  // pixels won by proposal n
+    int orig[PP_MAXN];                  // pixels with mask_n >= 0.5
+    int segid[PP_MAXN];                 // segment id painted for proposal n (0 = none)
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float depth_act_(float x, int mode) {
+    const float min_depth = 0.01f, max_depth = 80.f;
+    const float s = sigmoidf_(x);
+    if (mode == 0) {   // monodepth: 1 / (min_disp + (max_disp - min_disp) * sigmoid)
+        const float min_disp = 1.f / max_depth, max_disp = 1.f / min_depth;
+        return 1.f / (min_disp + (max_disp - min_disp) * s);
+    }
+    return s * (max_depth - min_depth) + min_depth;   // 'sigmoid'
+}
+
+// ATen upsample_bilinear2d, align_corners = False, scale = in / out = 0.25
+struct Tap {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ Tap make_tap(int dst, int in_size) {
+    const float s = fmaxf(0.25f * ((float)dst + 0.5f) - 0.5f, 0.f);
+    Tap t;
+    t.i0 = (int)s;
+    t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+    t.l1 = s - (float)t.i0;
+    t.l0 = 1.f - t.l1;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pp_select_kernel(const float* __restrict__ cls, PpTables* __restrict__ tb, int N,
+                                                         int P, int T, int ncls, int max_per_img) {
+    __shared__ float s_key[1024];
+    __shared__ int s_idx[1024];
+    const int t = threadIdx.x;
+    const int cand = P * T;
+    s_key[t] = t < cand ? cls[(t / T) * ncls + (t % T)] : -INFINITY;
+    s_idx[t] = t;
+    __syncthreads();
+    // bitonic sort, descending by score, ascending by index among equal scores
+    for (int k = 2; k <= 1024; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int o = t ^ j;
+            if (o > t) {
+                const float a = s_key[t], b = s_key[o];
+                const int ia = s_idx[t], ib = s_idx[o];
+                const bool a_first = a > b || (a == b && ia < ib);   // a should come before b
+                const bool up = (t & k) == 0;
+                if (up ? !a_first : a_first) {
+                    s_key[t] = b, s_key[o] = a;
+                    s_idx[t] = ib, s_idx[o] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    const int nt = max_per_img < cand ? max_per_img : cand;
+    if (t < nt) {
+        tb->entry_mask[t] = s_idx[t] / T;
+        tb->entry_label[t] = s_idx[t] % T;
+        tb->entry_score[t] = s_key[t];
+    }
+    if (t < PP_MAXN) tb->area[t] = 0, tb->orig[t] = 0, tb->segid[t] = 0, tb->champ_entry[t] = -1, tb->champ_score[t] = 0.f;
+    __syncthreads();
+    if (t == 0) {
+        const int S = N - P;   // stuff kernels: score = cls[P + i][T + i], sorted descending (kernel_update.py:449-451)
+        int order[PP_MAXN];
+        for (int i = 0; i < S; ++i) order[i] = i;
+        for (int i = 1; i < S; ++i) {
+            const int v = order[i];
+            const float sv = cls[(P + v) * ncls + T + v];
+            int j = i - 1;
+            while (j >= 0 && cls[(P + order[j]) * ncls + T + order[j]] < sv) order[j + 1] = order[j], --j;
+            order[j + 1] = v;
+        }
+        for (int i = 0; i < S; ++i) {
+            tb->entry_mask[nt + i] = P + order[i];
+            tb->entry_label[nt + i] = T + order[i];
+            tb->entry_score[nt + i] = cls[(P + order[i]) * ncls + T + order[i]];
+        }
+        tb->n_entries = nt + S, tb->n_thing_entries = nt;
+        for (int e = nt + S - 1; e >= 0; --e) {   // descending e: the smallest e of a proposal is written last
+            const int n = tb->entry_mask[e];
+            tb->champ_entry[n] = e;
+            tb->champ_score[n] = tb->entry_score[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __restrict__ mask_logits,
+                                                               PpTables* __restrict__ tb, uint8_t* __restrict__ ids,
+                                                               int N, int h, int w, int H0, int W0) {
+    extern __shared__ float s_sig[];   // [N][PP_PR][PP_PC] sigmoid of the low-resolution logits under this tile
+    __shared__ float s_score[PP_MAXN];
+    __shared__ int s_entry[PP_MAXN];
+    __shared__ int s_area[PP_MAXN], s_orig[PP_MAXN];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int Y0 = blockIdx.y * PP_TY, X0 = blockIdx.x * PP_TX;
+    const int py0 = make_tap(Y0, h).i0, px0 = make_tap(X0, w).i0;
+    for (int i = tid; i < PP_MAXN; i += PP_THREADS) {
+        s_area[i] = 0, s_orig[i] = 0;
+        s_score[i] = i < N ? tb->champ_score[i] : 0.f;
+        s_entry[i] = i < N ? tb->champ_entry[i] : -1;
+    }
+    constexpr int PATCH = PP_PR * PP_PC;
+    for (int i = tid; i < N * PATCH; i += PP_THREADS) {
+        const int n = i / PATCH, r = (i % PATCH) / PP_PC, c = i % PP_PC;
+        const int yy = min(py0 + r, h - 1), xx = min(px0 + c, w - 1);
+        s_sig[i] = sigmoidf_(__ldg(mask_logits + ((size_t)n * h + yy) * w + xx));
+    }
+    __syncthreads();
+    const int tx = tid & (PP_TX - 1), ty0 = tid / PP_TX;   // 4 pixels per thread: rows ty0 + 4 j
+    const int X = X0 + tx;
+    const Tap cx = make_tap(X, w);
+    const int ox0 = cx.i0 - px0, ox1 = cx.i1 - px0;
+    int o00[4], o10[4];
+    float ly0[4], ly1[4];
+    bool inside[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int Y = Y0 + ty0 + 4 * j;
+        const Tap cy = make_tap(Y, h);
+        o00[j] = (cy.i0 - py0) * PP_PC, o10[j] = (cy.i1 - py0) * PP_PC;
+        ly0[j] = cy.l0, ly1[j] = cy.l1;
+        inside[j] = Y < H0 && X < W0;
+    }
+    float best[4] = {-1.f, -1.f, -1.f, -1.f};
+    int best_e[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, best_n[4] = {0, 0, 0, 0};
+    for (int n = 0; n < N; ++n) {
+        const float* sp = s_sig + n * PATCH;
+        const float sc = s_score[n];
+        const int e = s_entry[n];
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = sp[o00[j] + ox0], b = sp[o00[j] + ox1], c = sp[o10[j] + ox0], d = sp[o10[j] + ox1];
+            const float m = ly0[j] * (cx.l0 * a + cx.l1 * b) + ly1[j] * (cx.l0 * c + cx.l1 * d);
+            cnt += __popc(__ballot_sync(0xffffffffu, inside[j] && m >= 0.5f));
+            const float prob = sc * m;
+            if (e >= 0 && (prob > best[j] || (prob == best[j] && e < best_e[j]))) best[j] = prob, best_e[j] = e, best_n[j] = n;
+        }
+        if (lane == 0 && cnt) atomicAdd(&s_orig[n], cnt);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int Y = Y0 + ty0 + 4 * j;
+        if (inside[j]) {
+            ids[(size_t)Y * W0 + X] = (uint8_t)best_n[j];
+            atomicAdd(&s_area[best_n[j]], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += PP_THREADS) {
+        if (s_area[i]) atomicAdd(&tb->area[i], s_area[i]);
+        if (s_orig[i]) atomicAdd(&tb->orig[i], s_orig[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pp_merge_kernel(PpTables* __restrict__ tb, pf_segment* __restrict__ segs, int* __restrict__ n_segs, int T,
+                                float instance_score_thr, float overlap_thr) {
+    if (threadIdx.x || blockIdx.x) return;
+    const int E = tb->n_entries;
+    int order[PP_MAXE];   // argsort(-total_scores), stable
+    for (int i = 0; i < E; ++i) order[i] = i;
+    for (int i = 1; i < E; ++i) {
+        const int v = order[i];
+        const float sv = tb->entry_score[v];
+        int j = i - 1;
+        while (j >= 0 && tb->entry_score[order[j]] < sv) order[j + 1] = order[j], --j;
+        order[j + 1] = v;
+    }
+    int seg = 0;
+    for (int i = 0; i < E; ++i) {
+        const int k = order[i];
+        const int label = tb->entry_label[k];
+        const bool isthing = label < T;
+        const float score = tb->entry_score[k];
+        if (isthing && score < instance_score_thr) continue;
+        const int n = tb->entry_mask[k];
+        if (tb->champ_entry[n] != k) continue;          // a better entry owns this mask: this one won no pixel
+        const int area = tb->area[n], orig = tb->orig[n];
+        if (area > 0 && orig > 0) {
+            if ((double)area / (double)orig < (double)overlap_thr) continue;
+            ++seg;
+            tb->segid[n] = seg;
+            pf_segment s;
+            s.id = seg, s.isthing = isthing ? 1 : 0, s.category_id = label, s.instance_id = k, s.area = area, s.score = score;
+            segs[seg - 1] = s;
+        }
+    }
+    *n_segs = seg;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pp_paint_kernel(const float* __restrict__ depth_logits,
+                                                       const float* __restrict__ depth_init,
+                                                       const PpTables* __restrict__ tb, const uint8_t* __restrict__ ids,
+                                                       int32_t* __restrict__ panoptic, float* __restrict__ depth_final,
+                                                       float* __restrict__ depth_basic, int h, int w, int H0, int W0,
+                                                       int depth_mode) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+    if (X >= W0 || Y >= H0) return;
+    const Tap cy = make_tap(Y, h), cx = make_tap(X, w);
+    auto sample = [&](const float* map) {
+        const float a = depth_act_(__ldg(map + cy.i0 * w + cx.i0), depth_mode), b = depth_act_(__ldg(map + cy.i0 * w + cx.i1), depth_mode);
+        const float c = depth_act_(__ldg(map + cy.i1 * w + cx.i0), depth_mode), d = depth_act_(__ldg(map + cy.i1 * w + cx.i1), depth_mode);
+        return cy.l0 * (cx.l0 * a + cx.l1 * b) + cy.l1 * (cx.l0 * c + cx.l1 * d);
+    };
+    const size_t p = (size_t)Y * W0 + X;
+    const int n = ids[p];
+    const int s = tb->segid[n];
+    const float dinit = sample(depth_init);
+    panoptic[p] = s;
+    depth_basic[p] = dinit;
+    depth_final[p] = s > 0 ? sample(depth_logits + (size_t)n * h * w) : dinit;
+}
+
+static size_t pp_align(size_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace pf
+
+extern "C" size_t pf_panoptic_workspace_bytes(int H0, int W0) {
+    if (H0 <= 0 || W0 <= 0) return 0;
+    return pf::pp_align(sizeof(pf::PpTables)) + pf::pp_align((size_t)H0 * W0);
+}
+
+extern "C" int pf_panoptic(const float* cls_scores, const float* mask_logits, const float* depth_logits,
+                           const float* depth_init, int N, int num_proposals, int num_thing_classes, int num_classes, int h,
+                           int w, int H0, int W0, int max_per_img, float instance_score_thr, float overlap_thr,
+                           int depth_mode, int32_t* panoptic, float* depth_final, float* depth_basic,
+                           pf_segment* segments, int* n_segments, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(cls_scores && mask_logits && depth_logits && depth_init && panoptic && depth_final && depth_basic && segments &&
+                   n_segments && workspace,
+               PF_ERR_ARG, "pf_panoptic: null pointer");
+    PF_REQUIRE(N > 0 && N <= PP_MAXN && num_proposals > 0 && num_proposals <= N && num_thing_classes > 0 &&
+                   num_thing_classes + (N - num_proposals) <= num_classes && num_proposals * num_thing_classes <= 1024,
+               PF_ERR_ARG, "pf_panoptic: bad class / proposal counts N=%d P=%d T=%d classes=%d", N, num_proposals,
+               num_thing_classes, num_classes);
+    PF_REQUIRE(h > 0 && w > 0 && H0 > 0 && W0 > 0 && H0 <= 4 * h && W0 <= 4 * w, PF_ERR_ARG,
+               "pf_panoptic: output %dx%d must be a crop of the x4 up-sampled %dx%d predictions", H0, W0, h, w);
+    PF_REQUIRE(max_per_img > 0 && max_per_img + (N - num_proposals) <= PP_MAXE, PF_ERR_ARG, "pf_panoptic: max_per_img=%d", max_per_img);
+    PF_REQUIRE(depth_mode == 0 || depth_mode == 1, PF_ERR_ARG, "pf_panoptic: depth_mode must be 0 (monodepth) or 1 (sigmoid)");
+    PF_REQUIRE(workspace_bytes >= pf_panoptic_workspace_bytes(H0, W0), PF_ERR_WORKSPACE, "pf_panoptic: workspace %zu < %zu",
+               workspace_bytes, pf_panoptic_workspace_bytes(H0, W0));
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PF_ERR_ALIGN, "pf_panoptic: workspace not 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PpTables* tb = static_cast<PpTables*>(workspace);
+    uint8_t* ids = static_cast<uint8_t*>(workspace) + pp_align(sizeof(PpTables));
+
+    pp_select_kernel<<<1, 1024, 0, st>>>(cls_scores, tb, N, num_proposals, num_thing_classes, num_classes, max_per_img);
+    PF_CHECK_LAUNCH("pp_select_kernel");
+    const size_t smem = (size_t)N * PP_PR * PP_PC * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(pp_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "pp_argmax smem attribute: %s", cudaGetErrorString(e));
+    dim3 grid((W0 + PP_TX - 1) / PP_TX, (H0 + PP_TY - 1) / PP_TY);
+    pp_argmax_kernel<<<grid, PP_THREADS, smem, st>>>(mask_logits, tb, ids, N, h, w, H0, W0);
+    PF_CHECK_LAUNCH("pp_argmax_kernel");
+    pp_merge_kernel<<<1, 32, 0, st>>>(tb, segments, n_segments, num_thing_classes, instance_score_thr, overlap_thr);
+    PF_CHECK_LAUNCH("pp_merge_kernel");
+    pp_paint_kernel<<<dim3((W0 + 255) / 256, H0), 256, 0, st>>>(depth_logits, depth_init, tb, ids, panoptic, depth_final,
+                                                                 depth_basic, h, w, H0, W0, depth_mode);
+    PF_CHECK_LAUNCH("pp_paint_kernel");
+    return PF_OK;
+}

@@ -50,3 +50,40 @@ def test_state_table_matches_reference_layout():
     """4.02 M parameters per stage."""
     n = sum(int(np.prod(s)) for s in synth.stage_state_shapes().values())
     assert abs(n / 1e6 - 4.02) < 0.01, n
+
+
+PANOPTIC_CASES = ['panoptic_h32_w64_s0', 'panoptic_h24_w40_crop_s1']
+
+
+def panoptic_args(g):
+    """(roi_head stand-in, last_head stand-in, test_cfg, img_meta, inputs) of a panoptic golden case."""
+    import json
+    from types import SimpleNamespace
+    from polyphonicformer_b200.registry import to_config
+    h, w, seed = int(g['h']), int(g['w']), int(g['seed'])
+    H0, W0 = [int(v) for v in g['img_hw']]
+    cfg = to_config(json.load(open(os.path.join(GOLDEN, 'roi_head_cfg.json')))['test_cfg'])
+    roi = SimpleNamespace(num_proposals=synth.N_PROPOSALS, num_thing_classes=synth.NUM_THING, merge_joint=True)
+    last = SimpleNamespace(depth_act_mode='sigmoid', num_classes=synth.NUM_CLASSES)   # the shipped config (roi_head_cfg.json)
+    meta = dict(img_shape=(H0, W0, 3), ori_shape=(H0, W0, 3), pad_shape=(4 * h, 4 * w, 3), scale_factor=1.0, flip=False,
+                batch_input_shape=(4 * h, 4 * w))
+    return roi, last, cfg, meta, synth.synth_panoptic_inputs(h, w, seed)
+
+
+def segments_as_array(info):
+    return np.array([[s['id'], int(s['isthing']), s['category_id'], s.get('instance_id', -1), s.get('area', -1)]
+                     for s in info], dtype=np.int64).reshape(-1, 5)
+
+
+@pytest.mark.parametrize('name', PANOPTIC_CASES)
+def test_panoptic_restatement_matches_reference(name):
+    """oracle/panoptic_ref.py == the reference's get_panoptic (kernel_update.py:421-535) on the same CPU ops: exact."""
+    from oracle import panoptic_ref
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    roi, last, cfg, meta, inp = panoptic_args(g)
+    with torch.no_grad():
+        _, _, (pan, info), dbasic, dfinal = panoptic_ref.get_panoptic(
+            roi, last, inp['cls_scores'], inp['mask_preds'], cfg, meta, inp['depth_preds'], inp['depth_init'])
+    assert np.array_equal(pan, g['panoptic'])
+    assert np.array_equal(segments_as_array(info), g['seg'])
+    assert np.array_equal(dbasic, g['depth_basic']) and np.array_equal(dfinal, g['depth_final'])
