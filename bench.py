@@ -44,6 +44,7 @@ def parse():
                     help='also materialise the (unobservable) fp32 logits + depth einsum of stages 0..S-2')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
     ap.add_argument('--no-graph', action='store_true', help='launch every step from the host instead of replaying a CUDA graph')
     ap.add_argument('--splits', type=int, default=None, help='batch windows decoded concurrently (default: 1)')
     return ap.parse_args()
@@ -288,6 +289,8 @@ def run_ours(args, rank, world, local_rank):
         line['e2e'] = e2e
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(args)
+    if not args.no_postprocess and world == 1:
+        line['postprocess'] = postprocess_timing(args, dev, cpu=not args.no_cpu_baseline)
     emit(line)
 
 
@@ -425,6 +428,49 @@ def run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier):
                 d2h_bytes_per_step=pipe.d2h_bytes(), steps=steps, ms_per_step=t.item() / steps,
                 note='HostPipeline: pinned host buffers, H2D | decode | D2H of neighbouring steps overlapped on 3 '
                      'streams, 2 device slots; bound by the PCIe read-back of the fp32 logits')
+
+
+def postprocess_timing(args, dev, cpu=True):
+    """NOT part of the headline metric (SURVEY.md section 8d excludes post-processing): pf_panoptic per frame -- the
+    reference's get_panoptic (kernel_update.py:421-535) -- on hand-constructed predictions at the frame size, device
+    time with CUDA events incl. the D2H of the three result maps; next to oracle/panoptic_ref.py on the host cores."""
+    import json as _json
+    from types import SimpleNamespace
+    from oracle import panoptic_ref, synth
+    from polyphonicformer_b200 import postprocess
+    from polyphonicformer_b200.registry import to_config
+    h, w = args.height // 4, args.width // 4
+    cfg = to_config(_json.load(open(os.path.join(ROOT, 'tests', 'golden', 'roi_head_cfg.json')))['test_cfg'])
+    roi = SimpleNamespace(num_proposals=synth.N_PROPOSALS, num_thing_classes=synth.NUM_THING, merge_joint=True)
+    last = SimpleNamespace(depth_act_mode='sigmoid', num_classes=synth.NUM_CLASSES)
+    meta = dict(img_shape=(4 * h, 4 * w, 3), ori_shape=(4 * h, 4 * w, 3), pad_shape=(4 * h, 4 * w, 3), scale_factor=1.0,
+                flip=False, batch_input_shape=(4 * h, 4 * w))
+    inp = synth.synth_panoptic_inputs(h, w, 0)
+    d = {k: v.to(dev) for k, v in inp.items()}
+    call = lambda: postprocess.get_panoptic(roi, last, d['cls_scores'], d['mask_preds'], cfg, meta, d['depth_preds'],
+                                            d['depth_init'])
+    for _ in range(3):
+        out = call()
+    torch.cuda.synchronize()
+    n = 10
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        call()
+    b.record()
+    torch.cuda.synchronize()
+    res = dict(ms_per_frame=a.elapsed_time(b) / n, segments=len(out[2][1]),
+               what='pf_panoptic on one %dx%d frame (111 kernels at %dx%d), incl. D2H of panoptic + 2 depth maps' %
+                    (4 * h, 4 * w, h, w))
+    if cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            panoptic_ref.get_panoptic(roi, last, inp['cls_scores'], inp['mask_preds'], cfg, meta, inp['depth_preds'],
+                                      inp['depth_init'])
+            res['cpu_port_ms_per_frame'] = 1e3 * (time.perf_counter() - t0)
+            res['cpu_cores'] = os.cpu_count() or 1
+    return res
 
 
 def cpu_baseline(args):
