@@ -291,6 +291,10 @@ def run_ours(args, rank, world, local_rank):
         line['cpu_baseline'] = cpu_baseline(args)
     if not args.no_postprocess and world == 1:
         line['postprocess'] = postprocess_timing(args, dev, cpu=not args.no_cpu_baseline)
+        line['e2e_simple_test'] = run_e2e_simple_test(args, eng, hin, B, N, H, W, dev)
+        if 'cpu_baseline' in line and 'cpu_port_ms_per_frame' in line['postprocess']:
+            per_frame = 1e3 / line['cpu_baseline']['value'] + line['postprocess']['cpu_port_ms_per_frame']
+            line['e2e_simple_test']['cpu_port_frames_per_s'] = 1e3 / per_frame
     emit(line)
 
 
@@ -428,6 +432,41 @@ def run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier):
                 d2h_bytes_per_step=pipe.d2h_bytes(), steps=steps, ms_per_step=t.item() / steps,
                 note='HostPipeline: pinned host buffers, H2D | decode | D2H of neighbouring steps overlapped on 3 '
                      'streams, 2 device slots; bound by the PCIe read-back of the fp32 logits')
+
+
+def run_e2e_simple_test(args, eng, hin, B, N, H, W, dev):
+    """NOT the headline (its workload includes the post-processing the metric excludes): the call a user of the
+    reference makes, KernelUpdateIterHead.simple_test, over pinned HOST buffers -- H2D of the decoder inputs, 3-stage
+    decode, pf_panoptic per frame, D2H of panoptic + depth maps + segment records (PanopticPipeline)."""
+    from polyphonicformer_b200.decoder import PanopticPipeline
+    depth = 2
+    g = torch.Generator().manual_seed(77)
+    pin_in = []
+    for _ in range(depth):
+        d = {k: v.clone().pin_memory() for k, v in hin.items()}
+        d['depth_pred'] = torch.randn(B, 1, H, W, generator=g).pin_memory()
+        pin_in.append(d)
+    H0, W0 = 8 * H, 8 * W
+    pin_out = [dict(panoptic=torch.empty((B, H0, W0), dtype=torch.int32).pin_memory(),
+                    depth_final=torch.empty((B, H0, W0)).pin_memory(), depth_basic=torch.empty((B, H0, W0)).pin_memory(),
+                    segments=torch.empty((B, 128, 24), dtype=torch.uint8).pin_memory(),
+                    nseg=torch.empty(B, dtype=torch.int32).pin_memory()) for _ in range(depth)]
+    pipe = PanopticPipeline(eng, B, N, H, W, depth=depth)
+    steps = max(4, min(args.steps, 20))
+    for i in range(3):
+        pipe.submit(pin_in[i % depth], pin_out[i % depth])
+    pipe.drain()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(pipe.s_in)
+    for i in range(steps):
+        pipe.submit(pin_in[i % depth], pin_out[i % depth])
+    b.record(pipe.s_out)
+    pipe.drain()
+    ms = a.elapsed_time(b)
+    return dict(value=B * steps / (ms / 1e3), unit='frames/s', ms_per_step=ms / steps, steps=steps,
+                h2d_bytes_per_step=pipe.h2d_bytes(), d2h_bytes_per_step=pipe.d2h_bytes(),
+                what='simple_test = decode + get_panoptic per frame; results = panoptic int32 + depth_final + depth_basic '
+                     '(12 B per pixel) + segment records')
 
 
 def postprocess_timing(args, dev, cpu=True):

@@ -103,30 +103,39 @@ __global__ void __launch_bounds__(1024) pp_select_kernel(const float* __restrict
         tb->entry_label[t] = s_idx[t] % T;
         tb->entry_score[t] = s_key[t];
     }
-    if (t < PP_MAXN) tb->area[t] = 0, tb->orig[t] = 0, tb->segid[t] = 0, tb->champ_entry[t] = -1, tb->champ_score[t] = 0.f;
+    if (t < PP_MAXN) tb->area[t] = 0, tb->orig[t] = 0, tb->segid[t] = 0;
+    __shared__ float s_stuff[PP_MAXN];
+    __shared__ int s_emask[PP_MAXE];
+    __shared__ float s_escore[PP_MAXE];
+    const int S = N - P;   // stuff kernels: score = cls[P + i][T + i], sorted descending (kernel_update.py:449-451)
+    if (t < S) s_stuff[t] = cls[(P + t) * ncls + T + t];
+    if (t < nt) s_emask[t] = s_idx[t] / T, s_escore[t] = s_key[t];
     __syncthreads();
     if (t == 0) {
-        const int S = N - P;   // stuff kernels: score = cls[P + i][T + i], sorted descending (kernel_update.py:449-451)
         int order[PP_MAXN];
         for (int i = 0; i < S; ++i) order[i] = i;
         for (int i = 1; i < S; ++i) {
             const int v = order[i];
-            const float sv = cls[(P + v) * ncls + T + v];
+            const float sv = s_stuff[v];
             int j = i - 1;
-            while (j >= 0 && cls[(P + order[j]) * ncls + T + order[j]] < sv) order[j + 1] = order[j], --j;
+            while (j >= 0 && s_stuff[order[j]] < sv) order[j + 1] = order[j], --j;
             order[j + 1] = v;
         }
         for (int i = 0; i < S; ++i) {
             tb->entry_mask[nt + i] = P + order[i];
             tb->entry_label[nt + i] = T + order[i];
-            tb->entry_score[nt + i] = cls[(P + order[i]) * ncls + T + order[i]];
+            tb->entry_score[nt + i] = s_stuff[order[i]];
+            s_emask[nt + i] = P + order[i], s_escore[nt + i] = s_stuff[order[i]];
         }
         tb->n_entries = nt + S, tb->n_thing_entries = nt;
-        for (int e = nt + S - 1; e >= 0; --e) {   // descending e: the smallest e of a proposal is written last
-            const int n = tb->entry_mask[e];
-            tb->champ_entry[n] = e;
-            tb->champ_score[n] = tb->entry_score[e];
-        }
+    }
+    __syncthreads();
+    if (t < N) {   // champion of proposal t: its lowest-numbered entry (thing entries are sorted by descending score)
+        int ce = -1;
+        for (int e = nt + S - 1; e >= 0; --e)
+            if (s_emask[e] == t) ce = e;
+        tb->champ_entry[t] = ce;
+        tb->champ_score[t] = ce >= 0 ? s_escore[ce] : 0.f;
     }
 }
 
@@ -138,6 +147,8 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
     __shared__ float s_score[PP_MAXN];
     __shared__ int s_entry[PP_MAXN];
     __shared__ int s_area[PP_MAXN], s_orig[PP_MAXN];
+    __shared__ float s_lo[PP_MAXN], s_hi[PP_MAXN];   // min / max of the sigmoid patch of proposal n
+    __shared__ int s_list[PP_MAXN], s_nlist;
     const int tid = threadIdx.x, lane = tid & 31;
     const int Y0 = blockIdx.y * PP_TY, X0 = blockIdx.x * PP_TX;
     const int py0 = make_tap(Y0, h).i0, px0 = make_tap(X0, w).i0;
@@ -153,6 +164,42 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
         s_sig[i] = sigmoidf_(__ldg(mask_logits + ((size_t)n * h + yy) * w + xx));
     }
     __syncthreads();
+    // Tile-level pruning (exact).  A bilinear sample is a convex combination of patch values, so inside this tile
+    // score_n * min(patch_n) <= score_n * mask_n(p) <= score_n * max(patch_n).  With LB = max_n score_n * min(patch_n)
+    // every pixel's winner has a product >= LB; proposal n cannot win anywhere in the tile if score_n * max(patch_n)
+    // < LB, and it adds nothing to the mask >= 0.5 counts if max(patch_n) < 0.5: such proposals are skipped.
+    for (int n = tid >> 5; n < N; n += PP_THREADS / 32) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int i = lane; i < PATCH; i += 32) {
+            const float v = s_sig[n * PATCH + i];
+            lo = fminf(lo, v), hi = fmaxf(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) s_lo[n] = lo, s_hi[n] = hi;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float lb = -1.f;
+        for (int n = lane; n < N; n += 32)
+            if (s_entry[n] >= 0) lb = fmaxf(lb, s_score[n] * s_lo[n]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lb = fmaxf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+        int cnt = 0;
+        for (int n0 = 0; n0 < N; n0 += 32) {   // ordered compaction: the list keeps ascending n
+            const int n = n0 + lane;
+            const bool keep = n < N && (s_hi[n] >= 0.5f || (s_entry[n] >= 0 && s_score[n] * s_hi[n] >= lb));
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) s_list[cnt + __popc(m & ((1u << lane) - 1u))] = n;
+            cnt += __popc(m);
+        }
+        if (lane == 0) s_nlist = cnt;
+    }
+    __syncthreads();
+    const int nlist = s_nlist;
     const int tx = tid & (PP_TX - 1), ty0 = tid / PP_TX;   // 4 pixels per thread: rows ty0 + 4 j
     const int X = X0 + tx;
     const Tap cx = make_tap(X, w);
@@ -170,7 +217,8 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
     }
     float best[4] = {-1.f, -1.f, -1.f, -1.f};
     int best_e[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, best_n[4] = {0, 0, 0, 0};
-    for (int n = 0; n < N; ++n) {
+    for (int li = 0; li < nlist; ++li) {
+        const int n = s_list[li];
         const float* sp = s_sig + n * PATCH;
         const float sc = s_score[n];
         const int e = s_entry[n];
@@ -201,39 +249,48 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void pp_merge_kernel(PpTables* __restrict__ tb, pf_segment* __restrict__ segs, int* __restrict__ n_segs, int T,
-                                float instance_score_thr, float overlap_thr) {
-    if (threadIdx.x || blockIdx.x) return;
-    const int E = tb->n_entries;
-    int order[PP_MAXE];   // argsort(-total_scores), stable
-    for (int i = 0; i < E; ++i) order[i] = i;
-    for (int i = 1; i < E; ++i) {
-        const int v = order[i];
-        const float sv = tb->entry_score[v];
-        int j = i - 1;
-        while (j >= 0 && tb->entry_score[order[j]] < sv) order[j + 1] = order[j], --j;
-        order[j + 1] = v;
-    }
-    int seg = 0;
-    for (int i = 0; i < E; ++i) {
-        const int k = order[i];
-        const int label = tb->entry_label[k];
-        const bool isthing = label < T;
-        const float score = tb->entry_score[k];
-        if (isthing && score < instance_score_thr) continue;
-        const int n = tb->entry_mask[k];
-        if (tb->champ_entry[n] != k) continue;          // a better entry owns this mask: this one won no pixel
-        const int area = tb->area[n], orig = tb->orig[n];
-        if (area > 0 && orig > 0) {
-            if ((double)area / (double)orig < (double)overlap_thr) continue;
-            ++seg;
-            tb->segid[n] = seg;
-            pf_segment s;
-            s.id = seg, s.isthing = isthing ? 1 : 0, s.category_id = label, s.instance_id = k, s.area = area, s.score = score;
-            segs[seg - 1] = s;
+__global__ void __launch_bounds__(128) pp_merge_kernel(PpTables* __restrict__ tb, pf_segment* __restrict__ segs,
+                                                       int* __restrict__ n_segs, int T, float instance_score_thr,
+                                                       float overlap_thr) {
+    __shared__ float s_score[PP_MAXE];
+    __shared__ int s_mask[PP_MAXE], s_label[PP_MAXE], s_champ[PP_MAXN], s_area[PP_MAXN], s_orig[PP_MAXN], s_segid[PP_MAXN];
+    __shared__ int s_order[PP_MAXE];
+    const int t = threadIdx.x;
+    const int E = tb->n_entries, nth = tb->n_thing_entries;
+    if (t < E) s_score[t] = tb->entry_score[t], s_mask[t] = tb->entry_mask[t], s_label[t] = tb->entry_label[t];
+    if (t < PP_MAXN) s_champ[t] = tb->champ_entry[t], s_area[t] = tb->area[t], s_orig[t] = tb->orig[t], s_segid[t] = 0;
+    __syncthreads();
+    if (t == 0) {
+        // argsort(-total_scores), stable: the thing entries [0, nth) and the stuff entries [nth, E) are each sorted
+        // by descending score already (pp_select), so this is a two-way merge
+        int i0 = 0, i1 = nth, no = 0;
+        while (i0 < nth || i1 < E) {
+            const bool take0 = i1 >= E || (i0 < nth && s_score[i0] >= s_score[i1]);
+            s_order[no++] = take0 ? i0++ : i1++;
         }
+        int seg = 0;
+        for (int i = 0; i < E; ++i) {
+            const int k = s_order[i];
+            const int label = s_label[k];
+            const bool isthing = label < T;
+            const float score = s_score[k];
+            if (isthing && score < instance_score_thr) continue;
+            const int n = s_mask[k];
+            if (s_champ[n] != k) continue;          // a better entry owns this mask: this one won no pixel
+            const int area = s_area[n], orig = s_orig[n];
+            if (area > 0 && orig > 0) {
+                if ((double)area / (double)orig < (double)overlap_thr) continue;
+                ++seg;
+                s_segid[n] = seg;
+                pf_segment sg;
+                sg.id = seg, sg.isthing = isthing ? 1 : 0, sg.category_id = label, sg.instance_id = k, sg.area = area, sg.score = score;
+                segs[seg - 1] = sg;
+            }
+        }
+        *n_segs = seg;
     }
-    *n_segs = seg;
+    __syncthreads();
+    if (t < PP_MAXN) tb->segid[t] = s_segid[t];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -302,7 +359,7 @@ extern "C" int pf_panoptic(const float* cls_scores, const float* mask_logits, co
     dim3 grid((W0 + PP_TX - 1) / PP_TX, (H0 + PP_TY - 1) / PP_TY);
     pp_argmax_kernel<<<grid, PP_THREADS, smem, st>>>(mask_logits, tb, ids, N, h, w, H0, W0);
     PF_CHECK_LAUNCH("pp_argmax_kernel");
-    pp_merge_kernel<<<1, 32, 0, st>>>(tb, segments, n_segments, num_thing_classes, instance_score_thr, overlap_thr);
+    pp_merge_kernel<<<1, 128, 0, st>>>(tb, segments, n_segments, num_thing_classes, instance_score_thr, overlap_thr);
     PF_CHECK_LAUNCH("pp_merge_kernel");
     pp_paint_kernel<<<dim3((W0 + 255) / 256, H0), 256, 0, st>>>(depth_logits, depth_init, tb, ids, panoptic, depth_final,
                                                                  depth_basic, h, w, H0, W0, depth_mode);

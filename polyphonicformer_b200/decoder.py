@@ -476,3 +476,79 @@ class HostPipeline:
     def drain(self):
         for st in (self.s_in, self.s_run, self.s_out):
             st.synchronize()
+
+
+class PanopticPipeline(HostPipeline):
+    """``KernelUpdateIterHead.simple_test`` over HOST buffers (kernel_update.py:282-354): like HostPipeline, but the
+    decoder's logits never leave the device -- ``pf_panoptic`` turns them into the panoptic map and the two depth maps
+    per frame, and only those (12 bytes per pixel) plus the segment records are copied back.
+
+    host_in : HostPipeline's inputs + depth_pred [B,1,H,W] f32 (KernelHead's initial depth prediction)
+    host_out: panoptic [B,H0,W0] i32; depth_final, depth_basic [B,H0,W0] f32; segments [B,128,24] u8 (struct
+              pf_segment records); nseg [B] i32 -- all pinned;  H0 = 8H, W0 = 8W (no padding crop)
+    """
+
+    def __init__(self, engine, B, N, H, W, num_proposals=100, num_thing_classes=8, max_per_img=100,
+                 instance_score_thr=0.3, overlap_thr=0.6, depth_act_mode='sigmoid', depth=2):
+        super().__init__(engine, B, N, H, W, upsample=True, depth=depth)
+        dev = engine.device
+        lib = _cabi.load()
+        self.cfg = (num_proposals, num_thing_classes, max_per_img, float(instance_score_thr), float(overlap_thr),
+                    {'monodepth': 0, 'sigmoid': 1}[depth_act_mode])
+        H0, W0 = 8 * H, 8 * W
+        self.pws_bytes = lib.pf_panoptic_workspace_bytes(H0, W0)
+        for s in self.slots:
+            s.update(dpred=torch.empty((B, 1, H, W), dtype=torch.float32, device=dev),
+                     dinit=torch.empty((B, 2 * H, 2 * W), dtype=torch.float32, device=dev),
+                     pan=torch.empty((B, H0, W0), dtype=torch.int32, device=dev),
+                     dfinal=torch.empty((B, H0, W0), dtype=torch.float32, device=dev),
+                     dbasic=torch.empty((B, H0, W0), dtype=torch.float32, device=dev),
+                     segs=torch.zeros((B, 128, 24), dtype=torch.uint8, device=dev),
+                     nseg=torch.zeros(B, dtype=torch.int32, device=dev),
+                     pws=[torch.empty(self.pws_bytes, dtype=torch.uint8, device=dev) for _ in range(B)])
+
+    def h2d_bytes(self):
+        return super().h2d_bytes() + self.slots[0]['dpred'].numel() * 4
+
+    def d2h_bytes(self):
+        s = self.slots[0]
+        return sum(s[k].numel() * s[k].element_size() for k in ('pan', 'dfinal', 'dbasic', 'segs', 'nseg'))
+
+    def submit(self, host_in, host_out):
+        s = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        B, N, H, W = self.B, self.N, self.H, self.W
+        P, T, max_per_img, thr_i, thr_o, dmode = self.cfg
+        ncls = self.eng.num_classes
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(s['ev_run'])
+            s['x'].copy_(host_in['x'], non_blocking=True), s['d'].copy_(host_in['d'], non_blocking=True)
+            s['mask'].copy_(host_in['mask'], non_blocking=True)
+            s['dpred'].copy_(host_in['depth_pred'], non_blocking=True)
+            s['buf']['obj'].copy_(host_in['prop'].reshape(B, N, PF_C), non_blocking=True)
+            s['buf']['dep'].copy_(host_in['dprop'].reshape(B, N, PF_C), non_blocking=True)
+            s['ev_in'].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(s['ev_in'])
+            self.s_run.wait_event(s['ev_out'])           # the previous results of this slot have been read back
+            if not self.direct:
+                HW = H * W
+                s['feats'][0, :, :, :HW].copy_(s['x'].reshape(B, PF_C, HW))
+                s['feats'][1, :, :, :HW].copy_(s['d'].reshape(B, PF_C, HW))
+            self.eng.decode_inplace(s['feats'], s['mask'], s['buf'], H, W)
+            st = _stream_ptr()
+            _cabi.call('pf_upsample2x', _ptr(s['dpred']), _ptr(s['dinit']), B, H, W, st)    # kernel_update.py:302-307
+            scaled, cls = s['buf']['scaled'], s['buf']['cls']
+            for b in range(B):
+                _cabi.call('pf_panoptic', _ptr(cls[b]), _ptr(scaled[0, b]), _ptr(scaled[1, b]), _ptr(s['dinit'][b]), N, P,
+                           T, ncls, 2 * H, 2 * W, 8 * H, 8 * W, max_per_img, thr_i, thr_o, dmode, _ptr(s['pan'][b]),
+                           _ptr(s['dfinal'][b]), _ptr(s['dbasic'][b]), _ptr(s['segs'][b]), _ptr(s['nseg'][b:]),
+                           _ptr(s['pws'][b]), self.pws_bytes, st)
+            s['ev_run'].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(s['ev_run'])
+            for k, hk in (('pan', 'panoptic'), ('dfinal', 'depth_final'), ('dbasic', 'depth_basic'), ('segs', 'segments'),
+                          ('nseg', 'nseg')):
+                host_out[hk].copy_(s[k], non_blocking=True)
+            s['ev_out'].record(self.s_out)
+        return s['ev_out']

@@ -98,3 +98,49 @@ def test_panoptic_unsupported_geometry_raises(dev):
     meta = dict(meta, ori_shape=(200, 400, 3))                            # a real rescale: not covered, must not fall back
     with pytest.raises(NotImplementedError):
         run(dev, roi, last, cfg, meta, inp)
+
+
+def test_panoptic_pipeline_matches_module_simple_test(dev):
+    """PanopticPipeline (host buffers, overlapped submissions) == decode + per-frame get_panoptic done step by step."""
+    from types import SimpleNamespace
+    import json
+    from polyphonicformer_b200 import postprocess
+    from polyphonicformer_b200.decoder import DecoderEngine, PanopticPipeline
+    from polyphonicformer_b200.registry import to_config
+    B, H, W = 2, 16, 24
+    sd = synth.synth_decoder_state(3, 0)
+    stage_dicts = [{k[len('mask_head.%d.' % s):]: v for k, v in sd.items() if k.startswith('mask_head.%d.' % s)}
+                   for s in range(3)]
+    eng = DecoderEngine(stage_dicts, dev)
+    cfg = to_config(json.load(open(os.path.join(GOLDEN, 'roi_head_cfg.json')))['test_cfg'])
+    roi = SimpleNamespace(num_proposals=synth.N_PROPOSALS, num_thing_classes=synth.NUM_THING, merge_joint=True)
+    last = SimpleNamespace(depth_act_mode='sigmoid', num_classes=synth.NUM_CLASSES)
+    meta = dict(img_shape=(8 * H, 8 * W, 3), ori_shape=(8 * H, 8 * W, 3), batch_input_shape=(8 * H, 8 * W))
+    pipe = PanopticPipeline(eng, B, synth.N_KERNELS, H, W)
+    ins, outs, want = [], [], []
+    for seed in range(3):
+        inp = synth.synth_decoder_inputs(B, H, W, seed)
+        feats = eng.prepare_feats(inp['x_feats'].to(dev), inp['depth_feats'].to(dev))
+        o = eng.decode(feats, inp['mask_preds'].to(dev), inp['proposal_feats'].to(dev), inp['depth_proposal'].to(dev), H, W)
+        dinit = eng.upsample2x(inp['depth_pred'].to(dev))
+        want.append([postprocess.get_panoptic(roi, last, o['cls_score'][b], o['scaled_mask_preds'][b], cfg, meta,
+                                              o['scaled_depth_preds'][b], dinit[b]) for b in range(B)])
+        ins.append(dict(x=inp['x_feats'].to(torch.bfloat16).pin_memory(), d=inp['depth_feats'].to(torch.bfloat16).pin_memory(),
+                        mask=inp['mask_preds'].pin_memory(), prop=inp['proposal_feats'].reshape(B, -1, 256).pin_memory(),
+                        dprop=inp['depth_proposal'].reshape(B, -1, 256).contiguous().pin_memory(),
+                        depth_pred=inp['depth_pred'].pin_memory()))
+        outs.append(dict(panoptic=torch.empty((B, 8 * H, 8 * W), dtype=torch.int32).pin_memory(),
+                         depth_final=torch.empty((B, 8 * H, 8 * W)).pin_memory(),
+                         depth_basic=torch.empty((B, 8 * H, 8 * W)).pin_memory(),
+                         segments=torch.empty((B, 128, 24), dtype=torch.uint8).pin_memory(),
+                         nseg=torch.empty(B, dtype=torch.int32).pin_memory()))
+    for i in range(3):
+        pipe.submit(ins[i], outs[i])
+    pipe.drain()
+    for i in range(3):
+        for b in range(B):
+            _, _, (pan, info), dbasic, dfinal = want[i][b]
+            assert np.array_equal(outs[i]['panoptic'][b].numpy(), pan)
+            assert np.array_equal(outs[i]['depth_final'][b].numpy(), dfinal)
+            assert np.array_equal(outs[i]['depth_basic'][b].numpy(), dbasic)
+            assert int(outs[i]['nseg'][b]) == len(info)
