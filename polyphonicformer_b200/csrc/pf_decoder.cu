@@ -81,13 +81,23 @@ extern "C" int pf_decoder_forward_slice(const pf_stage_weights* stages, int n_st
         if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, nullptr, s.kern, s.kbias,
                                      s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
             return e;
-        int e;
+        int e = PF_OK;
+        if (last && scaled_out && !(flags & PF_FWD_ALL_STAGE_OUTPUTS)) {
+            // last stage, branch by branch: einsum -> x2 up-sampling while the 58 MB of logits are still L2-resident
+            for (int br = 0; br < 2 && !e; ++br) {
+                e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, nullptr, B_total, b0, B, N, HW, HWp, B, br, 1, stream);
+                const size_t u0 = ((size_t)br * B_total + b0) * N;
+                if (!e) e = pf_upsample2x(logits_out + u0 * HW, scaled_out + u0 * 4 * HW, B * N, H, W, stream);
+            }
+            if (e) return e;
+            return PF_OK;
+        }
         if (last)
-            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, nullptr, B_total, b0, B, N, HW, HWp, 2 * B, 1, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, nullptr, B_total, b0, B, N, HW, HWp, 2 * B, 0, 1, stream);
         else if (flags & PF_FWD_ALL_STAGE_OUTPUTS)
-            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, s.bits, B_total, b0, B, N, HW, HWp, 2 * B, 1, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, logits_out, s.bits, B_total, b0, B, N, HW, HWp, 2 * B, 0, 1, stream);
         else  // only the sign of the next mask is observable (kernel_update_head.py:236-238)
-            e = mask_einsum_window(feats, s.kern, s.kbias, nullptr, s.bits, B_total, b0, B, N, HW, HWp, B, 1, stream);
+            e = mask_einsum_window(feats, s.kern, s.kbias, nullptr, s.bits, B_total, b0, B, N, HW, HWp, B, 0, 1, stream);
         if (e) return e;
     }
     if (scaled_out)

@@ -46,13 +46,15 @@ struct EinsumParams {
     int N, HW, words, B;
     int tiles_per_unit, ctas_per_unit;
     int Btot, b0;        // batch window inside the [2][Btot] feature / logits tensors
+    int unit0;           // first unit of this launch (B: depth branch only)
     int early_feats;     // the feature maps were complete before the PREVIOUS kernel started: prefetch them before pdl_wait
 };
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                                             uint64_t hint) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
                  :
-                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
                  : "memory");
 }
 __device__ __forceinline__ void epi_bar4() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
@@ -77,7 +79,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * E_STAGES + 2 * E_ACC + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int unit = blockIdx.x / p.ctas_per_unit;
+    const int unit = p.unit0 + blockIdx.x / p.ctas_per_unit;
     const int j = blockIdx.x % p.ctas_per_unit;
     const int tile_begin = (int)((long long)j * p.tiles_per_unit / p.ctas_per_unit);
     const int tile_end = (int)((long long)(j + 1) * p.tiles_per_unit / p.ctas_per_unit);
@@ -235,7 +237,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                     fence_proxy_async_smem();
                     epi_bar4();
                     if (threadIdx.x == 64) {
-                        tma_store_3d(&tmap_out, tile, hwb, 0, gunit);
+                        // evict-last: the x2 up-sampling that follows reads these logits back, ideally from L2
+                        tma_store_3d(&tmap_out, tile, hwb, 0, gunit, kEvictLast);
                         tma_store_commit();
                     }
                 } else if (orow && row_ok) {
@@ -296,17 +299,19 @@ extern "C" int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_u
 
 namespace pf {
 int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits, uint32_t* bits_out,
-                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int early_feats, void* stream);
+                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int branch0, int early_feats,
+                       void* stream);
 }
 extern "C" int pf_mask_einsum(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
                               uint32_t* bits_out, int B, int N, int HW, int HWp, int n_units, void* stream) {
-    return pf::mask_einsum_window(feats, kern, kbias, logits, bits_out, B, 0, B, N, HW, HWp, n_units, 0, stream);
+    return pf::mask_einsum_window(feats, kern, kbias, logits, bits_out, B, 0, B, N, HW, HWp, n_units, 0, 0, stream);
 }
 
-// feats / logits: the FULL [2][Btot][..] tensors; kern / kbias / bits_out: buffers of the window's B images
+// feats / logits: the FULL [2][Btot][..] tensors; kern / kbias / bits_out: buffers of the window's B images.
+// branch0 = 1 with n_units = B runs the depth branch alone (units B .. 2B-1).
 int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits,
-                           uint32_t* bits_out, int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int early_feats,
-                           void* stream) {
+                           uint32_t* bits_out, int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int branch0,
+                           int early_feats, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(Btot >= B && b0 >= 0 && b0 + B <= Btot, PF_ERR_ARG, "pf_mask_einsum: bad batch window %d+%d of %d", b0, B, Btot);
@@ -314,17 +319,18 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     PF_REQUIRE(logits || bits_out, PF_ERR_ARG, "pf_mask_einsum: no output requested");
     PF_REQUIRE(B > 0 && N > 0 && N <= PF_MAX_N && HW > 0, PF_ERR_ARG, "pf_mask_einsum: bad shape B=%d N=%d HW=%d", B, N, HW);
     PF_REQUIRE(n_units == B || n_units == 2 * B, PF_ERR_ARG, "pf_mask_einsum: n_units must be B or 2B");
+    PF_REQUIRE(branch0 == 0 || (branch0 == 1 && n_units == B && !bits_out), PF_ERR_ARG, "pf_mask_einsum: bad branch selection");
     PF_REQUIRE(HWp >= HW && HWp % 8 == 0, PF_ERR_ALIGN, "pf_mask_einsum: HWp=%d must be >= HW and a multiple of 8", HWp);
     PF_REQUIRE((reinterpret_cast<uintptr_t>(kern) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: kern_split not 16-byte aligned");
     PF_REQUIRE(!logits || (reinterpret_cast<uintptr_t>(logits) & 15) == 0, PF_ERR_ALIGN, "pf_mask_einsum: logits not 16-byte aligned");
 
     CUtensorMap tmap;
-    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)(n_units / B) * Btot * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
+    if (int e = make_tmap_bf16_2d(&tmap, feats, (uint64_t)(branch0 + n_units / B) * Btot * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
 
     EinsumParams p;
     p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
-    p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats;
+    p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats, p.unit0 = branch0 * B;
     p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
     int cpu = num_sms() / n_units;
     if (cpu < 1) cpu = 1;
@@ -335,7 +341,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     const bool tma_out = logits && (HW % 4) == 0;
     CUtensorMap tmap_o = tmap;
     if (tma_out)
-        if (int e = make_tmap_f32_3d(&tmap_o, logits, (uint64_t)(n_units / B) * Btot, (uint64_t)N, (uint64_t)HW, 128, 32)) return e;
+        if (int e = make_tmap_f32_3d(&tmap_o, logits, (uint64_t)(branch0 + n_units / B) * Btot, (uint64_t)N, (uint64_t)HW, 128, 32)) return e;
     auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
     cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));

@@ -32,7 +32,8 @@ int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d
 int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,
                      int N, int HW, int HWp, int n_branch, int S, int early_feats, void* stream);
 int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float* kbias, float* logits, uint32_t* bits_out,
-                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int early_feats, void* stream);
+                       int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int branch0, int early_feats,
+                       void* stream);
 
 // Launch with programmatic stream serialization (PDL): the kernel may begin before its predecessor in the stream has
 // finished; it must execute griddepcontrol.wait (pdl_wait) before touching anything the predecessor wrote.
