@@ -117,10 +117,11 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             // inside the decode loop the feature tiles are long-complete inputs: fill the ring before the grid
             // dependency resolves
             if (!p.early_feats) pdl_wait();
+            const uint64_t fhint = unit < p.B ? kEvictLast : kEvictFirst;   // x_feats stays L2-resident across kernels
             const int pre = ntiles < STAGES ? ntiles : STAGES;
             for (int i = 0; i < pre; ++i) {
                 mbar_arrive_expect_tx(&full[i], E_B_BYTES);
-                tma_load_2d(sB + i * E_B_BYTES, &tmap_feats, &full[i], (tile_begin + i) * E_BHW, gunit * E_C, kEvictFirst);
+                tma_load_2d(sB + i * E_B_BYTES, &tmap_feats, &full[i], (tile_begin + i) * E_BHW, gunit * E_C, fhint);
             }
             for (int i = pre; i < ntiles; ++i) {
                 const int s = i % STAGES;
@@ -129,8 +130,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 if (i == 3) DBG(2);
                 if (i == ntiles - 1) DBG(3);
                 mbar_arrive_expect_tx(&full[s], E_B_BYTES);
-                tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, gunit * E_C,
-                            kEvictFirst);
+                tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, gunit * E_C, fhint);
             }
         }
     } else if (warp == 1) {

@@ -95,8 +95,10 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
                 if (i == 4) DBG(2);
                 if (i == ntiles - 1) DBG(3);
                 mbar_arrive_expect_tx(&fullB[s], P_B_BYTES);
+                // x_feats (branch 0) is read by every kernel of every stage: keep it in the 126 MB L2 (evict-last);
+                // depth_feats is only read here (and by the last einsum): stream it (evict-first)
                 tma_load_2d(smem + s * P_STAGE_BYTES + P_A_BYTES, &tmap_feats, &fullB[s], (tile_begin + i) * P_BHW,
-                            ((unit / p.B) * p.Btot + p.b0 + b) * P_C, kEvictFirst);
+                            ((unit / p.B) * p.Btot + p.b0 + b) * P_C, unit < p.B ? kEvictLast : kEvictFirst);
             }
         }
     } else if (warp == 1) {

@@ -311,8 +311,8 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         const CUtensorMap* wm = p.w_ffn ? &tmap_wffn : &tmap_w256;
         const int k = p.w_k0 + (p.w_ffn ? split * T_K : 0) + kb * T_KC;
         mbar_arrive_expect_tx_warp(&full[s], T_STAGE);
-        tma_load_2d_warp(st + 2 * T_PLANE, wm, &full[s], k, p.w_row + nb, kEvictLast);
-        tma_load_2d_warp(st + 3 * T_PLANE, wm, &full[s], k, p.w_row + p.w_lo + nb, kEvictLast);
+        tma_load_2d_warp(st + 2 * T_PLANE, wm, &full[s], k, p.w_row + nb, kEvictNormal);
+        tma_load_2d_warp(st + 3 * T_PLANE, wm, &full[s], k, p.w_row + p.w_lo + nb, kEvictNormal);
     };
     auto issue_a = [&](int it) {
         const TcPass& p = g.pass[it >> 2];
