@@ -136,6 +136,12 @@ int pf_mask_pool(const uint16_t* feats, const uint32_t* bits, float* partial, fl
 int pf_pool_reduce(const float* partial, const float* cntp, float* pooled, float* count, int B, int N, int n_branch,
                    int S, void* stream);
 
+/* kernel_head.py:313-336 (the producer of the decoder's kernels): proposal_feats [B][P + n_stuff][256] =
+ * [init_kernels [P][256] + pooled features of the P proposal masks ; stuff_kernels [n_stuff][256] for every image].
+ * partial / cntp: output of pf_mask_pool(n_branch = 1, N = P) over x_feats and the sign bits of the initial masks. */
+int pf_init_proposals(const float* partial, const float* cntp, const float* init_kernels, const float* stuff_kernels,
+                      float* proposal_feats, int B, int P, int n_stuff, int S, void* stream);
+
 /* bytes of scratch pf_kernel_update needs */
 size_t pf_update_workspace_bytes(int B, int N, int ffn_channels);
 

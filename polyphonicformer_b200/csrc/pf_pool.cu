@@ -178,7 +178,9 @@ namespace pf {
 // sum over splits in a fixed order: pooled[g][n][c], count[b][n].  64 threads x float4 per row, 4 rows per block.
 __global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restrict__ partial,
                                                           const float* __restrict__ cntp, float* __restrict__ pooled,
-                                                          float* __restrict__ count, int G, int B, int N, int S) {
+                                                          float* __restrict__ count, int G, int B, int N, int S,
+                                                          const float* __restrict__ addend, int out_rows) {
+    pdl_wait();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 6);  // g * N + n
     if (row >= G * N) return;
     const int g = row / N, n = row % N;
@@ -198,7 +200,11 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restric
         const float4 v = __ldg(src + (size_t)s * stride4);
         acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
     }
-    reinterpret_cast<float4*>(pooled + (size_t)row * P_C)[c4] = acc;
+    if (addend) {   // KernelHead: proposal_feats = init_kernels.weight + obj_feats (kernel_head.py:324-326)
+        const float4 a = __ldg(reinterpret_cast<const float4*>(addend + (size_t)n * P_C) + c4);
+        acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+    }
+    reinterpret_cast<float4*>(pooled + ((size_t)g * out_rows + n) * P_C)[c4] = acc;
     if (c4 == 0 && g < B && count) {
         float k = 0.f;
         for (int s2 = 0; s2 < S; ++s2) k += cntp[((size_t)g * S + s2) * N + n];
@@ -259,8 +265,32 @@ extern "C" int pf_pool_reduce(const float* partial, const float* cntp, float* po
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(partial && cntp && pooled, PF_ERR_ARG, "pf_pool_reduce: null pointer");
-    pool_reduce_kernel<<<(n_branch * B * N + 3) / 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, cntp, pooled, count,
-                                                                                       n_branch * B, B, N, S);
-    PF_CHECK_LAUNCH("pool_reduce_kernel");
+    return launch_pdl("pool_reduce_kernel", pool_reduce_kernel, dim3((n_branch * B * N + 3) / 4), dim3(256), 0,
+                      static_cast<cudaStream_t>(stream), partial, cntp, pooled, count, n_branch * B, B, N, S,
+                      (const float*)nullptr, N);
+}
+
+// KernelHead._decode_init_proposals, the part that is "K1 with N = num_proposals" (polyphonic/kernel_head.py:313-336):
+//   proposal_feats[b][n] = init_kernels.weight[n] + sum_hw 1[mask_preds[b][n][hw] > 0] * x_feats[b][:, hw]   n < P
+//   proposal_feats[b][P + j] = conv_seg.weight[num_thing_classes + j]                                        (stuff kernels)
+// `partial` / `cntp` come from pf_mask_pool(n_branch = 1) over the P proposal masks.
+extern "C" int pf_init_proposals(const float* partial, const float* cntp, const float* init_kernels,
+                                 const float* stuff_kernels, float* proposal_feats, int B, int P, int n_stuff, int S,
+                                 void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(partial && cntp && init_kernels && proposal_feats && (n_stuff == 0 || stuff_kernels), PF_ERR_ARG,
+               "pf_init_proposals: null pointer");
+    PF_REQUIRE(B > 0 && P > 0 && n_stuff >= 0 && P + n_stuff <= PF_MAX_N && S > 0, PF_ERR_ARG, "pf_init_proposals: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int N = P + n_stuff;
+    if (int e = launch_pdl("pool_reduce_kernel", pool_reduce_kernel, dim3((B * P + 3) / 4), dim3(256), 0, st, partial, cntp,
+                           proposal_feats, (float*)nullptr, B, B, P, S, init_kernels, N))
+        return e;
+    for (int b = 0; b < B && n_stuff > 0; ++b) {   // the same stuff kernels for every image
+        cudaError_t e = cudaMemcpyAsync(proposal_feats + ((size_t)b * N + P) * P_C, stuff_kernels,
+                                        (size_t)n_stuff * P_C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "pf_init_proposals: stuff kernel copy: %s", cudaGetErrorString(e));
+    }
     return PF_OK;
 }

@@ -309,6 +309,35 @@ class DecoderEngine:
                    2 * B, st)
         return cls, logits, obj_out, dep_out
 
+    def init_proposals(self, feats, mask_preds, init_kernels_weight, seg_preds, conv_seg_weight, depth_kernel_weight,
+                       num_thing_classes):
+        """The tail of KernelHead._decode_init_proposals (polyphonic/kernel_head.py:313-336) on the decoder's kernels:
+        binarise the P initial masks, pool x_feats under them (pf_mask_pool, one branch), add init_kernels.weight
+        (pf_init_proposals), append the stuff masks / stuff kernels, expand the depth kernel.
+        feats: prepare_feats(...) layout; mask_preds [B,P,H,W]; returns (proposal_feats [B,N,256,1,1],
+        mask_preds [B,N,H,W], depth_proposal [B,N,256,1,1]) as the reference hands them to the decoder."""
+        lib = _cabi.load()
+        B, P, H, W = mask_preds.shape
+        HW, HWp = H * W, feats.shape[-1]
+        T = num_thing_classes
+        n_stuff = conv_seg_weight.shape[0] - T
+        N = P + n_stuff
+        st = _stream_ptr()
+        mask_preds = mask_preds.float().contiguous()
+        bits = torch.empty((B, (HW + 31) // 32, 128), dtype=torch.int32, device=self.device)
+        S = lib.pf_pool_splits(B, 1, HW)
+        partial = torch.empty((B, S, P, PF_C), dtype=torch.float32, device=self.device)
+        cntp = torch.empty((B, S, P), dtype=torch.float32, device=self.device)
+        wk = init_kernels_weight.reshape(P, PF_C).float().contiguous()
+        sk = conv_seg_weight.reshape(-1, PF_C)[T:].float().contiguous()
+        prop = torch.empty((B, N, PF_C), dtype=torch.float32, device=self.device)
+        _cabi.call('pf_binarise', _ptr(mask_preds), _ptr(bits), B, P, HW, st)
+        _cabi.call('pf_mask_pool', _ptr(feats), _ptr(bits), _ptr(partial), _ptr(cntp), B, P, HW, HWp, 1, S, st)
+        _cabi.call('pf_init_proposals', _ptr(partial), _ptr(cntp), _ptr(wk), _ptr(sk), _ptr(prop), B, P, n_stuff, S, st)
+        masks = torch.cat([mask_preds, seg_preds[:, T:T + n_stuff].float()], dim=1)             # data movement only
+        dprop = depth_kernel_weight.reshape(1, 1, PF_C, 1, 1).float().expand(B, N, PF_C, 1, 1)
+        return prop.reshape(B, N, PF_C, 1, 1), masks, dprop
+
     def upsample2x(self, maps):
         """[..., H, W] fp32 -> [..., 2H, 2W] (bilinear, align_corners=False)."""
         maps = maps.contiguous()

@@ -199,3 +199,33 @@ def test_kernel_updator_row_groups(dev, rows):
     torch.cuda.synchronize()
     l2, mx = rel_err(out.cpu(), want)
     assert l2 < 5e-5 and mx < 5e-5, (rows, l2, mx)
+
+
+def test_init_proposals_matches_kernel_head_tail(dev):
+    """KernelHead._decode_init_proposals' tail (kernel_head.py:313-336) restated with plain PyTorch ops vs
+    DecoderEngine.init_proposals (binarise + one-branch pooling + pf_init_proposals)."""
+    Bs, Hs, Ws, P, T, S_ = 2, 24, 40, synth.N_PROPOSALS, synth.NUM_THING, synth.NUM_STUFF
+    eng, _ = make_engine(0, dev)
+    g = torch.Generator().manual_seed(11)
+    x = synth.bf16_round(torch.relu(torch.randn(Bs, 256, Hs, Ws, generator=g)))
+    d = synth.bf16_round(torch.relu(torch.randn(Bs, 256, Hs, Ws, generator=g)))
+    mask = torch.randn(Bs, P, Hs, Ws, generator=g) - 0.3
+    mask[0, 3] = -2.0                                                     # an empty mask: obj_feats = 0
+    seg = torch.randn(Bs, T + S_, Hs, Ws, generator=g)
+    w_init = torch.randn(P, 256, 1, 1, generator=g)
+    w_seg = torch.randn(T + S_, 256, 1, 1, generator=g) * 0.01
+    w_dd = torch.randn(1, 256, 1, 1, generator=g) * 0.01
+    # kernel_head.py:313-336 (use_binary=True, proposal_feats_with_obj=True, cat_stuff_mask=True, eval)
+    obj = torch.einsum('bnhw,bchw->bnc', (mask.sigmoid() > 0.5).float(), x)
+    want_prop = torch.cat([w_init[None].expand(Bs, -1, -1, -1, -1) + obj.view(Bs, P, 256, 1, 1),
+                           w_seg[T:][None].expand(Bs, -1, -1, -1, -1)], dim=1)
+    want_mask = torch.cat([mask, seg[:, T:]], dim=1)
+    feats = eng.prepare_feats(x.to(dev), d.to(dev))
+    prop, masks, dprop = eng.init_proposals(feats, mask.to(dev), w_init.to(dev), seg.to(dev), w_seg.to(dev), w_dd.to(dev), T)
+    torch.cuda.synchronize()
+    assert prop.shape == (Bs, P + S_, 256, 1, 1) and dprop.shape == (Bs, P + S_, 256, 1, 1)
+    l2, mx = rel_err(prop.cpu(), want_prop)
+    assert l2 < 2e-6 and mx < 2e-6, (l2, mx)
+    assert torch.equal(prop[:, P:].cpu(), want_prop[:, P:]) and torch.equal(masks.cpu(), want_mask)
+    assert torch.equal(prop[0, 3].cpu().flatten(), w_init[3].flatten())   # empty mask -> the bare init kernel
+    assert torch.equal(dprop[1, 7].cpu(), w_dd[0])
