@@ -405,7 +405,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
     # measured DRAM traffic per launch from the committed ncu --set full capture of the same shapes (profiles/)
     ncu_name = {'binarise': ('binarise_kernel', 1), 'mask_pool': ('pool_kernel', 1),
                 'mask_einsum (bits only, mask branch)': ('einsum_kernel<0>', 1),
-                'mask_einsum (fp32 logits, both branches)': ('einsum_kernel<1>', 1),
+                'mask_einsum (fp32 logits, both branches)': ('einsum_kernel<1>', 2),   # the step launches it per branch
                 'upsample2x': ('upsample2x_kernel', 2)}     # the step launches it once per branch
     traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
