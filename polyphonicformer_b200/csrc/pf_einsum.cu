@@ -9,7 +9,8 @@
 //        128x64x16 MMA, in-kernel timeline), not by HBM; TS mode reads only the 2 KB feature slice per MMA;
 //   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 6-stage ring
 //        (192 KB in flight per SM);
-//   D  = [128 lanes][64 columns] fp32 in TMEM, 4 accumulator buffers so the epilogue overlaps the next tiles;
+//   D  = [128 lanes][64 | 128 columns] fp32 in TMEM, 4 | 2 accumulator buffers so the epilogue overlaps the next
+//        tiles (128-pixel tiles = MMA N 128 when only sign bits are emitted: half the MMA issues per pixel);
 //   epilogue: tcgen05.ld -> + bias -> the packed sign bits consumed by the next stage's pooling (thread = kernel row
 //             n, 32 consecutive pixels = one u32 word) and/or fp32 logits.  Logits leave through shared memory:
 //             each thread writes its 32 pixels into a 128-byte-swizzled [128 rows][32 px] tile, one thread issues a
@@ -29,8 +30,8 @@ constexpr int E_BHW = 64;            // pixels per tile (= N of the MMA, one 128
 constexpr int E_STAGES = 6;          // feature ring depth without the logits staging tiles
 constexpr int E_STAGES_TMA = 5;      // ... with them
 constexpr int E_OUT_BYTES = 128 * 32 * 4;   // one staged half tile: [128 rows][32 px] fp32
-constexpr int E_ACC = 2;             // TMEM accumulator buffers; each = a hi and a lo accumulator of 64 columns (the
-                                     // two MMA chains of a tile are independent, so they overlap in the tensor pipe)
+constexpr int E_ACC = 2;             // 2 * E_ACC * 64 = 256 TMEM columns of accumulators: 4 buffers of 64-pixel tiles
+                                     // or 2 buffers of 128-pixel tiles
 constexpr int E_TMEM_A = 2 * E_ACC * E_BHW; // first TMEM column of A hi; A lo follows 128 columns later
 constexpr int E_TMEM_COLS = 512;            // 256 accumulator + 2 x 128 A columns: the whole tensor memory
 constexpr int E_B_BYTES = E_C * E_BHW * 2;  // 32768 per stage
@@ -59,13 +60,18 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void epi_bar4() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
-// TMA_OUT: fp32 logits leave as TMA tensor stores of staged tiles (tmap_out over [units][N][HW]); the feature ring
-// then has STAGES = 2 and the two staging tiles live behind it.
+// TMA_OUT: fp32 logits leave as TMA tensor stores of staged tiles (tmap_out over [units][N][HW]).
+// Tile width: 128 pixels (two TMA boxes, MMA N = 128) when only the sign bits are emitted -- half as many MMA
+// issues per pixel, which is what bounds that variant -- and 64 pixels with the logits staging tiles.
 template <bool TMA_OUT>
 __global__ void __launch_bounds__(E_THREADS, 1)
 einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_out,
               const EinsumParams p) {
-    constexpr int STAGES = TMA_OUT ? E_STAGES_TMA : E_STAGES;
+    constexpr int TILE = TMA_OUT ? 64 : 128;                         // pixels per tile = MMA N = accumulator columns
+    constexpr int NBOX = TILE / E_BHW;
+    constexpr int STAGE_BYTES = NBOX * E_B_BYTES;
+    constexpr int STAGES = TMA_OUT ? E_STAGES_TMA : E_STAGES / NBOX;
+    constexpr int NACC = (2 * E_ACC * E_BHW) / TILE;                 // accumulator buffers in 256 TMEM columns
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
@@ -74,19 +80,19 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     uint64_t* full = bars;
     uint64_t* empty = bars + E_STAGES;
     uint64_t* tfull = bars + 2 * E_STAGES;
-    uint64_t* tempty = bars + 2 * E_STAGES + E_ACC;
-    uint64_t* abar = bars + 2 * E_STAGES + 2 * E_ACC;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * E_STAGES + 2 * E_ACC + 1);
+    uint64_t* tempty = bars + 2 * E_STAGES + 4;
+    uint64_t* abar = bars + 2 * E_STAGES + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * E_STAGES + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int unit = p.unit0 + blockIdx.x / p.ctas_per_unit;
     const int j = blockIdx.x % p.ctas_per_unit;
-    const int tile_begin = (int)((long long)j * p.tiles_per_unit / p.ctas_per_unit);
-    const int tile_end = (int)((long long)(j + 1) * p.tiles_per_unit / p.ctas_per_unit);
+    const int tiles_per_unit = (p.HW + TILE - 1) / TILE;
+    const int tile_begin = (int)((long long)j * tiles_per_unit / p.ctas_per_unit);
+    const int tile_end = (int)((long long)(j + 1) * tiles_per_unit / p.ctas_per_unit);
     const int ntiles = tile_end - tile_begin;
     const int gunit = (unit / p.B) * p.Btot + p.b0 + unit % p.B;   // unit inside the full-batch feature / logits tensors
     long long* dbg = dbg_claim_all(TMA_OUT ? 21 : 20);
-    __shared__ long long s_dbg2[8];
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_feats);
@@ -96,7 +102,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
-        for (int i = 0; i < E_ACC; ++i) {
+        for (int i = 0; i < NACC; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 4);
         }
@@ -107,7 +113,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // warp-uniform (REDUX -> uniform register): tcgen05 operands need no per-instruction R2UR
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // warp-uniform (REDUX -> uniform register)
     DBG(1);
     pdl_launch_dependents();
 
@@ -118,42 +124,37 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             // dependency resolves
             if (!p.early_feats) pdl_wait();
             const uint64_t fhint = unit < p.B ? kEvictLast : kEvictFirst;   // x_feats stays L2-resident across kernels
-            const int pre = ntiles < STAGES ? ntiles : STAGES;
-            for (int i = 0; i < pre; ++i) {
-                mbar_arrive_expect_tx(&full[i], E_B_BYTES);
-                tma_load_2d(sB + i * E_B_BYTES, &tmap_feats, &full[i], (tile_begin + i) * E_BHW, gunit * E_C, fhint);
-            }
-            for (int i = pre; i < ntiles; ++i) {
+            for (int i = 0; i < ntiles; ++i) {
                 const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                if (i == 3) DBG(2);
+                if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
                 if (i == ntiles - 1) DBG(3);
-                mbar_arrive_expect_tx(&full[s], E_B_BYTES);
-                tma_load_2d(sB + s * E_B_BYTES, &tmap_feats, &full[s], (tile_begin + i) * E_BHW, gunit * E_C, fhint);
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)   // a box that starts beyond HW is zero-filled by the TMA unit
+                    tma_load_2d(sB + s * STAGE_BYTES + bx * E_B_BYTES, &tmap_feats, &full[s],
+                                (tile_begin + i) * TILE + bx * E_BHW, gunit * E_C, fhint);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
-        constexpr uint32_t idesc = make_idesc_bf16(128, E_BHW, /*a_mn=*/0, /*b_mn=*/1);
+        constexpr uint32_t idesc = make_idesc_bf16(128, TILE, /*a_mn=*/0, /*b_mn=*/1);
         const uint32_t a_hi = tmem_base + E_TMEM_A, a_lo = a_hi + 128;
         mbar_wait(abar, 0);
         tc_fence_after();
         for (int i = 0; i < ntiles; ++i) {
-            const int s = i % STAGES, a = i % E_ACC;
-            mbar_wait(&tempty[a], ((i / E_ACC) & 1) ^ 1);
-            if (blockIdx.x == 0 && g_dbg && lane == 0 && i >= 4 && i < 8) s_dbg2[2 * (i - 4)] = gtime();
+            const int s = i % STAGES, a = i % NACC;
+            mbar_wait(&tempty[a], ((i / NACC) & 1) ^ 1);
             mbar_wait(&full[s], (i / STAGES) & 1);
-            if (blockIdx.x == 0 && g_dbg && lane == 0 && i >= 4 && i < 8) s_dbg2[2 * (i - 4) + 1] = gtime();
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + a * (2 * E_BHW);
-            // B (MN-major): 16 K-rows of 128 bytes per K step -> the start-address field advances by 2048 >> 4
-            const uint64_t db0 = make_smem_desc_sw128(smem_u32(sB + s * E_B_BYTES), 32768, 1024);
+            const uint32_t d_tmem = tmem_base + a * TILE;
+            // B (MN-major): 16 K-rows of 128 bytes per K step -> the start-address field advances by 2048 >> 4;
+            // successive 64-pixel chunks of N are one box (32 KB) apart (leading byte offset)
+            const uint64_t db0 = make_smem_desc_sw128(smem_u32(sB + s * STAGE_BYTES), E_B_BYTES, 1024);
 #pragma unroll
             for (int kb = 0; kb < E_C / 16; ++kb) {
-                // A (tensor memory): 16 K values = 8 columns per step
+                // A (tensor memory): 16 K values = 8 columns per step; hi and lo planes into the same accumulator
                 umma_bf16_ts_warp(d_tmem, a_hi + kb * 8, db0 + (uint64_t)(kb * 128), idesc, kb > 0);
-                umma_bf16_ts_warp(d_tmem + E_BHW, a_lo + kb * 8, db0 + (uint64_t)(kb * 128), idesc, kb > 0);
+                umma_bf16_ts_warp(d_tmem, a_lo + kb * 8, db0 + (uint64_t)(kb * 128), idesc, 1);
             }
             umma_commit_warp(&empty[s]);
             umma_commit_warp(&tfull[a]);
@@ -172,9 +173,9 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t v[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint4 t = row_ok ? __ldg(src + c0 / 4 + j) : make_uint4(0u, 0u, 0u, 0u);
-                        v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const uint4 t = row_ok ? __ldg(src + c0 / 4 + jj) : make_uint4(0u, 0u, 0u, 0u);
+                        v[4 * jj] = t.x, v[4 * jj + 1] = t.y, v[4 * jj + 2] = t.z, v[4 * jj + 3] = t.w;
                     }
                     tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + E_TMEM_A + h * 128 + c0, v);
                 }
@@ -188,33 +189,23 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
         const bool vec_ok = (p.HW & 3) == 0;
         uint32_t* brow = (p.bits && unit < p.B) ? p.bits + (size_t)unit * p.words * 128 + n : nullptr;
         for (int i = 0; i < ntiles; ++i) {
-            const int a = i % E_ACC;
-            mbar_wait(&tfull[a], (i / E_ACC) & 1);
+            const int a = i % NACC;
+            mbar_wait(&tfull[a], (i / NACC) & 1);
             tc_fence_after();
-            uint32_t v0[32], v1[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * (2 * E_BHW);
-            {
-                uint32_t w0[32], w1[32];
-                tmem_ld32(taddr, v0);
-                tmem_ld32(taddr + 32, v1);
-                tmem_ld32(taddr + E_BHW, w0);
-                tmem_ld32(taddr + E_BHW + 32, w1);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * TILE;
+            const int hw0 = (tile_begin + i) * TILE;
+#pragma unroll
+            for (int h = 0; h < TILE / 32; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
                 tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {   // hi chain + lo chain
-                    v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(w0[c]));
-                    v1[c] = __float_as_uint(__uint_as_float(v1[c]) + __uint_as_float(w1[c]));
+                if (h == TILE / 32 - 1) {   // the accumulator buffer is free once its last chunk is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[a]);
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
-            const int hw0 = (tile_begin + i) * E_BHW;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t(&v)[32] = h ? v1 : v0;
                 const int hwb = hw0 + h * 32;
-                if (hwb >= p.HW) break;
+                if (hwb >= p.HW) continue;
                 uint32_t word = 0;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -261,7 +252,6 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read<0>();   // shared memory must outlive the last store's read
     tc_fence_before();
     __syncthreads();
-    if (dbg) for (int k = 0; k < 8; ++k) dbg[4 + k] = s_dbg2[k];
     DBG(13);
     if (warp == 1) tmem_dealloc<E_TMEM_COLS>(tmem_base);
 }
@@ -331,14 +321,15 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
     p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats, p.unit0 = branch0 * B;
-    p.tiles_per_unit = (HW + E_BHW - 1) / E_BHW;
+    // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
+    const bool tma_out = logits && (HW % 4) == 0;
+    const int tile = tma_out ? 64 : 128;   // must match einsum_kernel<TMA_OUT>::TILE
+    p.tiles_per_unit = (HW + tile - 1) / tile;
     int cpu = num_sms() / n_units;
     if (cpu < 1) cpu = 1;
     if (cpu > p.tiles_per_unit) cpu = p.tiles_per_unit;
     p.ctas_per_unit = cpu;
 
-    // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
-    const bool tma_out = logits && (HW % 4) == 0;
     CUtensorMap tmap_o = tmap;
     if (tma_out)
         if (int e = make_tmap_f32_3d(&tmap_o, logits, (uint64_t)(branch0 + n_units / B) * Btot, (uint64_t)N, (uint64_t)HW, 128, 32)) return e;
