@@ -54,7 +54,8 @@ enum { SLOT_POOLED = 0, SLOT_INP, SLOT_GATEIN, SLOT_MIX, SLOT_OBJ0, SLOT_ATT, SL
        SLOT_OBJ2 = SLOT_HID0 + 8, SLOT_HEAD0, SLOT_HEAD1, NSLOT };
 constexpr size_t SLOT_ELEMS = 2 * 128 * 256;    // bf16 elements per slot (hi + lo)
 
-enum { MODE_GENERIC = 0, MODE_DUAL = 1, MODE_GATE = 2 };
+enum { MODE_GENERIC = 0, MODE_DUAL = 1, MODE_GATE = 2, MODE_GENERIC64 = 3 };   // GENERIC64: 64-column tiles
+constexpr int T_SLD64 = 68;                     // floats per row of the 64-column staging tile
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
 struct TcPass {
@@ -240,7 +241,8 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         dbg = s_dbg;
     }
     const TcJob& g = args.job[blockIdx.z];
-    const int tile = blockIdx.x, nb = tile * T_TN;
+    constexpr int TN = MODE == MODE_GENERIC64 ? 64 : T_TN;   // output columns of this CTA
+    const int tile = blockIdx.x, nb = tile * TN;
     const int b = blockIdx.y / args.ksplit, split = blockIdx.y % args.ksplit;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool active = tile < g.ntiles;   // uniform per cluster (ntiles is a multiple of the cluster size)
@@ -278,7 +280,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         const int which = warp - 2;
         const float* src = nullptr;
         int off = nb;   // column offset inside the source vector
-        if (MODE == MODE_GENERIC) {
+        if (MODE == MODE_GENERIC || MODE == MODE_GENERIC64) {
             const float* ln = nb < 256 ? g.ln0 : g.ln1;
             if (which == V_BIAS0) src = g.bias0;
             else if (which == V_GA0 && ln) src = ln, off = nb & 255;
@@ -335,7 +337,15 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     float cnt = 0.f;                    // DUAL: mask pixel count of this thread's row (phase-1 mapping)
     if (active && warp >= 2) {
         const int ew_ = warp - 2;
-        if (MODE == MODE_GENERIC) {
+        if (MODE == MODE_GENERIC64) {
+            if (g.res) {   // half-warp per row: lane & 15 -> 4 columns, lane >> 4 -> row parity
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int rr = ew_ + 16 * (2 * t + (lane >> 4));
+                    pref[t] = rr < N ? ld4(g.res + ((size_t)b * N + rr) * g.ldr + nb + (lane & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else if (MODE == MODE_GENERIC) {
             if (g.res && args.ksplit == 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -367,7 +377,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     } else if (active && warp == 1) {
         // ================= MMA issuer: D = Al*Wh + Ah*Wl + Ah*Wh =================
         // the whole warp runs the loop with warp-uniform operands, one lane elected inside the PTX block issues
-        constexpr uint32_t idesc = make_idesc_bf16(128, T_TN, 0, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(128, TN, 0, 0);   // TN = 64: the first 64 rows of the weight box
         for (int it = 0; it < total_it; ++it) {
             const int s = it % T_NSTG, kb = it & 3;
             mbar_wait(&full[s], (it / T_NSTG) & 1);
@@ -405,6 +415,115 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     const int cl = lane * 4;            // phase 2: column inside the tile
     const int col = nb + cl;            //          output column
     const int cg = col & 255;           //          column inside the 256-wide group
+    if (MODE == MODE_GENERIC64) {
+        // ---- 64-column tile: thread = (row, 16-column piece) in phase 1; half-warp per row in phase 2; LayerNorm
+        //      groups of 256 columns span the 4 CTAs of the cluster (16 pieces of 16 columns).
+        float2 (*box16)[128] = reinterpret_cast<float2(*)[128]>(smem + T_MAIL_OFF);   // [16 pieces][128 rows]
+        const int hl = lane >> 4, c4 = (lane & 15) * 4;
+        if (epi) {
+            mbar_wait(accfull, 0);
+            tc_fence_after();
+            epi_bar();
+            if (threadIdx.x == 64) DBG(8);
+            const int q = warp & 3, pc = ew >> 2;
+            const int r = q * 32 + lane;
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)pc * 16, v);
+            tmem_ld_wait();
+            float y[16];
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(vec + V_BIAS0 * 128 + pc * 16 + c);
+                y[c] = __uint_as_float(v[c]) + t.x, y[c + 1] = __uint_as_float(v[c + 1]) + t.y;
+                y[c + 2] = __uint_as_float(v[c + 2]) + t.z, y[c + 3] = __uint_as_float(v[c + 3]) + t.w;
+            }
+            auto stats_publish = [&]() {
+                float sm = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) sm += y[c];
+                const float mu = sm * (1.f / 16.f);
+                float m2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) m2 += (y[c] - mu) * (y[c] - mu);
+                for (int k = 0; k < 4; ++k) st_cluster_f32x2(&box16[(int)crank * 4 + pc][r], (uint32_t)k, mu, m2);
+            };
+            if (has_ln && !g.res) stats_publish();
+            float* d0 = S0 + r * T_SLD64 + pc * 16;
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(d0 + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+            epi_bar();
+            if (g.res) {   // residual: coalesced add into the tile, then the statistics of the finished rows
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float4* p4 = reinterpret_cast<float4*>(S0 + (ew + 16 * (2 * t + hl)) * T_SLD64 + c4);
+                    *p4 = add4(*p4, pref[t]);
+                }
+                epi_bar();
+                if (has_ln) {
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(d0 + c);
+                        y[c] = t.x, y[c + 1] = t.y, y[c + 2] = t.z, y[c + 3] = t.w;
+                    }
+                    stats_publish();
+                }
+            }
+            if (threadIdx.x == 64) DBG(9);
+        }
+        if (has_ln) {
+            cluster_arrive();
+            cluster_wait();
+        }
+        if (threadIdx.x == 64) DBG(11);
+        float pm = 0.f, pr = 1.f;
+        if (epi && has_ln && lane < 8) {   // (mean, rstd) of row ew + 16 * lane: merge of the 16 pieces (Chan et al.)
+            const int rr = ew + 16 * lane;
+            float2 pcs[16];
+            float sm = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) pcs[k] = box16[k][rr], sm += pcs[k].x;
+            pm = sm * (1.f / 16.f);
+            float m2 = 0.f, dv = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m2 += pcs[k].y, dv += (pcs[k].x - pm) * (pcs[k].x - pm);
+            pr = rsqrtf((m2 + 16.f * dv) * (1.f / 256.f) + U_LN_EPS);
+        }
+        if (threadIdx.x == 64) DBG(10);
+        if (epi) {
+            const int col64 = nb + c4, cg64 = col64 & 255;
+            const int act = nb < 256 ? g.act0 : g.act1;
+            const float4 ga = *reinterpret_cast<const float4*>(vec + V_GA0 * 128 + c4);
+            const float4 be = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + c4);
+            const int ldy = g.ldy, nstore = g.nstore, xrows = g.xrows;
+            const bool vecst = (ldy & 3) == 0 && col64 + 4 <= nstore;
+            float* Yb = g.Y ? g.Y + ((size_t)b * N) * ldy + col64 : nullptr;
+            uint16_t* Pb = g.p_slot >= 0 ? arena_row(args.arena, unit, g.p_slot + (nb >> 8), 0, 0) + cg64 : nullptr;
+            uint16_t* Xb = g.xplanes ? g.xplanes + (((size_t)(g.xunit0 + b) * 2) * xrows) * 256 + col64 : nullptr;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = 2 * t + hl;
+                const int rr = ew + 16 * i;
+                const bool rok = rr < N;
+                float4 v = *reinterpret_cast<const float4*>(S0 + rr * T_SLD64 + c4);
+                const float mean = __shfl_sync(0xffffffffu, pm, i), rstd = __shfl_sync(0xffffffffu, pr, i);
+                if (has_ln) v = ln4(v, mean, rstd, ga, be);
+                v = act4(v, act);
+                if (Yb && rok) {
+                    float* dst = Yb + (size_t)rr * ldy;
+                    if (vecst) {
+                        *reinterpret_cast<float4*>(dst) = v;
+                    } else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (col64 + j < nstore) dst[j] = e[j];
+                    }
+                }
+                if (Pb) store_planes4(rok ? v : make_float4(0.f, 0.f, 0.f, 0.f), Pb + rr * 256, Pb + (128 + rr) * 256);
+                if (Xb && rr < xrows) store_planes4(v, Xb + (size_t)rr * 256, Xb + ((size_t)xrows + rr) * 256);
+            }
+        }
+    } else {
     if (epi) {
         mbar_wait(accfull, 0);
         tc_fence_after();
@@ -566,6 +685,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             }
         }
     }
+    }   // MODE != MODE_GENERIC64
     if (threadIdx.x == 64) DBG(12);
     tc_fence_before();
     __syncthreads();
@@ -989,13 +1109,13 @@ static int run_updator(const Maps& mp, const pf_stage_weights* w, uint16_t* aren
     for (int b = 0; b < nbr; ++b) {
         const pf_branch_weights& bw = w->br[b];
         TcJob g = blank_job();
-        g.unit0 = b * B, g.ntiles = 2;
+        g.unit0 = b * B, g.ntiles = 4;
         g.pass[0] = TcPass{SLOT_MIX, 0, bw.fc_w, 256, 0};
         g.bias0 = bw.fc_b, g.ln0 = bw.ln_fc_norm, g.act0 = ACT_RELU;
         g.Y = out[b], g.ldy = 256, g.nstore = 256, g.p_slot = out_slot;
         a.job[b] = g;
     }
-    return launch_tc<MODE_GENERIC>(mp, a, 2, nbr, 2, st);
+    return launch_tc<MODE_GENERIC64>(mp, a, 4, nbr, 4, st);
 }
 
 }  // namespace pf
@@ -1079,12 +1199,12 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
         TcJob g = blank_job();
-        g.unit0 = b * B, g.ntiles = 6;
+        g.unit0 = b * B, g.ntiles = 12;
         g.pass[0] = TcPass{SLOT_OBJ0, 0, bw.qkv_w, 768, 0};
         g.bias0 = bw.qkv_b, g.Y = sc[b].qkv, g.ldy = 768, g.nstore = 768;
         a.job[b] = g;
     }
-    if (int e = launch_tc<MODE_GENERIC>(mp, a, 6, 2, 1, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC64>(mp, a, 12, 2, 1, st)) return e;
 
     // 5. softmax(q k^T) v per (branch, image, head) -> SLOT_ATT
     if (int e = launch_attention(sc[0].qkv, sc[1].qkv, arena, B, N, 2, st)) return e;
@@ -1093,13 +1213,13 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
         TcJob g = blank_job();
-        g.unit0 = b * B, g.ntiles = 2;
+        g.unit0 = b * B, g.ntiles = 4;
         g.pass[0] = TcPass{SLOT_ATT, 0, bw.out_w, 256, 0};
         g.bias0 = bw.out_b, g.res = sc[b].obj0, g.ldr = 256, g.ln0 = bw.ln_attn;
         g.Y = sc[b].obj1, g.ldy = 256, g.nstore = 256, g.p_slot = SLOT_OBJ1;
         a.job[b] = g;
     }
-    if (int e = launch_tc<MODE_GENERIC>(mp, a, 2, 2, 2, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC64>(mp, a, 4, 2, 4, st)) return e;
 
     // 7. FFN layer 1 + ReLU -> SLOT_HID0..7 (one slot per 256 hidden channels)
     for (int b = 0; b < 2; ++b) {
@@ -1141,14 +1261,14 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
         TcJob g = blank_job();
-        g.unit0 = b * B, g.ntiles = (b == 0) ? 4 : 2;
+        g.unit0 = b * B, g.ntiles = (b == 0) ? 8 : 4;
         g.pass[0] = TcPass{SLOT_OBJ2, 0, bw.head_w, (b == 0) ? 512 : 256, 0};
         g.ln0 = bw.ln_head_a, g.ln1 = bw.ln_head_b;
         g.act0 = g.act1 = bw.head_relu ? ACT_RELU : ACT_NONE;
         g.p_slot = (b == 0) ? SLOT_HEAD0 : SLOT_HEAD1;
         a.job[b] = g;
     }
-    if (int e = launch_tc<MODE_GENERIC>(mp, a, 4, 2, 2, st)) return e;
+    if (int e = launch_tc<MODE_GENERIC64>(mp, a, 8, 2, 4, st)) return e;
 
     // 11. fc_mask / fc_depth with feat_transform folded in -> dynamic kernels (bf16 hi/lo planes) + their logit bias
     //     (one extra weight row), fc_cls
@@ -1156,7 +1276,7 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
     for (int b = 0; b < 2; ++b) {
         const pf_branch_weights& bw = w->br[b];
         TcJob g = blank_job();
-        g.unit0 = b * B, g.ntiles = 2;
+        g.unit0 = b * B, g.ntiles = 4;
         g.pass[0] = TcPass{SLOT_HEAD1, 0, bw.kern_w, 256, 0};
         g.bias0 = bw.kern_b;
         g.Y = kern ? kern + (size_t)b * R * 256 : nullptr, g.ldy = 256, g.nstore = 256;
@@ -1178,7 +1298,7 @@ extern "C" int pf_kernel_update(const pf_stage_weights* w, const float* partial,
         g.Y = cls_out, g.ldy = w->num_classes, g.nstore = w->num_classes;
         a.job[nj++] = g;
     }
-    return launch_tc<MODE_GENERIC>(mp, a, 2, nj, 1, st);
+    return launch_tc<MODE_GENERIC64>(mp, a, 4, nj, 1, st);
 }
 
 extern "C" size_t pf_updator_workspace_bytes(int R) {
