@@ -42,7 +42,7 @@ constexpr int T_PLANE = 128 * T_KC * 2;         // 16384: one [128][64] bf16 box
 constexpr int T_STAGE = 4 * T_PLANE;            // A hi | A lo | W hi | W lo
 constexpr int T_BAR_OFF = T_NSTG * T_STAGE;     // 196608
 constexpr int T_MAIL_OFF = T_BAR_OFF + 256;
-constexpr int T_MAIL_BYTES = 2 * 8 * 128 * 8;   // [array][source][row] x (mean, M2)
+constexpr int T_MAIL_BYTES = 2 * 128 * 9 * 8;   // [array][row][piece, pitch 9] x (mean, M2); also [128][17] for 64-column tiles
 constexpr int T_VEC_OFF = T_MAIL_OFF + T_MAIL_BYTES;   // per-column parameter vectors of this tile: 8 x [128] floats
 enum { V_BIAS0 = 0, V_CBIAS0, V_BIAS1, V_GA0, V_BE0, V_GA1, V_BE1, V_COUNT };
 constexpr int T_SMEM_USED = T_VEC_OFF + V_COUNT * 128 * 4;
@@ -198,14 +198,14 @@ __device__ __forceinline__ uint16_t* arena_row(uint16_t* arena, int unit, int sl
 // (DSMEM stores); after one cluster barrier each CTA merges the pieces (Chan et al.), which is as stable as a
 // two-pass LayerNorm.
 struct Mail {
-    float2 (*box)[8][128];
+    float2 (*box)[128][9];   // row pitch 9: the rows a warp publishes / merges fall into different banks
     __device__ __forceinline__ void publish(int arr, int src, int r, float mean, float m2, int csize) const {
-        for (int k = 0; k < csize; ++k) st_cluster_f32x2(&box[arr][src][r], (uint32_t)k, mean, m2);
+        for (int k = 0; k < csize; ++k) st_cluster_f32x2(&box[arr][r][src], (uint32_t)k, mean, m2);
     }
     __device__ __forceinline__ void combine(int arr, int r, float& mean, float& rstd) const {
         float2 p[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) p[k] = box[arr][k][r];
+        for (int k = 0; k < 8; ++k) p[k] = box[arr][r][k];
         mean = (((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x))) * 0.125f;
         float m2 = 0.f, dv = 0.f;
 #pragma unroll
@@ -225,7 +225,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     uint64_t* empty = bars + T_NSTG;
     uint64_t* accfull = bars + 2 * T_NSTG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T_NSTG + 1);
-    Mail mail{reinterpret_cast<float2(*)[8][128]>(smem + T_MAIL_OFF)};
+    Mail mail{reinterpret_cast<float2(*)[128][9]>(smem + T_MAIL_OFF)};
     if (smem + T_SMEM_USED > smem_raw + T_SMEM) __trap();   // dynamic smem base less aligned than assumed
 
     long long* dbg = nullptr;
@@ -341,7 +341,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             if (g.res) {   // half-warp per row: lane & 15 -> 4 columns, lane >> 4 -> row parity
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const int rr = ew_ + 16 * (2 * t + (lane >> 4));
+                    const int rr = ew_ * 8 + 2 * t + (lane >> 4);
                     pref[t] = rr < N ? ld4(g.res + ((size_t)b * N + rr) * g.ldr + nb + (lane & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -349,7 +349,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             if (g.res && args.ksplit == 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int rr = ew_ + 16 * i;
+                    const int rr = ew_ * 8 + i;
                     pref[i] = rr < N ? ld4(g.res + ((size_t)b * N + rr) * g.ldr + nb + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -357,7 +357,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             const float* mul = ((lane >> 4) ? g.mul1 : g.mul0) + tile * 64 + (lane & 15) * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rr = ew_ + 16 * i;
+                const int rr = ew_ * 8 + i;
                 pref[i] = rr < N ? ld4(mul + ((size_t)b * N + rr) * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
@@ -418,7 +418,9 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     if (MODE == MODE_GENERIC64) {
         // ---- 64-column tile: thread = (row, 16-column piece) in phase 1; half-warp per row in phase 2; LayerNorm
         //      groups of 256 columns span the 4 CTAs of the cluster (16 pieces of 16 columns).
-        float2 (*box16)[128] = reinterpret_cast<float2(*)[128]>(smem + T_MAIL_OFF);   // [16 pieces][128 rows]
+        // mailbox [128 rows][16 pieces] with a row pitch of 17 float2: the 8 consecutive rows a warp merges (and the 32
+        // consecutive rows a warp publishes) fall into different banks
+        float2 (*box16)[17] = reinterpret_cast<float2(*)[17]>(smem + T_MAIL_OFF);
         const int hl = lane >> 4, c4 = (lane & 15) * 4;
         if (epi) {
             mbar_wait(accfull, 0);
@@ -445,7 +447,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
                 float m2 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) m2 += (y[c] - mu) * (y[c] - mu);
-                for (int k = 0; k < 4; ++k) st_cluster_f32x2(&box16[(int)crank * 4 + pc][r], (uint32_t)k, mu, m2);
+                for (int k = 0; k < 4; ++k) st_cluster_f32x2(&box16[r][(int)crank * 4 + pc], (uint32_t)k, mu, m2);
             };
             if (has_ln && !g.res) stats_publish();
             float* d0 = S0 + r * T_SLD64 + pc * 16;
@@ -455,7 +457,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             if (g.res) {   // residual: coalesced add into the tile, then the statistics of the finished rows
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    float4* p4 = reinterpret_cast<float4*>(S0 + (ew + 16 * (2 * t + hl)) * T_SLD64 + c4);
+                    float4* p4 = reinterpret_cast<float4*>(S0 + (ew * 8 + 2 * t + hl) * T_SLD64 + c4);
                     *p4 = add4(*p4, pref[t]);
                 }
                 epi_bar();
@@ -476,12 +478,12 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
         }
         if (threadIdx.x == 64) DBG(11);
         float pm = 0.f, pr = 1.f;
-        if (epi && has_ln && lane < 8) {   // (mean, rstd) of row ew + 16 * lane: merge of the 16 pieces (Chan et al.)
-            const int rr = ew + 16 * lane;
+        if (epi && has_ln && lane < 8) {   // (mean, rstd) of row 8 ew + lane: merge of the 16 pieces (Chan et al.)
+            const int rr = ew * 8 + lane;
             float2 pcs[16];
             float sm = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) pcs[k] = box16[k][rr], sm += pcs[k].x;
+            for (int k = 0; k < 16; ++k) pcs[k] = box16[rr][k], sm += pcs[k].x;
             pm = sm * (1.f / 16.f);
             float m2 = 0.f, dv = 0.f;
 #pragma unroll
@@ -502,7 +504,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int i = 2 * t + hl;
-                const int rr = ew + 16 * i;
+                const int rr = ew * 8 + i;
                 const bool rok = rr < N;
                 float4 v = *reinterpret_cast<const float4*>(S0 + rr * T_SLD64 + c4);
                 const float mean = __shfl_sync(0xffffffffu, pm, i), rstd = __shfl_sync(0xffffffffu, pr, i);
@@ -549,7 +551,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             if (res) {   // residual: coalesced add into the tile, then the statistics of the finished rows
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float4* p4 = reinterpret_cast<float4*>(S0 + (ew + 16 * i) * T_SLD + cl);
+                    float4* p4 = reinterpret_cast<float4*>(S0 + (ew * 8 + i) * T_SLD + cl);
                     *p4 = add4(*p4, pref[i]);
                 }
                 epi_bar();
@@ -595,7 +597,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
     if (threadIdx.x == 64) DBG(11);
     // LayerNorm (mean, rstd) of this warp's 8 rows, one row per lane (lanes 8..15: the second array)
     float pm = 0.f, pr = 1.f;
-    if (epi && has_ln && lane < (MODE == MODE_GENERIC ? 8 : 16)) mail.combine((lane >> 3) & 1, ew + 16 * (lane & 7), pm, pr);
+    if (epi && has_ln && lane < (MODE == MODE_GENERIC ? 8 : 16)) mail.combine((lane >> 3) & 1, ew * 8 + (lane & 7), pm, pr);
     if (threadIdx.x == 64) DBG(10);
 
     if (MODE == MODE_GENERIC) {
@@ -605,20 +607,20 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             const float4 be = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + cl);
             const int ldy = g.ldy, nstore = g.nstore, xrows = g.xrows;
             const bool vec = (ldy & 3) == 0 && col + 4 <= nstore;
-            float* yp = g.Y ? g.Y + ((size_t)split * args.R + (size_t)b * N + ew) * ldy + col : nullptr;
-            uint16_t* pp = g.p_slot >= 0 ? arena_row(args.arena, unit, g.p_slot + (nb >> 8), 0, ew) + cg : nullptr;
-            uint16_t* xp = g.xplanes ? g.xplanes + (((size_t)(g.xunit0 + b) * 2) * xrows + ew) * 256 + col : nullptr;
-            const float* sp = S0 + ew * T_SLD + cl;
+            float* yp = g.Y ? g.Y + ((size_t)split * args.R + (size_t)b * N + ew * 8) * ldy + col : nullptr;
+            uint16_t* pp = g.p_slot >= 0 ? arena_row(args.arena, unit, g.p_slot + (nb >> 8), 0, ew * 8) + cg : nullptr;
+            uint16_t* xp = g.xplanes ? g.xplanes + (((size_t)(g.xunit0 + b) * 2) * xrows + ew * 8) * 256 + col : nullptr;
+            const float* sp = S0 + ew * 8 * T_SLD + cl;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rr = ew + 16 * i;
+                const int rr = ew * 8 + i;
                 const bool rok = rr < N;
-                float4 v = *reinterpret_cast<const float4*>(sp + i * 16 * T_SLD);
+                float4 v = *reinterpret_cast<const float4*>(sp + i * T_SLD);
                 const float mean = __shfl_sync(0xffffffffu, pm, i), rstd = __shfl_sync(0xffffffffu, pr, i);
                 if (has_ln) v = ln4(v, mean, rstd, ga, be);
                 v = act4(v, act);
                 if (yp && rok) {
-                    float* dst = yp + (size_t)i * 16 * ldy;
+                    float* dst = yp + (size_t)i * ldy;
                     if (vec) {
                         *reinterpret_cast<float4*>(dst) = v;
                     } else {
@@ -628,18 +630,18 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
                             if (col + j < nstore) dst[j] = e[j];
                     }
                 }
-                if (pp) store_planes4(rok ? v : make_float4(0.f, 0.f, 0.f, 0.f), pp + i * 16 * 256, pp + (128 + i * 16) * 256);
-                if (xp && rr < xrows) store_planes4(v, xp + i * 16 * 256, xp + ((size_t)xrows + i * 16) * 256);
+                if (pp) store_planes4(rok ? v : make_float4(0.f, 0.f, 0.f, 0.f), pp + i * 256, pp + (128 + i) * 256);
+                if (xp && rr < xrows) store_planes4(v, xp + i * 256, xp + ((size_t)xrows + i) * 256);
             }
         }
     } else if (MODE == MODE_DUAL) {
         if (epi && !has_ln) {
-            uint16_t* pp = arena_row(args.arena, unit, g.p_slot, 0, ew) + col;
+            uint16_t* pp = arena_row(args.arena, unit, g.p_slot, 0, ew * 8) + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rr = ew + 16 * i;
+                const int rr = ew * 8 + i;
                 const float4 v = rr < N ? *reinterpret_cast<float4*>(S0 + rr * T_SLD + cl) : make_float4(0.f, 0.f, 0.f, 0.f);
-                store_planes4(v, pp + i * 16 * 256, pp + (128 + i * 16) * 256);
+                store_planes4(v, pp + i * 256, pp + (128 + i) * 256);
             }
         } else if (epi) {   // param_out = norm_out(.), input_out = input_norm_out(.)   (:78-79)
             const int c2 = col - 256;
@@ -647,17 +649,17 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             const float4 be0 = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + cl);
             const float4 ga1 = *reinterpret_cast<const float4*>(vec + V_GA1 * 128 + cl);
             const float4 be1 = *reinterpret_cast<const float4*>(vec + V_BE1 * 128 + cl);
-            float* y0 = g.Y + ((size_t)b * N + ew) * 256 + c2;
-            float* y1 = g.Y1 + ((size_t)b * N + ew) * 256 + c2;
+            float* y0 = g.Y + ((size_t)b * N + ew * 8) * 256 + c2;
+            float* y1 = g.Y1 + ((size_t)b * N + ew * 8) * 256 + c2;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rr = ew + 16 * i;
+                const int rr = ew * 8 + i;
                 const float mean0 = __shfl_sync(0xffffffffu, pm, i), rstd0 = __shfl_sync(0xffffffffu, pr, i);
                 const float mean1 = __shfl_sync(0xffffffffu, pm, i + 8), rstd1 = __shfl_sync(0xffffffffu, pr, i + 8);
                 if (rr < N) {
-                    *reinterpret_cast<float4*>(y0 + i * 16 * 256) =
+                    *reinterpret_cast<float4*>(y0 + i * 256) =
                         ln4(*reinterpret_cast<float4*>(S0 + rr * T_SLD + cl), mean0, rstd0, ga0, be0);
-                    *reinterpret_cast<float4*>(y1 + i * 16 * 256) =
+                    *reinterpret_cast<float4*>(y1 + i * 256) =
                         ln4(*reinterpret_cast<float4*>(S1 + rr * T_SLD + cl), mean1, rstd1, ga1, be1);
                 }
             }
@@ -668,10 +670,10 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
             const int f = tile * 64 + (lane & 15) * 4;   // feature column of this lane
             const float4 ga = *reinterpret_cast<const float4*>(vec + V_GA0 * 128 + cl);
             const float4 be = *reinterpret_cast<const float4*>(vec + V_BE0 * 128 + cl);
-            uint16_t* pp = arena_row(args.arena, unit, g.p_slot, 0, ew) + f;
+            uint16_t* pp = arena_row(args.arena, unit, g.p_slot, 0, ew * 8) + f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rr = ew + 16 * i;
+                const int rr = ew * 8 + i;
                 const float mean = __shfl_sync(0xffffffffu, pm, i + 8 * half);
                 const float rstd = __shfl_sync(0xffffffffu, pr, i + 8 * half);
                 float4 v = ln4(*reinterpret_cast<float4*>(S0 + rr * T_SLD + cl), mean, rstd, ga, be);
@@ -681,7 +683,7 @@ tcgemm_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_consta
                 // features = update_gate * param_out + input_gate * input_out: lanes l and l + 16 hold the same feature
                 v.x += __shfl_xor_sync(0xffffffffu, v.x, 16), v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
                 v.z += __shfl_xor_sync(0xffffffffu, v.z, 16), v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
-                if (half == 0) store_planes4(v, pp + i * 16 * 256, pp + (128 + i * 16) * 256);
+                if (half == 0) store_planes4(v, pp + i * 256, pp + (128 + i) * 256);
             }
         }
     }
