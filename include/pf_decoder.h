@@ -222,6 +222,44 @@ int pf_panoptic(const float* cls_scores, const float* mask_logits, const float* 
                 float* depth_final, float* depth_basic, pf_segment* segments, int* n_segments, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* ---- the producer of the decoder's inputs -----------------------------------------
+ * The tail of KernelHead._decode_init_proposals (polyphonic/kernel_head.py:250-336) after SemanticFPN:
+ *   loc / sem / dep = ReLU(GroupNorm32(conv1x1(maps[0 / 1 / 2])))       kernel_head.py:250-251, 264-265, 277-278
+ *   mask_preds = init_kernels(loc)                                      :256      (rows 0 .. P-1 of head_w)
+ *   seg_preds = conv_seg(sem), depth_pred = conv_direct_depth(dep)      :295, :285 (rows 112 .., row 144 of head_w)
+ *   x_feats = sem + loc                                                 :303
+ *   mask_preds = cat(mask_preds, seg_preds[:, num_thing_classes:])      :329-331 (cat_stuff_mask, eval)
+ * pf_mask_pool(bits) + pf_init_proposals finish :313-336.  Static weights, packed once by the host:
+ *   conv_split  bf16 [6][2][128][256]: block (half * 3 + map) = rows [128 half, 128 half + 128) of that map's
+ *               {loc,seg,depth}_convs.0.conv.weight as hi / lo planes (hi = bf16(w), lo = bf16(w - hi))
+ *   gn_gamma / gn_beta  fp32 [3][256]: {loc,seg,depth}_convs.0.gn.{weight,bias};  gn_eps = 1e-5
+ *   head_w      bf16 [2][160][256] hi / lo planes: rows 0..111 init_kernels.weight (zero-padded), 112..143
+ *               conv_seg.weight, 144..159 conv_direct_depth.weight;  head_b fp32 [160] the matching biases */
+typedef struct pf_head_weights {
+    const uint16_t* conv_split;
+    const float* gn_gamma;
+    const float* gn_beta;
+    const uint16_t* head_w;
+    const float* head_b;
+    int num_proposals;      /* P = 100 */
+    int num_classes;        /* 19 */
+    int num_thing_classes;  /* 8 */
+    float gn_eps;
+} pf_head_weights;
+
+/* fp32 [rows][HW] -> bf16 [rows][HWp] (pad columns zero): the storage cast of the SemanticFPN maps */
+int pf_cast_maps(const float* maps, uint16_t* out, int rows, int HW, int HWp, void* stream);
+
+size_t pf_kernel_head_workspace_bytes(int B, int HW);
+/*   maps        bf16 [3][B][256][HWp]   localization_feats (loc, semantic, depth) in the storage dtype
+ *   feats       out bf16 [2][B][256][HWp]   x_feats, depth_feats: the layout pf_decoder_forward consumes
+ *   x32 / d32   optional fp32 [B][256][HW] copies of the same (may be NULL)
+ *   mask_preds  out [B][P + num_classes - num_thing_classes][HW];  seg_preds out [B][num_classes][HW];
+ *   depth_pred  out [B][HW];  bits optional out u32 [B][ceil(HW/32)][128]: sigmoid(mask_preds[:, :P]) > 0.5 (:314-317) */
+int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, uint16_t* feats, float* x32, float* d32,
+                   float* mask_preds, float* seg_preds, float* depth_pred, uint32_t* bits, void* workspace,
+                   size_t workspace_bytes, int B, int HW, int HWp, void* stream);
+
 /* debug only: int64 device buffer [16 + 16*capacity], zero-filled by the caller; CTA (0,0,0) of every GEMM launch of
  * the small-N block appends 16 %globaltimer samples (see scripts/k2_timeline.py).  NULL switches it off. */
 int pf_debug_timeline(long long* device_buffer);

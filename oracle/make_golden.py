@@ -115,6 +115,56 @@ def run_panoptic_case(head, h, w, img_hw, seed):
                 img_hw=np.array(img_hw))
 
 
+KERNEL_HEAD_CASES = [
+    # name, B, H, W: the seed is the one of 0..15 whose initial thing-mask logits stay furthest from 0 (the pooled
+    # proposal features only see sigmoid(logit) > 0.5, kernel_head.py:314-317; same reasoning as above)
+    ('kernel_head_b2_h16_w24', 2, 16, 24),
+    ('kernel_head_b1_h10_w13', 1, 10, 13),   # HW=130: ragged 128-pixel tile, HW % 4 != 0 (no TMA store path)
+]
+
+
+class _FixedFPN(torch.nn.Module):
+    def __init__(self, maps):
+        super().__init__()
+        self.maps = maps
+
+    def forward(self, img):
+        return list(self.maps)
+
+
+def build_reference_rpn_head():
+    shim.install()
+    import polyphonic  # noqa: F401
+    from mmdet.models.builder import build_head
+    cfg = shim.load_config('/root/reference/configs/polyphonic_image/poly_r50_cityscapes_2x.py')
+    rpn = cfg.model.rpn_head
+    rpn['train_cfg'] = None
+    rpn['test_cfg'] = cfg.model.test_cfg.rpn
+    head = build_head(rpn)
+    head.eval()
+    return head
+
+
+def run_kernel_head_case(head, B, H, W):
+    """kernel_head.py:240-347 -- the reference's own _decode_init_proposals with SemanticFPN replaced by fixed maps."""
+    best = None
+    for seed in range(16):
+        sd = synth.synth_kernel_head_state(seed)
+        r = head.load_state_dict(sd, strict=False)
+        assert not r.unexpected_keys and all(k.startswith('localization_fpn.') for k in r.missing_keys), r
+        maps = synth.synth_fpn_maps(B, H, W, seed)
+        head._modules['localization_fpn'] = _FixedFPN(maps)
+        with torch.no_grad():
+            out = head._decode_init_proposals(None, [None] * B)
+        names = ('proposal_feats', 'x_feats', 'mask_preds', 'cls_scores', 'seg_preds', 'depth_feats', 'depth_proposal',
+                 'depth_pred', 'semantic_aspp_out')
+        out = {k: v.numpy().astype(np.float32) for k, v in zip(names, out) if v is not None}
+        margin = float(np.abs(out['mask_preds'][:, :head.num_proposals]).min())
+        if best is None or margin > best[1]:
+            best = (seed, margin, out)
+    return best
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -130,6 +180,13 @@ def main():
         out = run_panoptic_case(head, h, w, img_hw, seed)
         np.savez_compressed(os.path.join(GOLD, name + '.npz'), h=h, w=w, seed=seed, **out)
         print(name, out['panoptic'].shape, 'segments', len(out['seg']), np.unique(out['panoptic']))
+    rpn = build_reference_rpn_head()
+    for name, B, H, W in KERNEL_HEAD_CASES:
+        seed, margin, out = run_kernel_head_case(rpn, B, H, W)
+        path = os.path.join(GOLD, name + '.npz')
+        np.savez_compressed(path, B=B, H=H, W=W, seed=seed, margin=np.float32(margin), **out)
+        print(name, 'seed', seed, 'margin', margin, {k: v.shape for k, v in out.items()},
+              f'{os.path.getsize(path) / 1e6:.2f} MB')
     u = run_updator_case(head)
     np.savez_compressed(os.path.join(GOLD, 'updator_r37_s0.npz'), **u)
     print('updator', u['out'].shape)

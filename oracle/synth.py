@@ -157,3 +157,34 @@ def synth_panoptic_inputs(h, w, seed=0, n_kernels=N_KERNELS):
     dinit = torch.nn.functional.interpolate(torch.randn(1, 1, max(h // 8, 1), max(w // 8, 1), generator=g), size=(h, w),
                                             mode='bilinear', align_corners=False)[0]
     return dict(cls_scores=cls, mask_preds=mask.contiguous(), depth_preds=depth.contiguous(), depth_init=dinit.contiguous())
+
+
+def kernel_head_state_shapes(num_proposals=N_PROPOSALS):
+    """name -> shape of the KernelHead parameters AFTER SemanticFPN (kernel_head.py:142-200)."""
+    s = {}
+    for m in ('loc', 'seg', 'depth'):
+        s[f'{m}_convs.0.conv.weight'] = (C, C, 1, 1)
+        s[f'{m}_convs.0.gn.weight'] = (C,)
+        s[f'{m}_convs.0.gn.bias'] = (C,)
+    s['init_kernels.weight'] = (num_proposals, C, 1, 1)
+    s['conv_seg.weight'] = (NUM_CLASSES, C, 1, 1)
+    s['conv_seg.bias'] = (NUM_CLASSES,)
+    s['conv_direct_depth.weight'] = (1, C, 1, 1)
+    s['conv_direct_depth.bias'] = (1,)
+    return s
+
+
+def synth_kernel_head_state(seed=0, num_proposals=N_PROPOSALS):
+    return {k: synth_tensor('kernel_head.' + k, shp, seed) for k, shp in kernel_head_state_shapes(num_proposals).items()}
+
+
+def synth_fpn_maps(B, H, W, seed=0):
+    """The three SemanticFPN outputs (localization, semantic, depth; each the ReLU output of a conv+GN stack,
+    semantic_fpn.py:221-229), pre-rounded to bf16 -- the storage dtype both sides consume."""
+    g = _gen(f'fpn.{B}.{H}.{W}', seed)
+    maps = []
+    for scale in (1.0, 0.8, 1.3):
+        coarse = torch.randn(B, C, max(H // 4, 1), max(W // 4, 1), generator=g)
+        t = torch.nn.functional.interpolate(coarse, size=(H, W), mode='bilinear', align_corners=False)
+        maps.append(bf16_round(torch.relu(scale * (t + 0.7 * torch.randn(B, C, H, W, generator=g)) + 0.2)))
+    return maps

@@ -45,7 +45,18 @@ class StageWeights(Structure):
                 ('wstack256_rows', c_int), ('wstack_ffn_rows', c_int), ('ffn_channels', c_int), ('num_classes', c_int)]
 
 
+class HeadWeights(Structure):
+    """struct pf_head_weights."""
+    _fields_ = [('conv_split', c_void_p), ('gn_gamma', c_void_p), ('gn_beta', c_void_p), ('head_w', c_void_p),
+                ('head_b', c_void_p), ('num_proposals', c_int), ('num_classes', c_int), ('num_thing_classes', c_int),
+                ('gn_eps', c_float)]
+
+
 _SIGS = {
+    'pf_cast_maps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pf_kernel_head_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'pf_kernel_head': (c_int, [POINTER(HeadWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     'pf_version': (c_int, []),
     'pf_last_error_string': (c_char_p, []),
     'pf_last_launch_count': (c_int, []),

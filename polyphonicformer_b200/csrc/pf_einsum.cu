@@ -49,6 +49,8 @@ struct EinsumParams {
     int Btot, b0;        // batch window inside the [2][Btot] feature / logits tensors
     int unit0;           // first unit of this launch (B: depth branch only)
     int early_feats;     // the feature maps were complete before the PREVIOUS kernel started: prefetch them before pdl_wait
+    int kdiv;            // kernel set of unit u = u / kdiv (1: one set per unit; B: one set shared by the B images of a map)
+    int fmod;            // feature map of unit u = u % fmod (pf_kernel_head: the two 128-row halves of a conv share a map)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
@@ -92,6 +94,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
     const int tile_end = (int)((long long)(j + 1) * tiles_per_unit / p.ctas_per_unit);
     const int ntiles = tile_end - tile_begin;
     const int gunit = (unit / p.B) * p.Btot + p.b0 + unit % p.B;   // unit inside the full-batch feature / logits tensors
+    const int funit = gunit % p.fmod;                              // its feature map
+    const int kunit = unit / p.kdiv;                               // its kernel set
     long long* dbg = dbg_claim_all(TMA_OUT ? 21 : 20);
 
     if (threadIdx.x == 0) {
@@ -132,7 +136,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
 #pragma unroll
                 for (int bx = 0; bx < NBOX; ++bx)   // a box that starts beyond HW is zero-filled by the TMA unit
                     tma_load_2d(sB + s * STAGE_BYTES + bx * E_B_BYTES, &tmap_feats, &full[s],
-                                (tile_begin + i) * TILE + bx * E_BHW, gunit * E_C, fhint);
+                                (tile_begin + i) * TILE + bx * E_BHW, funit * E_C, fhint);
             }
         }
     } else if (warp == 1) {
@@ -168,7 +172,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
         {   // A operand -> tensor memory: this thread's kernel row, hi plane then lo plane (rows >= N: zeros)
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.kern + (((size_t)unit * 2 + h) * p.N + (row_ok ? n : 0)) * E_C);
+                const uint4* src = reinterpret_cast<const uint4*>(p.kern + (((size_t)kunit * 2 + h) * p.N + (row_ok ? n : 0)) * E_C);
 #pragma unroll 1
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t v[32];
@@ -184,7 +188,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             tc_fence_before();
             mbar_arrive(abar);
         }
-        const float bias = row_ok ? __ldg(p.kbias + (size_t)unit * p.N + n) : 0.f;
+        const float bias = (row_ok && p.kbias) ? __ldg(p.kbias + (size_t)kunit * p.N + n) : 0.f;
         float* orow = p.logits ? p.logits + ((size_t)gunit * p.N + (row_ok ? n : 0)) * p.HW : nullptr;
         const bool vec_ok = (p.HW & 3) == 0;
         uint32_t* brow = (p.bits && unit < p.B) ? p.bits + (size_t)unit * p.words * 128 + n : nullptr;
@@ -321,6 +325,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
     p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats, p.unit0 = branch0 * B;
+    p.kdiv = 1, p.fmod = 0x7fffffff;
     // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
     const bool tma_out = logits && (HW % 4) == 0;
     const int tile = tma_out ? 64 : 128;   // must match einsum_kernel<TMA_OUT>::TILE
@@ -337,5 +342,36 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
     return launch_pdl("einsum_kernel", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,
+                      static_cast<cudaStream_t>(stream), tmap, tmap_o, p);
+}
+
+// pf_kernel_head's three 1x1 convolutions (kernel_head.py:250-251, 264-265, 277-278; ConvModule without bias) as ONE
+// launch of the einsum kernel: unit u = half * 3B + map * B + b computes rows [128 * half, 128 * half + 128) of
+// W_map . maps[map][b]; conv_split holds the six (half, map) row blocks as bf16 hi / lo planes [6][2][128][256].
+// Y: fp32 [6B][128][HW].
+int pf::conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y, int B, int HW, int HWp, void* stream) {
+    using namespace pf;
+    const int n_units = 6 * B;
+    CUtensorMap tmap;
+    if (int e = make_tmap_bf16_2d(&tmap, maps, (uint64_t)3 * B * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
+    EinsumParams p;
+    p.kern = conv_split, p.kbias = nullptr, p.logits = Y, p.bits = nullptr;
+    p.N = 128, p.HW = HW, p.words = (HW + 31) / 32, p.B = n_units;
+    p.Btot = n_units, p.b0 = 0, p.early_feats = 0, p.unit0 = 0;
+    p.kdiv = B, p.fmod = 3 * B;
+    const bool tma_out = (HW % 4) == 0;
+    const int tile = tma_out ? 64 : 128;
+    p.tiles_per_unit = (HW + tile - 1) / tile;
+    int cpu = num_sms() / n_units;
+    if (cpu < 1) cpu = 1;
+    if (cpu > p.tiles_per_unit) cpu = p.tiles_per_unit;
+    p.ctas_per_unit = cpu;
+    CUtensorMap tmap_o = tmap;
+    if (tma_out)
+        if (int e = make_tmap_f32_3d(&tmap_o, Y, (uint64_t)n_units, 128, (uint64_t)HW, 128, 32)) return e;
+    auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
+    cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
+    if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
+    return launch_pdl("einsum_kernel(conv1x1)", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,
                       static_cast<cudaStream_t>(stream), tmap, tmap_o, p);
 }

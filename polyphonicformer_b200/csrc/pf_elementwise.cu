@@ -153,6 +153,19 @@ extern "C" int pf_cast_feats(const float* x_feats, const float* depth_feats, uin
     return PF_OK;
 }
 
+extern "C" int pf_cast_maps(const float* maps, uint16_t* out, int rows, int HW, int HWp, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(maps && out, PF_ERR_ARG, "pf_cast_maps: null pointer");
+    PF_REQUIRE(rows > 0 && HW > 0 && HWp >= HW && HWp % 8 == 0, PF_ERR_ARG, "pf_cast_maps: bad shape rows=%d HW=%d HWp=%d", rows, HW, HWp);
+    PF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, PF_ERR_ALIGN, "pf_cast_maps: out not 16-byte aligned");
+    int gx = (HWp / 4 + 255) / 256;
+    if (gx > 32) gx = 32;
+    cast_feats_kernel<<<dim3(gx, rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(maps, maps, out, rows, HW, HWp);
+    PF_CHECK_LAUNCH("cast_feats_kernel");
+    return PF_OK;
+}
+
 extern "C" int pf_binarise(const float* mask_logits, uint32_t* bits, int B, int N, int HW, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;

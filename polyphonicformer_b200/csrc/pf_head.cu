@@ -1,0 +1,372 @@
+// K5 -- the tail of KernelHead._decode_init_proposals (polyphonic/kernel_head.py:250-336 of the reference): the step
+// that produces the decoder's inputs from the three SemanticFPN maps (localization, semantic, depth):
+//
+//     loc   = ReLU(GN32(W_loc . maps[0]))      sem = ReLU(GN32(W_seg . maps[1]))      dep = ReLU(GN32(W_dep . maps[2]))
+//     mask_preds  = init_kernels . loc          seg_preds = conv_seg . sem + b         depth_pred = conv_direct_depth . dep + b
+//     x_feats     = sem + loc                   mask_preds := [mask_preds ; seg_preds[num_things:]]   (cat_stuff_mask)
+//
+// Three launches (then pf_mask_pool + pf_init_proposals, which already exist, finish kernel_head.py:313-336):
+//   1. conv1x1_maps (pf_einsum.cu): the three 256x256 1x1 convolutions as one launch of the einsum kernel -> Y fp32.
+//   2. gn_stats_kernel: GroupNorm statistics (32 groups of 8 channels over the whole map, biased variance, fp64
+//      merge) folded with gamma / beta into one (scale, shift) pair per channel.
+//   3. head_apply_kernel (below): one streaming pass over Y.  Thread = pixel: normalise + ReLU the three maps 32
+//      channels at a time, write x_feats / depth_feats in the decoder's bf16 layout, and feed the SAME registers to the
+//      tensor cores as the A operand of the three prediction heads: the activations are split into bf16 hi + lo, packed
+//      two channels per 32-bit word and stored with tcgen05.st into tensor memory (row = pixel in lane, K = channel
+//      along the columns), the head weights (bf16 hi + lo, K-major, 128-byte swizzle) sit in shared memory for the
+//      whole kernel, three TS-mode MMAs per K step (Al.Wh + Ah.Wl + Ah.Wh, fp32 accumulate) keep fp32-level accuracy.
+//      D = [128 pixels][112 | 32 | 16 columns] per worker group; the group reads it back with tcgen05.ld, adds the
+//      biases, writes mask_preds / seg_preds / depth_pred coalesced along the pixels and ballots the sign bits of the
+//      initial masks (kernel_head.py:314-317) in the layout pf_mask_pool consumes.
+//   Warp roles (320 threads, one persistent CTA per SM): warps 0..3 / 4..7 = two worker groups (TMEM lane quadrant =
+//   warp % 4, each group owns 256 TMEM columns and its own tiles), warps 8 / 9 = their MMA issuers.
+// HBM-bound: 3 KB of Y read, 1 KB of bf16 features and ~0.5 KB of predictions written per pixel.
+#include "pf_internal.h"
+#include "pf_sm100.cuh"
+
+namespace pf {
+
+constexpr int H_THREADS = 320;
+constexpr int H_ROWS = 160;                 // head rows: init_kernels 0..111 | conv_seg 112..143 | conv_direct_depth 144..159
+constexpr int H_ROW_SEG = 112, H_ROW_DEP = 144;
+constexpr int H_KBLK = H_ROWS * 128;        // bytes of one 64-channel block of one weight plane
+constexpr int H_WBYTES = 2 * 4 * H_KBLK;    // hi / lo planes x 4 channel blocks = 163840
+constexpr int H_CH = 32;                    // channels per chunk
+constexpr int H_DCOLS = 160;                // accumulator columns of a group
+constexpr int H_GCOLS = 256;                // TMEM columns per group
+constexpr int H_AFF_OFF = H_WBYTES;                         // float2 [2 groups][3][256]
+constexpr int H_BIAS_OFF = H_AFF_OFF + 2 * 3 * 256 * 8;     // float [160]
+constexpr int H_BAR_OFF = H_BIAS_OFF + H_ROWS * 4;
+constexpr int H_SMEM = H_BAR_OFF + 128 + 1024;
+
+struct HeadParams {
+    const float* Y;          // [6B][128][HW]: unit = half * 3B + map * B + b
+    const float2* affine;    // [3B][256] (scale, shift): unit = map * B + b
+    const float* head_b;     // [160]
+    uint16_t* feats;         // out bf16 [2][B][256][HWp]
+    float* x32;              // optional fp32 [B][256][HW]
+    float* d32;              // optional fp32 [B][256][HW]
+    float* mask_preds;       // [B][P + n_stuff][HW]
+    float* seg_preds;        // [B][num_classes][HW]
+    float* depth_pred;       // [B][HW]
+    uint32_t* bits;          // optional [B][WORDS][128]: sign bits of the P initial masks
+    int B, HW, HWp, P, num_classes, num_things, words;
+    int tiles_per_img, n_tiles;
+};
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+
+// one map's 32-channel chunk: v[] (already normalised + ReLU) -> bf16 hi / lo, two channels per column
+__device__ __forceinline__ void st_split16(uint32_t taddr, const float (&v)[32]) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        hi[j] = pack_bf16x2(a, b);
+        lo[j] = pack_bf16x2(a - __uint_as_float(hi[j] << 16), b - __uint_as_float(hi[j] & 0xFFFF0000u));
+    }
+    tmem_st16(taddr, hi);
+    tmem_st16(taddr + 16, lo);
+}
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float2* s_aff = reinterpret_cast<float2*>(smem + H_AFF_OFF);
+    float* s_bias = reinterpret_cast<float*>(smem + H_BIAS_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + H_BAR_OFF);
+    uint64_t* wfull = bars;          // head weights landed
+    uint64_t* afull = bars + 1;      // [2] the group's A chunk is in tensor memory (128 arrivals)
+    uint64_t* afree = bars + 3;      // [2] the MMAs that read it have completed
+    uint64_t* dfull = bars + 5;      // [2] the tile's accumulators are complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_w);
+        mbar_init(wfull, 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&afull[g], 128);
+            mbar_init(&afree[g], 1);
+            mbar_init(&dfull[g], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    for (int i = threadIdx.x; i < H_ROWS; i += H_THREADS) s_bias[i] = __ldg(p.head_b + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+    pdl_launch_dependents();
+
+    if (warp >= 8) {
+        // ================= MMA issuer of group g (the weights are static: their TMA does not wait for the grid) ====
+        const int g = warp - 8;
+        if (g == 0 && lane == 0) {
+            mbar_arrive_expect_tx(wfull, H_WBYTES);
+            for (int i = 0; i < 8; ++i)   // (plane, channel block): a [160 rows][64 channels] box
+                tma_load_2d(smem + i * H_KBLK, &tmap_w, wfull, (i & 3) * 64, (i >> 2) * H_ROWS, kEvictLast);
+        }
+        mbar_wait(wfull, 0);
+        const uint32_t tD = tmem_base + g * H_GCOLS, tA = tD + H_DCOLS;
+        const uint32_t wbase = smem_u32(smem);
+        constexpr uint32_t idesc[3] = {make_idesc_bf16(128, 112, 0, 0), make_idesc_bf16(128, 32, 0, 0),
+                                       make_idesc_bf16(128, 16, 0, 0)};
+        constexpr int rowoff[3] = {0, H_ROW_SEG, H_ROW_DEP};
+        uint32_t n = 0;
+        for (int t = blockIdx.x * 2 + g; t < p.n_tiles; t += gridDim.x * 2) {
+            for (int k = 0; k < 256 / H_CH; ++k, ++n) {
+                mbar_wait(&afull[g], n & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const int c0 = k * H_CH + ks * 16;
+                        const uint32_t wa = wbase + (c0 >> 6) * H_KBLK + rowoff[m] * 128;
+                        const uint64_t koff = (uint64_t)(((c0 & 63) * 2) >> 4);
+                        const uint64_t bh = make_smem_desc_sw128(wa, 16, 1024) + koff;
+                        const uint64_t bl = make_smem_desc_sw128(wa + 4 * H_KBLK, 16, 1024) + koff;
+                        const uint32_t ah = tA + m * 32 + ks * 8, al = ah + 16;
+                        const uint32_t d = tD + rowoff[m];
+                        umma_bf16_ts_warp(d, al, bh, idesc[m], (k | ks) != 0);
+                        umma_bf16_ts_warp(d, ah, bl, idesc[m], 1);
+                        umma_bf16_ts_warp(d, ah, bh, idesc[m], 1);
+                    }
+                }
+                umma_commit_warp(&afree[g]);
+                if (k == 256 / H_CH - 1) umma_commit_warp(&dfull[g]);
+            }
+        }
+    } else {
+        // ================= worker group g: thread = pixel =================
+        const int g = warp >> 2, q = warp & 3;
+        const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16) + g * H_GCOLS, tA = tD + H_DCOLS;
+        float2* aff = s_aff + g * 3 * 256;
+        const int tg = threadIdx.x & 127;
+        const int NM = p.P + p.num_classes - p.num_things;   // channels of mask_preds
+        pdl_wait();   // Y and the affine table come from the previous kernels
+        int cur_b = -1;
+        uint32_t n = 0, tile_i = 0;
+        for (int t = blockIdx.x * 2 + g; t < p.n_tiles; t += gridDim.x * 2, ++tile_i) {
+            const int b = t / p.tiles_per_img;
+            const int hw0 = (t - b * p.tiles_per_img) * 128;
+            if (b != cur_b) {   // (scale, shift) of this image's three maps -> shared memory
+                group_bar(g);
+                for (int i = tg; i < 3 * 256; i += 128)
+                    aff[i] = __ldg(p.affine + ((size_t)(i >> 8) * p.B + b) * 256 + (i & 255));
+                group_bar(g);
+                cur_b = b;
+            }
+            const int px = hw0 + q * 32 + lane;
+            const bool ok = px < p.HW, okp = px < p.HWp;
+            for (int k = 0; k < 256 / H_CH; ++k, ++n) {
+                const int c0 = k * H_CH;
+                const size_t urow = (size_t)((c0 >> 7) * 3 * p.B + b) * 128 + (c0 & 127);   // map 0; map m: + m * B * 128
+                const float* yl = p.Y + urow * p.HW + px;
+                const float* ys = yl + (size_t)p.B * 128 * p.HW;
+                const float* yd = ys + (size_t)p.B * 128 * p.HW;
+                float vl[32], vs[32], vd[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vl[j] = ok ? __ldcs(yl + (size_t)j * p.HW) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vs[j] = ok ? __ldcs(ys + (size_t)j * p.HW) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vd[j] = ok ? __ldcs(yd + (size_t)j * p.HW) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 a = aff[c0 + j];
+                    vl[j] = ok ? fmaxf(fmaf(vl[j], a.x, a.y), 0.f) : 0.f;
+                }
+                if (n > 0) {   // the MMAs of the previous chunk have read the A buffer
+                    mbar_wait(&afree[g], (n - 1) & 1);
+                    tc_fence_after();
+                }
+                st_split16(tA, vl);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 a = aff[256 + c0 + j];
+                    vs[j] = ok ? fmaxf(fmaf(vs[j], a.x, a.y), 0.f) : 0.f;
+                }
+                st_split16(tA + 32, vs);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float2 a = aff[512 + c0 + j];
+                    vd[j] = ok ? fmaxf(fmaf(vd[j], a.x, a.y), 0.f) : 0.f;
+                }
+                st_split16(tA + 64, vd);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&afull[g]);
+                // x_feats = sem + loc (kernel_head.py:303), depth_feats: the decoder's bf16 maps (+ optional fp32 copies)
+                if (okp) {
+                    uint16_t* xo = p.feats + ((size_t)b * 256 + c0) * p.HWp + px;
+                    uint16_t* dxo = xo + (size_t)p.B * 256 * p.HWp;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        xo[(size_t)j * p.HWp] = (uint16_t)(pack_bf16x2(vl[j] + vs[j], 0.f) & 0xFFFFu);
+                        dxo[(size_t)j * p.HWp] = (uint16_t)(pack_bf16x2(vd[j], 0.f) & 0xFFFFu);
+                    }
+                }
+                if (ok && p.x32) {
+                    float* o = p.x32 + ((size_t)b * 256 + c0) * p.HW + px;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[(size_t)j * p.HW] = vl[j] + vs[j];
+                }
+                if (ok && p.d32) {
+                    float* o = p.d32 + ((size_t)b * 256 + c0) * p.HW + px;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[(size_t)j * p.HW] = vd[j];
+                }
+            }
+            // ---- the three heads of this tile: accumulators -> predictions
+            mbar_wait(&dfull[g], tile_i & 1);
+            tc_fence_after();
+            float* mp = p.mask_preds + (size_t)b * NM * p.HW + px;
+            float* sp = p.seg_preds + (size_t)b * p.num_classes * p.HW + px;
+            uint32_t* bw = p.bits ? p.bits + ((size_t)b * p.words + (px >> 5)) * 128 : nullptr;
+#pragma unroll 1
+            for (int cb = 0; cb < 5; ++cb) {   // columns [32 cb, 32 cb + 32)
+                uint32_t v[32];
+                tmem_ld32(tD + cb * 32, v);
+                tmem_ld_wait();
+                uint32_t word = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = cb * 32 + j;
+                    const float f = __uint_as_float(v[j]) + s_bias[col];
+                    if (col < H_ROW_SEG) {
+                        const uint32_t bal = __ballot_sync(0xffffffffu, ok && col < p.P && f > 0.f);
+                        if (lane == j) word = bal;
+                        if (ok && col < p.P) __stcs(mp + (size_t)col * p.HW, f);
+                    } else if (col < H_ROW_DEP) {
+                        const int cls = col - H_ROW_SEG;
+                        if (ok && cls < p.num_classes) {
+                            sp[(size_t)cls * p.HW] = f;
+                            if (cls >= p.num_things) mp[(size_t)(p.P + cls - p.num_things) * p.HW] = f;
+                        }
+                    } else if (col == H_ROW_DEP) {
+                        if (ok) p.depth_pred[(size_t)b * p.HW + px] = f;
+                    }
+                }
+                if (bw && cb < 4 && (px - lane) < p.HW) bw[cb * 32 + lane] = word;   // rows >= P: zero
+            }
+            tc_fence_before();   // the next tile's first MMA overwrites these accumulators
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+// GroupNorm statistics of one (map-image unit, group): 8 consecutive channel rows of Y, then the per-channel
+// (scale, shift) = (gamma * rstd, beta - mean * gamma * rstd).  torch.nn.GroupNorm: biased variance, eps inside the sqrt.
+constexpr int GN_THREADS = 512;
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const float* __restrict__ Y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float2* __restrict__ affine, int B, int HW, float eps) {
+    __shared__ double s_sum[GN_THREADS / 32], s_sq[GN_THREADS / 32];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int grp = blockIdx.x;            // 0..31
+    const int u = blockIdx.y;              // map * B + b
+    const int c0 = grp * 8;
+    const float* src = Y + ((size_t)((c0 >> 7) * 3 * B + u) * 128 + (c0 & 127)) * HW;
+    const size_t total = (size_t)8 * HW;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    if ((HW & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        const size_t n4 = total / 4;
+        size_t i = threadIdx.x;
+        for (; i + 3 * GN_THREADS < n4; i += 4 * GN_THREADS) {   // four independent 16-byte loads in flight
+            float4 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = __ldg(s4 + i + r * GN_THREADS);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                s[r] += (v[r].x + v[r].y) + (v[r].z + v[r].w);
+                ss[r] += (v[r].x * v[r].x + v[r].y * v[r].y) + (v[r].z * v[r].z + v[r].w * v[r].w);
+            }
+        }
+        for (; i < n4; i += GN_THREADS) {
+            const float4 v = __ldg(s4 + i);
+            s[0] += (v.x + v.y) + (v.z + v.w);
+            ss[0] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < total; i += GN_THREADS) {
+            const float v = __ldg(src + i);
+            s[0] += v, ss[0] += v * v;
+        }
+    }
+    double ds = ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
+    double dq = ((double)ss[0] + (double)ss[1]) + ((double)ss[2] + (double)ss[3]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = ds, s_sq[threadIdx.x >> 5] = dq;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double a = 0.0, q2 = 0.0;
+        for (int w = 0; w < GN_THREADS / 32; ++w) a += s_sum[w], q2 += s_sq[w];
+        const double mean = a / (double)total;
+        double var = q2 / (double)total - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        const int map = u / B, c = c0 + threadIdx.x;
+        const double sc = (double)gamma[map * 256 + c] * rstd;
+        affine[(size_t)u * 256 + c] = make_float2((float)sc, (float)((double)beta[map * 256 + c] - mean * sc));
+    }
+}
+
+}  // namespace pf
+
+extern "C" size_t pf_kernel_head_workspace_bytes(int B, int HW) {
+    if (B <= 0 || HW <= 0) return 0;
+    return (size_t)6 * B * 128 * HW * 4 + (size_t)3 * B * 256 * 8 + 256;
+}
+
+extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, uint16_t* feats, float* x32, float* d32,
+                              float* mask_preds, float* seg_preds, float* depth_pred, uint32_t* bits, void* workspace,
+                              size_t workspace_bytes, int B, int HW, int HWp, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(w && maps && feats && mask_preds && seg_preds && depth_pred && workspace, PF_ERR_ARG, "pf_kernel_head: null pointer");
+    PF_REQUIRE(w->conv_split && w->gn_gamma && w->gn_beta && w->head_w && w->head_b, PF_ERR_ARG, "pf_kernel_head: null weight pointer");
+    PF_REQUIRE(B > 0 && HW > 0 && HWp >= HW && HWp % 8 == 0, PF_ERR_ARG, "pf_kernel_head: bad shape B=%d HW=%d HWp=%d", B, HW, HWp);
+    PF_REQUIRE(w->num_proposals > 0 && w->num_proposals <= H_ROW_SEG && w->num_classes > 0 && w->num_classes <= H_ROW_DEP - H_ROW_SEG &&
+                   w->num_thing_classes >= 0 && w->num_thing_classes <= w->num_classes,
+               PF_ERR_ARG, "pf_kernel_head: unsupported head sizes P=%d classes=%d things=%d", w->num_proposals, w->num_classes,
+               w->num_thing_classes);
+    PF_REQUIRE(workspace_bytes >= pf_kernel_head_workspace_bytes(B, HW), PF_ERR_WORKSPACE, "pf_kernel_head: workspace too small");
+    PF_REQUIRE(((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(maps) | reinterpret_cast<uintptr_t>(feats) |
+                 reinterpret_cast<uintptr_t>(w->conv_split) | reinterpret_cast<uintptr_t>(w->head_w)) & 15) == 0,
+               PF_ERR_ALIGN, "pf_kernel_head: pointers must be 16-byte aligned");
+    reset_launch_count();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* Y = static_cast<float*>(workspace);
+    float2* affine = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)6 * B * 128 * HW * 4 + 255) & ~(size_t)255));
+
+    if (int e = conv1x1_maps(maps, w->conv_split, Y, B, HW, HWp, stream)) return e;
+    if (int e = launch_pdl("gn_stats_kernel", gn_stats_kernel, dim3(32, 3 * B), dim3(GN_THREADS), 0, st, (const float*)Y,
+                           w->gn_gamma, w->gn_beta, affine, B, HW, w->gn_eps))
+        return e;
+
+    HeadParams p;
+    p.Y = Y, p.affine = affine, p.head_b = w->head_b, p.feats = feats, p.x32 = x32, p.d32 = d32;
+    p.mask_preds = mask_preds, p.seg_preds = seg_preds, p.depth_pred = depth_pred, p.bits = bits;
+    p.B = B, p.HW = HW, p.HWp = HWp, p.P = w->num_proposals, p.num_classes = w->num_classes, p.num_things = w->num_thing_classes;
+    p.words = (HW + 31) / 32;
+    p.tiles_per_img = (HWp + 127) / 128, p.n_tiles = B * p.tiles_per_img;
+    CUtensorMap tmap_w;
+    if (int e = make_tmap_bf16_2d(&tmap_w, w->head_w, 2 * H_ROWS, 256, 256, H_ROWS, 64)) return e;
+    cudaError_t ea = cudaFuncSetAttribute(head_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+    if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "head_apply smem attribute: %s", cudaGetErrorString(ea));
+    int grid = num_sms();
+    if (grid * 2 > p.n_tiles) grid = (p.n_tiles + 1) / 2;
+    return launch_pdl("head_apply_kernel", head_apply_kernel, dim3(grid), dim3(H_THREADS), H_SMEM, st, tmap_w, p);
+}

@@ -35,6 +35,9 @@ int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float*
                        int Btot, int b0, int B, int N, int HW, int HWp, int n_units, int branch0, int early_feats,
                        void* stream);
 
+// the three 1x1 convolutions of pf_kernel_head as one einsum launch (pf_einsum.cu)
+int conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y, int B, int HW, int HWp, void* stream);
+
 // Launch with programmatic stream serialization (PDL): the kernel may begin before its predecessor in the stream has
 // finished; it must execute griddepcontrol.wait (pdl_wait) before touching anything the predecessor wrote.
 template <typename... KArgs, typename... Args>

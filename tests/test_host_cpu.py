@@ -125,3 +125,30 @@ def test_packed_weights_reproduce_reference_stage():
                       (outs[0][0], obj.reshape(B, N, 256)), (outs[1][0], dep.reshape(B, N, 256))):
         l2, mx = rel_err(got, want)
         assert l2 < 2e-5 and mx < 2e-5, (l2, mx)      # fp32 re-association of the fold only
+
+
+def test_head_weights_struct_and_packing():
+    """struct pf_head_weights layout and PackedKernelHead's row blocks (hi + lo planes reproduce the fp32 weights)."""
+    from oracle import synth
+    from polyphonicformer_b200 import _cabi
+    from polyphonicformer_b200.kernel_head import PackedKernelHead, H_ROW_SEG, H_ROW_DEP
+    hdr = open(os.path.join(ROOT, 'include', 'pf_decoder.h')).read()
+    body = hdr[hdr.index('typedef struct pf_head_weights {'):hdr.index('} pf_head_weights;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = re.findall(r'(\w+);', body)
+    assert names == [f[0] for f in _cabi.HeadWeights._fields_]
+    assert ctypes.sizeof(_cabi.HeadWeights) == 5 * 8 + 4 * 4
+    sd = synth.synth_kernel_head_state(1)
+    pk = PackedKernelHead(sd, 'cpu')
+    conv = pk.conv_split.float().reshape(2, 3, 2, 128, 256)            # [half][map][plane][row][in]
+    for m, name in enumerate(('loc', 'seg', 'depth')):
+        w = sd[f'{name}_convs.0.conv.weight'].reshape(256, 256)
+        rec = torch.cat([conv[0, m, 0] + conv[0, m, 1], conv[1, m, 0] + conv[1, m, 1]])
+        assert (rec - w).abs().max() < 2e-5 * w.abs().max()
+    hw = pk.head_w.float().sum(0)
+    assert (hw[:100] - sd['init_kernels.weight'].reshape(100, 256)).abs().max() < 1e-5
+    assert (hw[H_ROW_SEG:H_ROW_SEG + 19] - sd['conv_seg.weight'].reshape(19, 256)).abs().max() < 1e-5
+    assert (hw[H_ROW_DEP] - sd['conv_direct_depth.weight'].reshape(256)).abs().max() < 1e-5
+    assert float(hw[100:H_ROW_SEG].abs().max()) == 0 and float(hw[H_ROW_DEP + 1:].abs().max()) == 0
+    assert torch.equal(pk.head_b[H_ROW_SEG:H_ROW_SEG + 19], sd['conv_seg.bias'])
+    assert pk.stuff_kernels.shape == (11, 256)

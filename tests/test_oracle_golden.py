@@ -87,3 +87,17 @@ def test_panoptic_restatement_matches_reference(name):
     assert np.array_equal(pan, g['panoptic'])
     assert np.array_equal(segments_as_array(info), g['seg'])
     assert np.array_equal(dbasic, g['depth_basic']) and np.array_equal(dfinal, g['depth_final'])
+
+
+@pytest.mark.parametrize('name', ['kernel_head_b2_h16_w24', 'kernel_head_b1_h10_w13'])
+def test_kernel_head_restatement_matches_reference(name):
+    """oracle/kernel_head_ref.py against the real KernelHead._decode_init_proposals (kernel_head.py:240-347)."""
+    from oracle import kernel_head_ref
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    B, H, W, seed = int(g['B']), int(g['H']), int(g['W']), int(g['seed'])
+    with torch.no_grad():
+        out = kernel_head_ref.decode_init_proposals(synth.synth_kernel_head_state(seed), synth.synth_fpn_maps(B, H, W, seed))
+    for k in ('proposal_feats', 'x_feats', 'mask_preds', 'seg_preds', 'depth_feats', 'depth_proposal', 'depth_pred'):
+        l2, mx = rel_err(out[k], g[k])
+        assert l2 < 1e-6 and mx < 1e-6, (name, k, l2, mx)
+    assert float(g['margin']) > 5e-5
