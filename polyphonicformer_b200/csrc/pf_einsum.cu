@@ -51,6 +51,8 @@ struct EinsumParams {
     int early_feats;     // the feature maps were complete before the PREVIOUS kernel started: prefetch them before pdl_wait
     int kdiv;            // kernel set of unit u = u / kdiv (1: one set per unit; B: one set shared by the B images of a map)
     int fmod;            // feature map of unit u = u % fmod (pf_kernel_head: the two 128-row halves of a conv share a map)
+    int out_blocked;     // 0, or the number of 32-pixel blocks per unit: logits leave as [unit][block][128 rows][32 px]
+    float2* stats;       // STATS: [units][ctas_per_unit][128] per-row (sum, sum of squares) over the CTA's pixels
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
@@ -65,7 +67,9 @@ __device__ __forceinline__ void epi_bar4() { asm volatile("bar.sync 1, 128;" :::
 // TMA_OUT: fp32 logits leave as TMA tensor stores of staged tiles (tmap_out over [units][N][HW]).
 // Tile width: 128 pixels (two TMA boxes, MMA N = 128) when only the sign bits are emitted -- half as many MMA
 // issues per pixel, which is what bounds that variant -- and 64 pixels with the logits staging tiles.
-template <bool TMA_OUT>
+// STATS (pf_kernel_head's convolutions): every epilogue thread also accumulates the sum and the sum of squares of its
+// row over the CTA's pixels -- the GroupNorm statistics, without a second pass over the output.
+template <bool TMA_OUT, bool STATS = false>
 __global__ void __launch_bounds__(E_THREADS, 1)
 einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_out,
               const EinsumParams p) {
@@ -192,6 +196,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
         float* orow = p.logits ? p.logits + ((size_t)gunit * p.N + (row_ok ? n : 0)) * p.HW : nullptr;
         const bool vec_ok = (p.HW & 3) == 0;
         uint32_t* brow = (p.bits && unit < p.B) ? p.bits + (size_t)unit * p.words * 128 + n : nullptr;
+        float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
         for (int i = 0; i < ntiles; ++i) {
             const int a = i % NACC;
             mbar_wait(&tfull[a], (i / NACC) & 1);
@@ -216,6 +221,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                     const float f = __uint_as_float(v[c]) + bias;
                     v[c] = __float_as_uint(f);
                     word |= (f > 0.f ? 1u : 0u) << c;
+                    if (STATS) st_s[c & 1] += f, st_q[c & 1] = fmaf(f, f, st_q[c & 1]);   // pixels beyond HW are exact zeros
                 }
                 const int valid = p.HW - hwb;  // > 0
                 if (valid < 32) word &= (1u << valid) - 1u;
@@ -233,7 +239,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                     epi_bar4();
                     if (threadIdx.x == 64) {
                         // evict-last: the x2 up-sampling that follows reads these logits back, ideally from L2
-                        tma_store_3d(&tmap_out, tile, hwb, 0, gunit, kEvictLast);
+                        if (p.out_blocked) tma_store_3d(&tmap_out, tile, 0, 0, gunit * p.out_blocked + (hwb >> 5), kEvictNormal);
+                        else tma_store_3d(&tmap_out, tile, hwb, 0, gunit, kEvictLast);
                         tma_store_commit();
                     }
                 } else if (orow && row_ok) {
@@ -252,6 +259,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 }
             }
         }
+        if (STATS)
+            p.stats[((size_t)unit * p.ctas_per_unit + j) * 128 + n] = make_float2(st_s[0] + st_s[1], st_q[0] + st_q[1]);
     }
     if (TMA_OUT && threadIdx.x == 64) tma_store_wait_read<0>();   // shared memory must outlive the last store's read
     tc_fence_before();
@@ -325,7 +334,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     p.kern = kern, p.kbias = kbias, p.logits = logits, p.bits = bits_out;
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
     p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats, p.unit0 = branch0 * B;
-    p.kdiv = 1, p.fmod = 0x7fffffff;
+    p.kdiv = 1, p.fmod = 0x7fffffff, p.stats = nullptr, p.out_blocked = 0;
     // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
     const bool tma_out = logits && (HW % 4) == 0;
     const int tile = tma_out ? 64 : 128;   // must match einsum_kernel<TMA_OUT>::TILE
@@ -338,7 +347,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     CUtensorMap tmap_o = tmap;
     if (tma_out)
         if (int e = make_tmap_f32_3d(&tmap_o, logits, (uint64_t)(branch0 + n_units / B) * Btot, (uint64_t)N, (uint64_t)HW, 128, 32)) return e;
-    auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
+    auto kern_fn = tma_out ? einsum_kernel<true, false> : einsum_kernel<false, false>;
     cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
     return launch_pdl("einsum_kernel", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,
@@ -348,8 +357,16 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
 // pf_kernel_head's three 1x1 convolutions (kernel_head.py:250-251, 264-265, 277-278; ConvModule without bias) as ONE
 // launch of the einsum kernel: unit u = half * 3B + map * B + b computes rows [128 * half, 128 * half + 128) of
 // W_map . maps[map][b]; conv_split holds the six (half, map) row blocks as bf16 hi / lo planes [6][2][128][256].
-// Y: fp32 [6B][128][HW].
-int pf::conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y, int B, int HW, int HWp, void* stream) {
+// Y: fp32 [6B][ceil(HW/32)][128][32] (pixel-blocked).
+int pf::conv1x1_ctas_per_unit(int B, int HW) {
+    const int tile = 64;
+    int cpu = num_sms() / (6 * B);
+    const int tiles = (HW + tile - 1) / tile;
+    return cpu < 1 ? 1 : (cpu > tiles ? tiles : cpu);
+}
+
+int pf::conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y, float2* stats, int B, int HW, int HWp,
+                     void* stream) {
     using namespace pf;
     const int n_units = 6 * B;
     CUtensorMap tmap;
@@ -358,18 +375,18 @@ int pf::conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y,
     p.kern = conv_split, p.kbias = nullptr, p.logits = Y, p.bits = nullptr;
     p.N = 128, p.HW = HW, p.words = (HW + 31) / 32, p.B = n_units;
     p.Btot = n_units, p.b0 = 0, p.early_feats = 0, p.unit0 = 0;
-    p.kdiv = B, p.fmod = 3 * B;
-    const bool tma_out = (HW % 4) == 0;
-    const int tile = tma_out ? 64 : 128;
+    p.kdiv = B, p.fmod = 3 * B, p.stats = stats;
+    // blocked output: 16 KB [128 rows][32 px] blocks, written whole by the TMA stores (no row-pitch constraint) and
+    // read back by head_apply_kernel with a compile-time channel stride
+    const int nblk = (HW + 31) / 32;
+    p.out_blocked = nblk;
+    const int tile = 64;
     p.tiles_per_unit = (HW + tile - 1) / tile;
-    int cpu = num_sms() / n_units;
-    if (cpu < 1) cpu = 1;
-    if (cpu > p.tiles_per_unit) cpu = p.tiles_per_unit;
+    const int cpu = conv1x1_ctas_per_unit(B, HW);
     p.ctas_per_unit = cpu;
-    CUtensorMap tmap_o = tmap;
-    if (tma_out)
-        if (int e = make_tmap_f32_3d(&tmap_o, Y, (uint64_t)n_units, 128, (uint64_t)HW, 128, 32)) return e;
-    auto kern_fn = tma_out ? einsum_kernel<true> : einsum_kernel<false>;
+    CUtensorMap tmap_o;
+    if (int e = make_tmap_f32_3d(&tmap_o, Y, (uint64_t)n_units * nblk, 128, 32, 128, 32)) return e;
+    auto kern_fn = einsum_kernel<true, true>;
     cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
     return launch_pdl("einsum_kernel(conv1x1)", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,

@@ -7,14 +7,15 @@
 //
 // Three launches (then pf_mask_pool + pf_init_proposals, which already exist, finish kernel_head.py:313-336):
 //   1. conv1x1_maps (pf_einsum.cu): the three 256x256 1x1 convolutions as one launch of the einsum kernel -> Y fp32.
-//   2. gn_stats_kernel: GroupNorm statistics (32 groups of 8 channels over the whole map, biased variance, fp64
-//      merge) folded with gamma / beta into one (scale, shift) pair per channel.
-//   3. head_apply_kernel (below): one streaming pass over Y.  Thread = pixel: normalise + ReLU the three maps 32
-//      channels at a time, write x_feats / depth_feats in the decoder's bf16 layout, and feed the SAME registers to the
+//      Its epilogue also accumulates every row's sum and sum of squares: the GroupNorm statistics cost no extra pass.
+//   2. gn_finalize_kernel: merges those partials (32 groups of 8 channels over the whole map, biased variance, fp64)
+//      and folds gamma / beta into one (scale, shift) pair per channel.
+//   3. head_apply_kernel (below): one streaming pass over Y.  Thread = pixel: normalise + ReLU the three maps 16
+//      channels at a time (the next 16 already in flight), write x_feats / depth_feats in the decoder's bf16 layout, and feed the SAME registers to the
 //      tensor cores as the A operand of the three prediction heads: the activations are split into bf16 hi + lo, packed
 //      two channels per 32-bit word and stored with tcgen05.st into tensor memory (row = pixel in lane, K = channel
 //      along the columns), the head weights (bf16 hi + lo, K-major, 128-byte swizzle) sit in shared memory for the
-//      whole kernel, three TS-mode MMAs per K step (Al.Wh + Ah.Wl + Ah.Wh, fp32 accumulate) keep fp32-level accuracy.
+//      whole kernel, two A buffers per group, three TS-mode MMAs per K step (Al.Wh + Ah.Wl + Ah.Wh, fp32 accumulate) keep fp32-level accuracy.
 //      D = [128 pixels][112 | 32 | 16 columns] per worker group; the group reads it back with tcgen05.ld, adds the
 //      biases, writes mask_preds / seg_preds / depth_pred coalesced along the pixels and ballots the sign bits of the
 //      initial masks (kernel_head.py:314-317) in the layout pf_mask_pool consumes.
@@ -31,16 +32,19 @@ constexpr int H_ROWS = 160;                 // head rows: init_kernels 0..111 | 
 constexpr int H_ROW_SEG = 112, H_ROW_DEP = 144;
 constexpr int H_KBLK = H_ROWS * 128;        // bytes of one 64-channel block of one weight plane
 constexpr int H_WBYTES = 2 * 4 * H_KBLK;    // hi / lo planes x 4 channel blocks = 163840
-constexpr int H_CH = 32;                    // channels per chunk
+constexpr int H_CH = 16;                    // channels per chunk = one K step of the MMAs
+constexpr int H_NCH = 256 / H_CH;
 constexpr int H_DCOLS = 160;                // accumulator columns of a group
-constexpr int H_GCOLS = 256;                // TMEM columns per group
+constexpr int H_ACOLS = 48;                 // one A chunk: 3 maps x (hi, lo) x 8 columns; two buffers per group
+constexpr int H_GCOLS = 256;                // TMEM columns per group: 160 + 2 * 48
 constexpr int H_AFF_OFF = H_WBYTES;                         // float2 [2 groups][3][256]
 constexpr int H_BIAS_OFF = H_AFF_OFF + 2 * 3 * 256 * 8;     // float [160]
 constexpr int H_BAR_OFF = H_BIAS_OFF + H_ROWS * 4;
 constexpr int H_SMEM = H_BAR_OFF + 128 + 1024;
+static_assert(H_DCOLS + 2 * H_ACOLS == H_GCOLS, "tensor memory budget of a worker group");
 
 struct HeadParams {
-    const float* Y;          // [6B][128][HW]: unit = half * 3B + map * B + b
+    const float* Y;          // [6B][nblk][128][32]: unit = half * 3B + map * B + b, 32-pixel blocks
     const float2* affine;    // [3B][256] (scale, shift): unit = map * B + b
     const float* head_b;     // [160]
     uint16_t* feats;         // out bf16 [2][B][256][HWp]
@@ -51,22 +55,22 @@ struct HeadParams {
     float* depth_pred;       // [B][HW]
     uint32_t* bits;          // optional [B][WORDS][128]: sign bits of the P initial masks
     int B, HW, HWp, P, num_classes, num_things, words;
-    int tiles_per_img, n_tiles;
+    int tiles_per_img, n_tiles, nblk;
 };
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
-// one map's 32-channel chunk: v[] (already normalised + ReLU) -> bf16 hi / lo, two channels per column
-__device__ __forceinline__ void st_split16(uint32_t taddr, const float (&v)[32]) {
-    uint32_t hi[16], lo[16];
+// 16 channels of one map (already normalised + ReLU) -> bf16 hi / lo, two channels per 32-bit column
+__device__ __forceinline__ void st_split8(uint32_t taddr, const float* v) {
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
         const float a = v[2 * j], b = v[2 * j + 1];
         hi[j] = pack_bf16x2(a, b);
         lo[j] = pack_bf16x2(a - __uint_as_float(hi[j] << 16), b - __uint_as_float(hi[j] & 0xFFFF0000u));
     }
-    tmem_st16(taddr, hi);
-    tmem_st16(taddr + 16, lo);
+    tmem_st8(taddr, hi);
+    tmem_st8(taddr + 8, lo);
 }
 
 __global__ void __launch_bounds__(H_THREADS, 1)
@@ -77,20 +81,21 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
     float* s_bias = reinterpret_cast<float*>(smem + H_BIAS_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + H_BAR_OFF);
     uint64_t* wfull = bars;          // head weights landed
-    uint64_t* afull = bars + 1;      // [2] the group's A chunk is in tensor memory (128 arrivals)
-    uint64_t* afree = bars + 3;      // [2] the MMAs that read it have completed
-    uint64_t* dfull = bars + 5;      // [2] the tile's accumulators are complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* afull = bars + 1;      // [group][buffer] the A chunk is in tensor memory (128 arrivals)
+    uint64_t* afree = bars + 5;      // [group][buffer] the MMAs that read it have completed
+    uint64_t* dfull = bars + 9;      // [group] the tile's accumulators are complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_w);
         mbar_init(wfull, 1);
-        for (int g = 0; g < 2; ++g) {
-            mbar_init(&afull[g], 128);
-            mbar_init(&afree[g], 1);
-            mbar_init(&dfull[g], 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&afull[i], 128);
+            mbar_init(&afree[i], 1);
         }
+        mbar_init(&dfull[0], 1);
+        mbar_init(&dfull[1], 1);
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc<512>(tmem_slot);
@@ -117,27 +122,26 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
         constexpr int rowoff[3] = {0, H_ROW_SEG, H_ROW_DEP};
         uint32_t n = 0;
         for (int t = blockIdx.x * 2 + g; t < p.n_tiles; t += gridDim.x * 2) {
-            for (int k = 0; k < 256 / H_CH; ++k, ++n) {
-                mbar_wait(&afull[g], n & 1);
+#pragma unroll 1
+            for (int k = 0; k < H_NCH; ++k, ++n) {
+                const uint32_t buf = n & 1;
+                mbar_wait_backoff(&afull[g * 2 + buf], (n >> 1) & 1, 64);   // shares a scheduler with two worker warps
                 tc_fence_after();
+                const int c0 = k * H_CH;
+                const uint64_t koff = (uint64_t)(((c0 & 63) * 2) >> 4);
 #pragma unroll
                 for (int m = 0; m < 3; ++m) {
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const int c0 = k * H_CH + ks * 16;
-                        const uint32_t wa = wbase + (c0 >> 6) * H_KBLK + rowoff[m] * 128;
-                        const uint64_t koff = (uint64_t)(((c0 & 63) * 2) >> 4);
-                        const uint64_t bh = make_smem_desc_sw128(wa, 16, 1024) + koff;
-                        const uint64_t bl = make_smem_desc_sw128(wa + 4 * H_KBLK, 16, 1024) + koff;
-                        const uint32_t ah = tA + m * 32 + ks * 8, al = ah + 16;
-                        const uint32_t d = tD + rowoff[m];
-                        umma_bf16_ts_warp(d, al, bh, idesc[m], (k | ks) != 0);
-                        umma_bf16_ts_warp(d, ah, bl, idesc[m], 1);
-                        umma_bf16_ts_warp(d, ah, bh, idesc[m], 1);
-                    }
+                    const uint32_t wa = wbase + (c0 >> 6) * H_KBLK + rowoff[m] * 128;
+                    const uint64_t bh = make_smem_desc_sw128(wa, 16, 1024) + koff;
+                    const uint64_t bl = make_smem_desc_sw128(wa + 4 * H_KBLK, 16, 1024) + koff;
+                    const uint32_t ah = tA + buf * H_ACOLS + m * 16, al = ah + 8;
+                    const uint32_t d = tD + rowoff[m];
+                    umma_bf16_ts_warp(d, al, bh, idesc[m], k != 0);
+                    umma_bf16_ts_warp(d, ah, bl, idesc[m], 1);
+                    umma_bf16_ts_warp(d, ah, bh, idesc[m], 1);
                 }
-                umma_commit_warp(&afree[g]);
-                if (k == 256 / H_CH - 1) umma_commit_warp(&dfull[g]);
+                umma_commit_warp(&afree[g * 2 + buf]);
+                if (k == H_NCH - 1) umma_commit_warp(&dfull[g]);
             }
         }
     } else {
@@ -147,12 +151,90 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
         float2* aff = s_aff + g * 3 * 256;
         const int tg = threadIdx.x & 127;
         const int NM = p.P + p.num_classes - p.num_things;   // channels of mask_preds
+        const size_t feat_branch = (size_t)p.B * 256 * p.HWp;   // feats: x_feats -> depth_feats
         pdl_wait();   // Y and the affine table come from the previous kernels
         int cur_b = -1;
         uint32_t n = 0, tile_i = 0;
-        for (int t = blockIdx.x * 2 + g; t < p.n_tiles; t += gridDim.x * 2, ++tile_i) {
-            const int b = t / p.tiles_per_img;
-            const int hw0 = (t - b * p.tiles_per_img) * 128;
+
+        // Y is pixel-blocked ([unit][32-px block][128 channels][32 px]): a warp reads ONE block, its channel stride is a
+        // compile-time 128 bytes, so the 48 loads of a chunk are immediates off three running pointers (the first
+        // version spent 45 % of its instructions on 64-bit index arithmetic, ncu source page).
+        const size_t hw = (size_t)p.HW, hwp = (size_t)p.HWp;
+        const size_t map_stride = (size_t)p.B * p.nblk * 4096;   // Y: from one map's unit to the next map's
+        const size_t half_jump = ((size_t)3 * p.B * p.nblk - 1) * 4096;   // channel 128 of half 0 -> channel 0 of half 1
+        // the three maps' 16 channels of chunk k: 48 independent loads through the running pointer y (map 0)
+        auto load_chunk = [&](float (&v)[48], const float*& y, int k) {
+            const float* y1 = y + map_stride;
+            const float* y2 = y1 + map_stride;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldcs(y + j * 32), v[16 + j] = __ldcs(y1 + j * 32), v[32 + j] = __ldcs(y2 + j * 32);
+            y += 16 * 32 + (k == 7 ? half_jump : 0);
+        };
+        // normalise + ReLU, A operand -> tensor memory, feature maps -> global (xo / x32o / d32o: running pointers)
+        auto process_chunk = [&](float (&v)[48], int k, bool ok, bool okp, uint16_t*& xo, float*& x32o, float*& d32o) {
+            const float2* a0 = aff + k * H_CH;
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 a = a0[m * 256 + j];
+                    v[m * 16 + j] = fmaxf(fmaf(v[m * 16 + j], a.x, a.y), 0.f);
+                }
+            const uint32_t buf = n & 1;
+            if (n >= 2) {   // the MMAs that read this buffer two chunks ago have completed
+                mbar_wait(&afree[g * 2 + buf], ((n >> 1) - 1) & 1);
+                tc_fence_after();
+            }
+            const uint32_t ta = tA + buf * H_ACOLS;
+            st_split8(ta, v);
+            st_split8(ta + 16, v + 16);
+            st_split8(ta + 32, v + 32);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&afull[g * 2 + buf]);
+            ++n;
+            // x_feats = sem + loc (kernel_head.py:303), depth_feats: the decoder's bf16 maps (+ optional fp32 copies)
+            if (okp) {
+                uint16_t* xp = xo;
+                uint16_t* dp = xo + feat_branch;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t pk = pack_bf16x2(ok ? v[j] + v[16 + j] : 0.f, ok ? v[32 + j] : 0.f);   // pad columns: zero
+                    *xp = (uint16_t)(pk & 0xFFFFu), *dp = (uint16_t)(pk >> 16);
+                    xp += hwp, dp += hwp;
+                }
+            }
+            xo += 16 * hwp;
+            if (x32o) {
+                if (ok) {
+                    float* o = x32o;
+                    float* d = d32o;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        *o = v[j] + v[16 + j], *d = v[32 + j];
+                        o += hw, d += hw;
+                    }
+                }
+                x32o += 16 * hw, d32o += 16 * hw;
+            }
+        };
+
+        float va[48], vb[48];
+        int t = blockIdx.x * 2 + g;
+        int b = 0, px = 0;
+        const float* y = p.Y;
+        auto locate = [&](int tt) {   // tile -> image, this thread's pixel, its first Y row (clamped inside the map)
+            b = tt / p.tiles_per_img;
+            px = (tt - b * p.tiles_per_img) * 128 + q * 32 + lane;
+            int blk = (px - lane) >> 5;   // this warp's 32-pixel block (clamped: rows of A / D beyond HW are never stored)
+            if (blk >= p.nblk) blk = p.nblk - 1;
+            y = p.Y + ((size_t)b * p.nblk + blk) * 4096 + lane;
+        };
+        if (t < p.n_tiles) {
+            locate(t);
+            load_chunk(va, y, 0);
+        }
+        for (; t < p.n_tiles; ++tile_i) {
             if (b != cur_b) {   // (scale, shift) of this image's three maps -> shared memory
                 group_bar(g);
                 for (int i = tg; i < 3 * 256; i += 128)
@@ -160,73 +242,30 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
                 group_bar(g);
                 cur_b = b;
             }
-            const int px = hw0 + q * 32 + lane;
-            const bool ok = px < p.HW, okp = px < p.HWp;
-            for (int k = 0; k < 256 / H_CH; ++k, ++n) {
-                const int c0 = k * H_CH;
-                const size_t urow = (size_t)((c0 >> 7) * 3 * p.B + b) * 128 + (c0 & 127);   // map 0; map m: + m * B * 128
-                const float* yl = p.Y + urow * p.HW + px;
-                const float* ys = yl + (size_t)p.B * 128 * p.HW;
-                const float* yd = ys + (size_t)p.B * 128 * p.HW;
-                float vl[32], vs[32], vd[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) vl[j] = ok ? __ldcs(yl + (size_t)j * p.HW) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) vs[j] = ok ? __ldcs(ys + (size_t)j * p.HW) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) vd[j] = ok ? __ldcs(yd + (size_t)j * p.HW) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 a = aff[c0 + j];
-                    vl[j] = ok ? fmaxf(fmaf(vl[j], a.x, a.y), 0.f) : 0.f;
-                }
-                if (n > 0) {   // the MMAs of the previous chunk have read the A buffer
-                    mbar_wait(&afree[g], (n - 1) & 1);
-                    tc_fence_after();
-                }
-                st_split16(tA, vl);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 a = aff[256 + c0 + j];
-                    vs[j] = ok ? fmaxf(fmaf(vs[j], a.x, a.y), 0.f) : 0.f;
-                }
-                st_split16(tA + 32, vs);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float2 a = aff[512 + c0 + j];
-                    vd[j] = ok ? fmaxf(fmaf(vd[j], a.x, a.y), 0.f) : 0.f;
-                }
-                st_split16(tA + 64, vd);
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&afull[g]);
-                // x_feats = sem + loc (kernel_head.py:303), depth_feats: the decoder's bf16 maps (+ optional fp32 copies)
-                if (okp) {
-                    uint16_t* xo = p.feats + ((size_t)b * 256 + c0) * p.HWp + px;
-                    uint16_t* dxo = xo + (size_t)p.B * 256 * p.HWp;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        xo[(size_t)j * p.HWp] = (uint16_t)(pack_bf16x2(vl[j] + vs[j], 0.f) & 0xFFFFu);
-                        dxo[(size_t)j * p.HWp] = (uint16_t)(pack_bf16x2(vd[j], 0.f) & 0xFFFFu);
-                    }
-                }
-                if (ok && p.x32) {
-                    float* o = p.x32 + ((size_t)b * 256 + c0) * p.HW + px;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[(size_t)j * p.HW] = vl[j] + vs[j];
-                }
-                if (ok && p.d32) {
-                    float* o = p.d32 + ((size_t)b * 256 + c0) * p.HW + px;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[(size_t)j * p.HW] = vd[j];
-                }
+            const int b0 = b, px0 = px;
+            const bool ok0 = px0 < p.HW, okp0 = px0 < p.HWp;
+            uint16_t* xo = p.feats + (size_t)b0 * 256 * hwp + (okp0 ? px0 : 0);
+            float* x32o = p.x32 ? p.x32 + (size_t)b0 * 256 * hw + (ok0 ? px0 : 0) : nullptr;
+            float* d32o = p.x32 ? p.d32 + (size_t)b0 * 256 * hw + (ok0 ? px0 : 0) : nullptr;
+            // software pipeline: the loads of chunk k + 1 are in flight while chunk k is processed
+#pragma unroll 1
+            for (int k = 0; k < H_NCH; k += 2) {
+                load_chunk(vb, y, k + 1);
+                process_chunk(va, k, ok0, okp0, xo, x32o, d32o);
+                if (k + 2 < H_NCH) load_chunk(va, y, k + 2);
+                process_chunk(vb, k + 1, ok0, okp0, xo, x32o, d32o);
+            }
+            t += gridDim.x * 2;
+            if (t < p.n_tiles) {   // the next tile's first chunk streams in under this tile's read-out
+                locate(t);
+                load_chunk(va, y, 0);
             }
             // ---- the three heads of this tile: accumulators -> predictions
             mbar_wait(&dfull[g], tile_i & 1);
             tc_fence_after();
-            float* mp = p.mask_preds + (size_t)b * NM * p.HW + px;
-            float* sp = p.seg_preds + (size_t)b * p.num_classes * p.HW + px;
-            uint32_t* bw = p.bits ? p.bits + ((size_t)b * p.words + (px >> 5)) * 128 : nullptr;
+            float* mp = p.mask_preds + (size_t)b0 * NM * p.HW + px0;
+            float* sp = p.seg_preds + (size_t)b0 * p.num_classes * p.HW + px0;
+            uint32_t* bw = p.bits ? p.bits + ((size_t)b0 * p.words + (px0 >> 5)) * 128 : nullptr;
 #pragma unroll 1
             for (int cb = 0; cb < 5; ++cb) {   // columns [32 cb, 32 cb + 32)
                 uint32_t v[32];
@@ -238,20 +277,20 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
                     const int col = cb * 32 + j;
                     const float f = __uint_as_float(v[j]) + s_bias[col];
                     if (col < H_ROW_SEG) {
-                        const uint32_t bal = __ballot_sync(0xffffffffu, ok && col < p.P && f > 0.f);
+                        const uint32_t bal = __ballot_sync(0xffffffffu, ok0 && col < p.P && f > 0.f);
                         if (lane == j) word = bal;
-                        if (ok && col < p.P) __stcs(mp + (size_t)col * p.HW, f);
+                        if (ok0 && col < p.P) mp[(size_t)col * p.HW] = f;
                     } else if (col < H_ROW_DEP) {
                         const int cls = col - H_ROW_SEG;
-                        if (ok && cls < p.num_classes) {
+                        if (ok0 && cls < p.num_classes) {
                             sp[(size_t)cls * p.HW] = f;
                             if (cls >= p.num_things) mp[(size_t)(p.P + cls - p.num_things) * p.HW] = f;
                         }
                     } else if (col == H_ROW_DEP) {
-                        if (ok) p.depth_pred[(size_t)b * p.HW + px] = f;
+                        if (ok0) p.depth_pred[(size_t)b0 * p.HW + px0] = f;
                     }
                 }
-                if (bw && cb < 4 && (px - lane) < p.HW) bw[cb * 32 + lane] = word;   // rows >= P: zero
+                if (bw && cb < 4 && (px0 - lane) < p.HW) bw[cb * 32 + lane] = word;   // rows >= P: zero
             }
             tc_fence_before();   // the next tile's first MMA overwrites these accumulators
         }
@@ -261,60 +300,32 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
     if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
-// GroupNorm statistics of one (map-image unit, group): 8 consecutive channel rows of Y, then the per-channel
-// (scale, shift) = (gamma * rstd, beta - mean * gamma * rstd).  torch.nn.GroupNorm: biased variance, eps inside the sqrt.
-constexpr int GN_THREADS = 512;
-__global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const float* __restrict__ Y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float2* __restrict__ affine, int B, int HW, float eps) {
-    __shared__ double s_sum[GN_THREADS / 32], s_sq[GN_THREADS / 32];
+// GroupNorm finalisation of one (map-image unit u, group of 8 channels): merge the per-row partial sums the conv
+// epilogue left (fp64), then per channel (scale, shift) = (gamma * rstd, beta - mean * gamma * rstd).
+// torch.nn.GroupNorm: biased variance, eps inside the sqrt.
+__global__ void __launch_bounds__(32)
+gn_finalize_kernel(const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float2* __restrict__ affine, int B, int HW, int cpu, float eps) {
     pdl_wait();
     pdl_launch_dependents();
     const int grp = blockIdx.x;            // 0..31
     const int u = blockIdx.y;              // map * B + b
     const int c0 = grp * 8;
-    const float* src = Y + ((size_t)((c0 >> 7) * 3 * B + u) * 128 + (c0 & 127)) * HW;
-    const size_t total = (size_t)8 * HW;
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    if ((HW & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        const size_t n4 = total / 4;
-        size_t i = threadIdx.x;
-        for (; i + 3 * GN_THREADS < n4; i += 4 * GN_THREADS) {   // four independent 16-byte loads in flight
-            float4 v[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = __ldg(s4 + i + r * GN_THREADS);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                s[r] += (v[r].x + v[r].y) + (v[r].z + v[r].w);
-                ss[r] += (v[r].x * v[r].x + v[r].y * v[r].y) + (v[r].z * v[r].z + v[r].w * v[r].w);
-            }
-        }
-        for (; i < n4; i += GN_THREADS) {
-            const float4 v = __ldg(s4 + i);
-            s[0] += (v.x + v.y) + (v.z + v.w);
-            ss[0] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        }
-    } else {
-        for (size_t i = threadIdx.x; i < total; i += GN_THREADS) {
-            const float v = __ldg(src + i);
-            s[0] += v, ss[0] += v * v;
-        }
+    const int unit = (c0 >> 7) * 3 * B + u;
+    double ds = 0.0, dq = 0.0;
+    for (int i = threadIdx.x; i < 8 * cpu; i += 32) {
+        const float2 v = __ldg(stats + ((size_t)unit * cpu + (i >> 3)) * 128 + (c0 & 127) + (i & 7));
+        ds += (double)v.x, dq += (double)v.y;
     }
-    double ds = ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
-    double dq = ((double)ss[0] + (double)ss[1]) + ((double)ss[2] + (double)ss[3]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ds += __shfl_xor_sync(0xffffffffu, ds, o);
         dq += __shfl_xor_sync(0xffffffffu, dq, o);
     }
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = ds, s_sq[threadIdx.x >> 5] = dq;
-    __syncthreads();
     if (threadIdx.x < 8) {
-        double a = 0.0, q2 = 0.0;
-        for (int w = 0; w < GN_THREADS / 32; ++w) a += s_sum[w], q2 += s_sq[w];
-        const double mean = a / (double)total;
-        double var = q2 / (double)total - mean * mean;
+        const double total = 8.0 * (double)HW;
+        const double mean = ds / total;
+        double var = dq / total - mean * mean;
         if (var < 0.0) var = 0.0;
         const double rstd = 1.0 / sqrt(var + (double)eps);
         const int map = u / B, c = c0 + threadIdx.x;
@@ -327,7 +338,8 @@ gn_stats_kernel(const float* __restrict__ Y, const float* __restrict__ gamma, co
 
 extern "C" size_t pf_kernel_head_workspace_bytes(int B, int HW) {
     if (B <= 0 || HW <= 0) return 0;
-    return (size_t)6 * B * 128 * HW * 4 + (size_t)3 * B * 256 * 8 + 256;
+    // Y fp32 [6B][ceil(HW/32)][128][32] | affine float2 [3B][256] | statistics partials float2 [6B][<= SMs][128]
+    return (size_t)6 * B * ((HW + 31) / 32) * 16384 + (size_t)3 * B * 256 * 8 + (size_t)6 * B * 148 * 128 * 8;
 }
 
 extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, uint16_t* feats, float* x32, float* d32,
@@ -342,6 +354,7 @@ extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, ui
                    w->num_thing_classes >= 0 && w->num_thing_classes <= w->num_classes,
                PF_ERR_ARG, "pf_kernel_head: unsupported head sizes P=%d classes=%d things=%d", w->num_proposals, w->num_classes,
                w->num_thing_classes);
+    PF_REQUIRE((x32 == nullptr) == (d32 == nullptr), PF_ERR_ARG, "pf_kernel_head: x32 and d32 go together");
     PF_REQUIRE(workspace_bytes >= pf_kernel_head_workspace_bytes(B, HW), PF_ERR_WORKSPACE, "pf_kernel_head: workspace too small");
     PF_REQUIRE(((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(maps) | reinterpret_cast<uintptr_t>(feats) |
                  reinterpret_cast<uintptr_t>(w->conv_split) | reinterpret_cast<uintptr_t>(w->head_w)) & 15) == 0,
@@ -349,11 +362,14 @@ extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, ui
     reset_launch_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* Y = static_cast<float*>(workspace);
-    float2* affine = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)6 * B * 128 * HW * 4 + 255) & ~(size_t)255));
+    float2* affine = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)6 * B * ((HW + 31) / 32) * 16384);
 
-    if (int e = conv1x1_maps(maps, w->conv_split, Y, B, HW, HWp, stream)) return e;
-    if (int e = launch_pdl("gn_stats_kernel", gn_stats_kernel, dim3(32, 3 * B), dim3(GN_THREADS), 0, st, (const float*)Y,
-                           w->gn_gamma, w->gn_beta, affine, B, HW, w->gn_eps))
+    float2* stats = affine + (size_t)3 * B * 256;
+    const int cpu = conv1x1_ctas_per_unit(B, HW);
+    PF_REQUIRE(cpu <= 148, PF_ERR_WORKSPACE, "pf_kernel_head: %d CTAs per unit exceed the statistics scratch", cpu);
+    if (int e = conv1x1_maps(maps, w->conv_split, Y, stats, B, HW, HWp, stream)) return e;
+    if (int e = launch_pdl("gn_finalize_kernel", gn_finalize_kernel, dim3(32, 3 * B), dim3(32), 0, st, (const float2*)stats,
+                           w->gn_gamma, w->gn_beta, affine, B, HW, cpu, w->gn_eps))
         return e;
 
     HeadParams p;
@@ -361,7 +377,7 @@ extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, ui
     p.mask_preds = mask_preds, p.seg_preds = seg_preds, p.depth_pred = depth_pred, p.bits = bits;
     p.B = B, p.HW = HW, p.HWp = HWp, p.P = w->num_proposals, p.num_classes = w->num_classes, p.num_things = w->num_thing_classes;
     p.words = (HW + 31) / 32;
-    p.tiles_per_img = (HWp + 127) / 128, p.n_tiles = B * p.tiles_per_img;
+    p.tiles_per_img = (HWp + 127) / 128, p.n_tiles = B * p.tiles_per_img, p.nblk = (HW + 31) / 32;
     CUtensorMap tmap_w;
     if (int e = make_tmap_bf16_2d(&tmap_w, w->head_w, 2 * H_ROWS, 256, 256, H_ROWS, 64)) return e;
     cudaError_t ea = cudaFuncSetAttribute(head_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
