@@ -19,21 +19,24 @@
 //      D = [128 pixels][112 | 32 | 16 columns] per worker group; the group reads it back with tcgen05.ld, adds the
 //      biases, writes mask_preds / seg_preds / depth_pred coalesced along the pixels and ballots the sign bits of the
 //      initial masks (kernel_head.py:314-317) in the layout pf_mask_pool consumes.
-//   Warp roles (320 threads, one persistent CTA per SM): warps 0..3 / 4..7 = two worker groups (TMEM lane quadrant =
-//   warp % 4, each group owns 256 TMEM columns and its own tiles), warps 8 / 9 = their MMA issuers.
+//   Warp roles (576 threads, one persistent CTA per SM): warps 0..7 / 8..15 = two worker groups (each owns 256 TMEM
+//   columns and its own tiles); inside a group two sets of 4 warps (TMEM lane quadrant = warp % 4) share the tile's
+//   pixels and split its channel chunks (even / odd = A buffer 0 / 1); warps 16 / 17 = the groups' MMA issuers.
+//   (With 8 worker warps the kernel was issue-latency-bound: 121 of 175 us remained with every global access off.)
 // HBM-bound: 3 KB of Y read, 1 KB of bf16 features and ~0.5 KB of predictions written per pixel.
 #include "pf_internal.h"
 #include "pf_sm100.cuh"
 
 namespace pf {
 
-constexpr int H_THREADS = 320;
+constexpr int H_THREADS = 576;
 constexpr int H_ROWS = 160;                 // head rows: init_kernels 0..111 | conv_seg 112..143 | conv_direct_depth 144..159
 constexpr int H_ROW_SEG = 112, H_ROW_DEP = 144;
 constexpr int H_KBLK = H_ROWS * 128;        // bytes of one 64-channel block of one weight plane
 constexpr int H_WBYTES = 2 * 4 * H_KBLK;    // hi / lo planes x 4 channel blocks = 163840
 constexpr int H_CH = 16;                    // channels per chunk = one K step of the MMAs
 constexpr int H_NCH = 256 / H_CH;
+constexpr int H_PF = 2;                     // L2 prefetch distance in a set's own chunks
 constexpr int H_DCOLS = 160;                // accumulator columns of a group
 constexpr int H_ACOLS = 48;                 // one A chunk: 3 maps x (hi, lo) x 8 columns; two buffers per group
 constexpr int H_GCOLS = 256;                // TMEM columns per group: 160 + 2 * 48
@@ -58,7 +61,7 @@ struct HeadParams {
     int tiles_per_img, n_tiles, nblk;
 };
 
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }   // the 8 warps of a group
 
 // 16 channels of one map (already normalised + ReLU) -> bf16 hi / lo, two channels per 32-bit column
 __device__ __forceinline__ void st_split8(uint32_t taddr, const float* v) {
@@ -86,7 +89,8 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
     uint64_t* dfull = bars + 9;      // [group] the tile's accumulators are complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role branches below are not treated as divergent
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_w);
         mbar_init(wfull, 1);
@@ -98,7 +102,7 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
         mbar_init(&dfull[1], 1);
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (warp == 16) tmem_alloc<512>(tmem_slot);
     for (int i = threadIdx.x; i < H_ROWS; i += H_THREADS) s_bias[i] = __ldg(p.head_b + i);
     tc_fence_before();
     __syncthreads();
@@ -106,9 +110,9 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
     const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
     pdl_launch_dependents();
 
-    if (warp >= 8) {
+    if (warp >= 16) {
         // ================= MMA issuer of group g (the weights are static: their TMA does not wait for the grid) ====
-        const int g = warp - 8;
+        const int g = warp - 16;
         if (g == 0 && lane == 0) {
             mbar_arrive_expect_tx(wfull, H_WBYTES);
             for (int i = 0; i < 8; ++i)   // (plane, channel block): a [160 rows][64 channels] box
@@ -145,129 +149,113 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
             }
         }
     } else {
-        // ================= worker group g: thread = pixel =================
-        const int g = warp >> 2, q = warp & 3;
-        const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16) + g * H_GCOLS, tA = tD + H_DCOLS;
+        // ================= worker: group g (its own tiles), set (even / odd chunks -> A buffer `set`), quadrant q ====
+        // thread = pixel; the two sets of a group work on the SAME pixels (TMEM lanes) and different channels
+        const int g = warp >> 3, set = (warp >> 2) & 1, q = warp & 3;
+        const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16) + g * H_GCOLS;
+        const uint32_t ta = tD + H_DCOLS + set * H_ACOLS;
+        uint64_t* my_full = &afull[g * 2 + set];
+        uint64_t* my_free = &afree[g * 2 + set];
         float2* aff = s_aff + g * 3 * 256;
-        const int tg = threadIdx.x & 127;
+        const int tg = threadIdx.x & 255;
         const int NM = p.P + p.num_classes - p.num_things;   // channels of mask_preds
-        const size_t feat_branch = (size_t)p.B * 256 * p.HWp;   // feats: x_feats -> depth_feats
+        // Y is pixel-blocked ([unit][32-px block][128 channels][32 px]): a warp reads ONE block, its channel stride is a
+        // compile-time 128 bytes, so the 48 loads of a chunk are immediates off three pointers (the first version spent
+        // 45 % of its instructions on 64-bit index arithmetic, ncu source page).
+        const size_t hw = (size_t)p.HW, hwp = (size_t)p.HWp;
+        const size_t map_stride = (size_t)p.B * p.nblk * 4096;            // Y: from one map's unit to the next map's
+        const size_t half_jump = ((size_t)3 * p.B * p.nblk - 1) * 4096;   // channel 128 of half 0 -> channel 0 of half 1
+        const size_t feat_branch = (size_t)p.B * 256 * p.HWp;             // feats: x_feats -> depth_feats
         pdl_wait();   // Y and the affine table come from the previous kernels
         int cur_b = -1;
-        uint32_t n = 0, tile_i = 0;
-
-        // Y is pixel-blocked ([unit][32-px block][128 channels][32 px]): a warp reads ONE block, its channel stride is a
-        // compile-time 128 bytes, so the 48 loads of a chunk are immediates off three running pointers (the first
-        // version spent 45 % of its instructions on 64-bit index arithmetic, ncu source page).
-        const size_t hw = (size_t)p.HW, hwp = (size_t)p.HWp;
-        const size_t map_stride = (size_t)p.B * p.nblk * 4096;   // Y: from one map's unit to the next map's
-        const size_t half_jump = ((size_t)3 * p.B * p.nblk - 1) * 4096;   // channel 128 of half 0 -> channel 0 of half 1
-        // the three maps' 16 channels of chunk k: 48 independent loads through the running pointer y (map 0)
-        auto load_chunk = [&](float (&v)[48], const float*& y, int k) {
-            const float* y1 = y + map_stride;
-            const float* y2 = y1 + map_stride;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __ldcs(y + j * 32), v[16 + j] = __ldcs(y1 + j * 32), v[32 + j] = __ldcs(y2 + j * 32);
-            y += 16 * 32 + (k == 7 ? half_jump : 0);
+        uint32_t use = 0, tile_i = 0;   // uses of this set's A buffer so far
+        bool pending = false;           // the last chunk is in tensor memory but not yet handed to the MMA warp
+        // The tcgen05.st of a chunk get the following chunk's loads and arithmetic to land before they are retired.
+        auto flush_a = [&]() {
+            if (pending) {
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(my_full);
+                pending = false;
+            }
         };
-        // normalise + ReLU, A operand -> tensor memory, feature maps -> global (xo / x32o / d32o: running pointers)
-        auto process_chunk = [&](float (&v)[48], int k, bool ok, bool okp, uint16_t*& xo, float*& x32o, float*& d32o) {
-            const float2* a0 = aff + k * H_CH;
-#pragma unroll
-            for (int m = 0; m < 3; ++m)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 a = a0[m * 256 + j];
-                    v[m * 16 + j] = fmaxf(fmaf(v[m * 16 + j], a.x, a.y), 0.f);
-                }
-            const uint32_t buf = n & 1;
-            if (n >= 2) {   // the MMAs that read this buffer two chunks ago have completed
-                mbar_wait(&afree[g * 2 + buf], ((n >> 1) - 1) & 1);
-                tc_fence_after();
+        for (int t = blockIdx.x * 2 + g; t < p.n_tiles; t += gridDim.x * 2, ++tile_i) {
+            const int b = t / p.tiles_per_img;
+            const int px = (t - b * p.tiles_per_img) * 128 + q * 32 + lane;
+            const bool ok = px < p.HW, okp = px < p.HWp;
+            if (b != cur_b) {   // (scale, shift) of this image's three maps -> shared memory
+                group_bar(g);
+                for (int i = tg; i < 3 * 256; i += 256)
+                    aff[i] = __ldg(p.affine + ((size_t)(i >> 8) * p.B + b) * 256 + (i & 255));
+                group_bar(g);
+                cur_b = b;
             }
-            const uint32_t ta = tA + buf * H_ACOLS;
-            st_split8(ta, v);
-            st_split8(ta + 16, v + 16);
-            st_split8(ta + 32, v + 32);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&afull[g * 2 + buf]);
-            ++n;
-            // x_feats = sem + loc (kernel_head.py:303), depth_feats: the decoder's bf16 maps (+ optional fp32 copies)
-            if (okp) {
-                uint16_t* xp = xo;
-                uint16_t* dp = xo + feat_branch;
+            int blk = (px - lane) >> 5;   // this warp's 32-pixel block (clamped: rows of A / D beyond HW are never stored)
+            if (blk >= p.nblk) blk = p.nblk - 1;
+            const float* yb = p.Y + ((size_t)b * p.nblk + blk) * 4096 + lane;
+            uint16_t* xb = p.feats + (size_t)b * 256 * hwp + (okp ? px : 0);
+#pragma unroll 1
+            for (int k = set; k < H_NCH; k += 2) {
+                const float* y0 = yb + k * 512 + (k >= 8 ? half_jump : 0);
+                const float* y1 = y0 + map_stride;
+                const float* y2 = y1 + map_stride;
+                float v[48];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint32_t pk = pack_bf16x2(ok ? v[j] + v[16 + j] : 0.f, ok ? v[32 + j] : 0.f);   // pad columns: zero
-                    *xp = (uint16_t)(pk & 0xFFFFu), *dp = (uint16_t)(pk >> 16);
-                    xp += hwp, dp += hwp;
+                for (int j = 0; j < 16; ++j) v[j] = __ldcs(y0 + j * 32), v[16 + j] = __ldcs(y1 + j * 32), v[32 + j] = __ldcs(y2 + j * 32);
+                if (lane == 0 && k + 2 * H_PF < H_NCH) {   // L2 prefetch of this set's chunk H_PF turns ahead (3 x 2 KB)
+                    const float* yc = y0 + 2 * H_PF * 512 + ((k < 8 && k + 2 * H_PF >= 8) ? half_jump : 0);
+                    prefetch_l2_bulk(yc, 2048);
+                    prefetch_l2_bulk(yc + map_stride, 2048);
+                    prefetch_l2_bulk(yc + 2 * map_stride, 2048);
                 }
-            }
-            xo += 16 * hwp;
-            if (x32o) {
-                if (ok) {
-                    float* o = x32o;
-                    float* d = d32o;
+                const float2* a0 = aff + k * H_CH;
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 a = a0[m * 256 + j];
+                        v[m * 16 + j] = fmaxf(fmaf(v[m * 16 + j], a.x, a.y), 0.f);
+                    }
+                flush_a();
+                if (use >= 1) {   // the MMAs that read this buffer on its previous use have completed
+                    mbar_wait(my_free, (use - 1) & 1);
+                    tc_fence_after();
+                }
+                st_split8(ta, v);
+                st_split8(ta + 16, v + 16);
+                st_split8(ta + 32, v + 32);
+                pending = true;
+                ++use;
+                // x_feats = sem + loc (kernel_head.py:303), depth_feats: the decoder's bf16 maps (+ optional fp32 copies)
+                if (okp) {
+                    uint16_t* xp = xb + (size_t)k * 16 * hwp;
+                    uint16_t* dp = xp + feat_branch;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t pk = ok ? pack_bf16x2(v[j] + v[16 + j], v[32 + j]) : 0u;   // pad columns: zero
+                        *xp = (uint16_t)(pk & 0xFFFFu), *dp = (uint16_t)(pk >> 16);
+                        xp += hwp, dp += hwp;
+                    }
+                }
+                if (p.x32 && ok) {
+                    float* o = p.x32 + ((size_t)b * 256 + k * 16) * hw + px;
+                    float* d = p.d32 + ((size_t)b * 256 + k * 16) * hw + px;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         *o = v[j] + v[16 + j], *d = v[32 + j];
                         o += hw, d += hw;
                     }
                 }
-                x32o += 16 * hw, d32o += 16 * hw;
             }
-        };
-
-        float va[48], vb[48];
-        int t = blockIdx.x * 2 + g;
-        int b = 0, px = 0;
-        const float* y = p.Y;
-        auto locate = [&](int tt) {   // tile -> image, this thread's pixel, its first Y row (clamped inside the map)
-            b = tt / p.tiles_per_img;
-            px = (tt - b * p.tiles_per_img) * 128 + q * 32 + lane;
-            int blk = (px - lane) >> 5;   // this warp's 32-pixel block (clamped: rows of A / D beyond HW are never stored)
-            if (blk >= p.nblk) blk = p.nblk - 1;
-            y = p.Y + ((size_t)b * p.nblk + blk) * 4096 + lane;
-        };
-        if (t < p.n_tiles) {
-            locate(t);
-            load_chunk(va, y, 0);
-        }
-        for (; t < p.n_tiles; ++tile_i) {
-            if (b != cur_b) {   // (scale, shift) of this image's three maps -> shared memory
-                group_bar(g);
-                for (int i = tg; i < 3 * 256; i += 128)
-                    aff[i] = __ldg(p.affine + ((size_t)(i >> 8) * p.B + b) * 256 + (i & 255));
-                group_bar(g);
-                cur_b = b;
-            }
-            const int b0 = b, px0 = px;
-            const bool ok0 = px0 < p.HW, okp0 = px0 < p.HWp;
-            uint16_t* xo = p.feats + (size_t)b0 * 256 * hwp + (okp0 ? px0 : 0);
-            float* x32o = p.x32 ? p.x32 + (size_t)b0 * 256 * hw + (ok0 ? px0 : 0) : nullptr;
-            float* d32o = p.x32 ? p.d32 + (size_t)b0 * 256 * hw + (ok0 ? px0 : 0) : nullptr;
-            // software pipeline: the loads of chunk k + 1 are in flight while chunk k is processed
-#pragma unroll 1
-            for (int k = 0; k < H_NCH; k += 2) {
-                load_chunk(vb, y, k + 1);
-                process_chunk(va, k, ok0, okp0, xo, x32o, d32o);
-                if (k + 2 < H_NCH) load_chunk(va, y, k + 2);
-                process_chunk(vb, k + 1, ok0, okp0, xo, x32o, d32o);
-            }
-            t += gridDim.x * 2;
-            if (t < p.n_tiles) {   // the next tile's first chunk streams in under this tile's read-out
-                locate(t);
-                load_chunk(va, y, 0);
-            }
-            // ---- the three heads of this tile: accumulators -> predictions
+            // ---- the three heads of this tile: accumulators -> predictions (set 0: columns 0..95, set 1: 96..159)
+            flush_a();
             mbar_wait(&dfull[g], tile_i & 1);
             tc_fence_after();
-            float* mp = p.mask_preds + (size_t)b0 * NM * p.HW + px0;
-            float* sp = p.seg_preds + (size_t)b0 * p.num_classes * p.HW + px0;
-            uint32_t* bw = p.bits ? p.bits + ((size_t)b0 * p.words + (px0 >> 5)) * 128 : nullptr;
+            float* mp = p.mask_preds + (size_t)b * NM * p.HW + px;
+            float* sp = p.seg_preds + (size_t)b * p.num_classes * p.HW + px;
+            uint32_t* bw = p.bits ? p.bits + ((size_t)b * p.words + (px >> 5)) * 128 : nullptr;
 #pragma unroll 1
-            for (int cb = 0; cb < 5; ++cb) {   // columns [32 cb, 32 cb + 32)
+            for (int cb = set * 3; cb < 3 + set * 2; ++cb) {   // columns [32 cb, 32 cb + 32)
                 uint32_t v[32];
                 tmem_ld32(tD + cb * 32, v);
                 tmem_ld_wait();
@@ -277,27 +265,28 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
                     const int col = cb * 32 + j;
                     const float f = __uint_as_float(v[j]) + s_bias[col];
                     if (col < H_ROW_SEG) {
-                        const uint32_t bal = __ballot_sync(0xffffffffu, ok0 && col < p.P && f > 0.f);
+                        const uint32_t bal = __ballot_sync(0xffffffffu, ok && col < p.P && f > 0.f);
                         if (lane == j) word = bal;
-                        if (ok0 && col < p.P) mp[(size_t)col * p.HW] = f;
+                        if (ok && col < p.P) mp[(size_t)col * p.HW] = f;
                     } else if (col < H_ROW_DEP) {
                         const int cls = col - H_ROW_SEG;
-                        if (ok0 && cls < p.num_classes) {
+                        if (ok && cls < p.num_classes) {
                             sp[(size_t)cls * p.HW] = f;
                             if (cls >= p.num_things) mp[(size_t)(p.P + cls - p.num_things) * p.HW] = f;
                         }
                     } else if (col == H_ROW_DEP) {
-                        if (ok0) p.depth_pred[(size_t)b0 * p.HW + px0] = f;
+                        if (ok) p.depth_pred[(size_t)b * p.HW + px] = f;
                     }
                 }
-                if (bw && cb < 4 && (px0 - lane) < p.HW) bw[cb * 32 + lane] = word;   // rows >= P: zero
+                if (bw && cb < 4 && (px - lane) < p.HW) bw[cb * 32 + lane] = word;   // rows >= P: zero
             }
-            tc_fence_before();   // the next tile's first MMA overwrites these accumulators
+            tc_fence_before();
+            group_bar(g);   // both sets have read D: the next tile's first MMA may overwrite it
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem_base);
+    if (warp == 16) tmem_dealloc<512>(tmem_base);
 }
 
 // GroupNorm finalisation of one (map-image unit u, group of 8 channels): merge the per-row partial sums the conv

@@ -53,6 +53,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): no registers, no completion
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // polling with a back-off: for a warp whose wake-up latency does not matter but whose issue slots do
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
