@@ -129,7 +129,7 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
 #pragma unroll 1
             for (int k = 0; k < H_NCH; ++k, ++n) {
                 const uint32_t buf = n & 1;
-                mbar_wait_backoff(&afull[g * 2 + buf], (n >> 1) & 1, 64);   // shares a scheduler with two worker warps
+                mbar_wait_backoff(&afull[g * 2 + buf], (n >> 1) & 1, 32);   // shares a scheduler with two worker warps
                 tc_fence_after();
                 const int c0 = k * H_CH;
                 const uint64_t koff = (uint64_t)(((c0 & 63) * 2) >> 4);
@@ -170,7 +170,6 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
         int cur_b = -1;
         uint32_t use = 0, tile_i = 0;   // uses of this set's A buffer so far
         bool pending = false;           // the last chunk is in tensor memory but not yet handed to the MMA warp
-        // The tcgen05.st of a chunk get the following chunk's loads and arithmetic to land before they are retired.
         auto flush_a = [&]() {
             if (pending) {
                 tmem_st_wait();
@@ -216,7 +215,6 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
                         const float2 a = a0[m * 256 + j];
                         v[m * 16 + j] = fmaxf(fmaf(v[m * 16 + j], a.x, a.y), 0.f);
                     }
-                flush_a();
                 if (use >= 1) {   // the MMAs that read this buffer on its previous use have completed
                     mbar_wait(my_free, (use - 1) & 1);
                     tc_fence_after();
@@ -246,6 +244,7 @@ head_apply_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadParams p
                         o += hw, d += hw;
                     }
                 }
+                flush_a();   // the tcgen05.st above had the global stores to land: hand the chunk to the MMA warp
             }
             // ---- the three heads of this tile: accumulators -> predictions (set 0: columns 0..95, set 1: 96..159)
             flush_a();
