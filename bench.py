@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
+    ap.add_argument('--no-kernel-head', action='store_true', help='skip the (non-headline) KernelHead-tail timing')
     ap.add_argument('--no-graph', action='store_true', help='launch every step from the host instead of replaying a CUDA graph')
     ap.add_argument('--splits', type=int, default=None, help='batch windows decoded concurrently (default: 1)')
     return ap.parse_args()
@@ -317,7 +318,55 @@ def run_ours(args, rank, world, local_rank):
         if 'cpu_baseline' in line and 'cpu_port_ms_per_frame' in line['postprocess']:
             per_frame = 1e3 / line['cpu_baseline']['value'] + line['postprocess']['cpu_port_ms_per_frame']
             line['e2e_simple_test']['cpu_port_frames_per_s'] = 1e3 / per_frame
+    if not args.no_kernel_head and world == 1:
+        torch.cuda.empty_cache()
+        line['kernel_head'] = kernel_head_timing(args, B, dev, pk['hbm'], cpu=not args.no_cpu_baseline)
     emit(line)
+
+
+def kernel_head_timing(args, B, dev, peak_gbs, cpu=True):
+    """NOT part of the headline metric: the producer of the decoder's inputs, i.e. the
+    tail of KernelHead._decode_init_proposals (kernel_head.py:250-336) = pf_kernel_head + pf_mask_pool +
+    pf_init_proposals on B frames, device time with CUDA events over rotating input sets (3 x 201 MB of bf16 maps at
+    B=4 > L2), next to oracle/kernel_head_ref.py on the host cores (one frame)."""
+    from oracle import kernel_head_ref, synth
+    from polyphonicformer_b200.kernel_head import KernelHeadTail
+    H, W = args.height // 8, args.width // 8
+    HW = H * W
+    sd = synth.synth_kernel_head_state(0)
+    tail = KernelHeadTail(sd, dev)
+    g = torch.Generator(device='cpu').manual_seed(7)
+    sets = [torch.relu(torch.randn(3, B, C, HW, generator=g)).to(torch.bfloat16).to(dev) for _ in range(3)]
+    for i in range(3):
+        tail.forward(sets[i % 3], H, W)
+    torch.cuda.synchronize()
+    n = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n):
+        tail.forward(sets[i % 3], H, W)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    # algorithmic bytes per frame: three bf16 maps in, two bf16 maps out, 111 + 19 + 1 fp32 prediction maps out
+    alg = B * HW * (3 * C * 2 + 2 * C * 2 + (N_KERNELS + synth.NUM_CLASSES + 1) * 4)
+    res = dict(ms_per_call=ms, frames_per_s=B / ms * 1e3, batch=B, launches=tail.last_launches,
+               algorithmic_MB=alg / 1e6, achieved_GBps=alg / ms / 1e6, frac_of_measured_hbm_peak=alg / ms / 1e6 / peak_gbs,
+               what='pf_kernel_head (1x1 convs + GN + ReLU + prediction heads) + pf_mask_pool + pf_init_proposals, '
+                    '%d frames of %dx%d maps; intermediate conv output (fp32, %.0f MB written + read) not counted as '
+                    'algorithmic' % (B, H, W, B * 3 * C * HW * 4 / 1e6))
+    del sets
+    if cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        maps = [torch.relu(torch.randn(1, C, H, W, generator=g)) for _ in range(3)]
+        with torch.no_grad():
+            kernel_head_ref.decode_init_proposals(sd, maps)
+            t0 = time.perf_counter()
+            kernel_head_ref.decode_init_proposals(sd, maps)
+            res['cpu_port_ms_per_frame'] = 1e3 * (time.perf_counter() - t0)
+            res['cpu_cores'] = cores
+    return res
 
 
 def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, dev):
