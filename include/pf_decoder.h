@@ -260,6 +260,18 @@ int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, uint16_t* fea
                    float* mask_preds, float* seg_preds, float* depth_pred, uint32_t* bits, void* workspace,
                    size_t workspace_bytes, int B, int HW, int HWp, void* stream);
 
+/* ---- the last step of SemanticFPN (partial) ------------------------------------------
+ * SemanticFPNWrapper.forward, polyphonic/funcs/semantic_fpn.py:221-229: conv_pred and the two aux_convs (mmcv
+ * ConvModule 1x1 conv without bias + GN32 + ReLU, built :159-178) applied to the SAME fused map -- the three
+ * localization_feats pf_kernel_head consumes.
+ *   conv_split / gn_gamma / gn_beta   as in struct pf_head_weights, for (conv_pred, aux_convs.0, aux_convs.1)
+ *   fused    bf16 [B][256][HWp]       feature_add_all_level in the storage dtype (pf_cast_maps)
+ *   maps     out bf16 [3][B][256][HWp];  maps32 optional fp32 [3][B][256][HW] (may be NULL)
+ *   workspace: pf_kernel_head_workspace_bytes(B, HW) bytes */
+int pf_fpn_pred(const uint16_t* conv_split, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                const uint16_t* fused, uint16_t* maps, float* maps32, void* workspace, size_t workspace_bytes, int B,
+                int HW, int HWp, void* stream);
+
 /* debug only: int64 device buffer [16 + 16*capacity], zero-filled by the caller; CTA (0,0,0) of every GEMM launch of
  * the small-N block appends 16 %globaltimer samples (see scripts/k2_timeline.py).  NULL switches it off. */
 int pf_debug_timeline(long long* device_buffer);

@@ -16,6 +16,17 @@ def conv_gn_relu(sd, name, x, num_groups=32, eps=1e-5):
     return F.relu(y)
 
 
+def fpn_pred(sd, fused, num_groups=32, eps=1e-5):
+    """SemanticFPNWrapper.forward, polyphonic/funcs/semantic_fpn.py:221-229 with num_aux_convs=2: conv_pred and the two
+    aux_convs (ConvModule 1x1 + GN32 + ReLU, built :159-178) on the fused map.  Returns [out, aux0, aux1]."""
+    outs = []
+    for name in ('conv_pred', 'aux_convs.0', 'aux_convs.1'):
+        y = F.conv2d(fused, sd[name + '.conv.weight'])
+        y = F.group_norm(y, num_groups, sd[name + '.gn.weight'], sd[name + '.gn.bias'], eps)
+        outs.append(F.relu(y))
+    return outs
+
+
 def decode_init_proposals(sd, localization_feats, num_thing_classes=8):
     """kernel_head.py:250-336 in eval mode with the shipped configuration (cat_stuff_mask, use_binary,
     proposal_feats_with_obj, no feat_refine, no semantic_aspp).  Returns the reference's 9-tuple as a dict."""

@@ -165,6 +165,21 @@ def run_kernel_head_case(head, B, H, W):
     return best
 
 
+FPN_PRED_CASES = [('fpn_pred_b2_h16_w24_s0', 2, 16, 24, 0), ('fpn_pred_b1_h10_w13_s1', 1, 10, 13, 1)]
+
+
+def run_fpn_pred_case(rpn, B, H, W, seed):
+    """semantic_fpn.py:221-229 -- the reference's own conv_pred / aux_convs modules on a fixed fused map."""
+    fpn = rpn.localization_fpn
+    sd = synth.synth_fpn_pred_state(seed)
+    r = fpn.load_state_dict(sd, strict=False)
+    assert not r.unexpected_keys and all(k.startswith('convs_all_levels.') or k.startswith('positional') for k in r.missing_keys), r
+    fused = synth.synth_fused_map(B, H, W, seed)
+    with torch.no_grad():
+        outs = [fpn.conv_pred(fused)] + [conv(fused) for conv in fpn.aux_convs]
+    return dict(maps=torch.stack(outs).numpy().astype(np.float32))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -181,6 +196,10 @@ def main():
         np.savez_compressed(os.path.join(GOLD, name + '.npz'), h=h, w=w, seed=seed, **out)
         print(name, out['panoptic'].shape, 'segments', len(out['seg']), np.unique(out['panoptic']))
     rpn = build_reference_rpn_head()
+    for name, B, H, W, seed in FPN_PRED_CASES:   # before the kernel-head cases replace localization_fpn
+        out = run_fpn_pred_case(rpn, B, H, W, seed)
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), B=B, H=H, W=W, seed=seed, **out)
+        print(name, out['maps'].shape)
     for name, B, H, W in KERNEL_HEAD_CASES:
         seed, margin, out = run_kernel_head_case(rpn, B, H, W)
         path = os.path.join(GOLD, name + '.npz')

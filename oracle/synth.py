@@ -188,3 +188,20 @@ def synth_fpn_maps(B, H, W, seed=0):
         t = torch.nn.functional.interpolate(coarse, size=(H, W), mode='bilinear', align_corners=False)
         maps.append(bf16_round(torch.relu(scale * (t + 0.7 * torch.randn(B, C, H, W, generator=g)) + 0.2)))
     return maps
+
+
+def synth_fpn_pred_state(seed=0):
+    """conv_pred + two aux_convs of SemanticFPNWrapper (semantic_fpn.py:159-178)."""
+    out = {}
+    for n in ('conv_pred', 'aux_convs.0', 'aux_convs.1'):
+        out[n + '.conv.weight'] = synth_tensor('fpn.' + n + '.conv.weight', (C, C, 1, 1), seed)
+        out[n + '.gn.weight'] = synth_tensor('fpn.' + n + '.gn.weight', (C,), seed)
+        out[n + '.gn.bias'] = synth_tensor('fpn.' + n + '.gn.bias', (C,), seed)
+    return out
+
+
+def synth_fused_map(B, H, W, seed=0):
+    """feature_add_all_level: the sum of four post-ReLU level maps (semantic_fpn.py:216-219), pre-rounded to bf16."""
+    g = _gen(f'fused.{B}.{H}.{W}', seed)
+    t = sum(torch.relu(torch.randn(B, C, H, W, generator=g) * s) for s in (1.0, 0.7, 0.5, 0.4))
+    return bf16_round(t)

@@ -54,6 +54,8 @@ class HeadWeights(Structure):
 
 _SIGS = {
     'pf_cast_maps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pf_fpn_pred': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                            c_int, c_int, c_void_p]),
     'pf_kernel_head_workspace_bytes': (c_size_t, [c_int, c_int]),
     'pf_kernel_head': (c_int, [POINTER(HeadWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),

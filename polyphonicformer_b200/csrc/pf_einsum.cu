@@ -356,7 +356,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
 
 // pf_kernel_head's three 1x1 convolutions (kernel_head.py:250-251, 264-265, 277-278; ConvModule without bias) as ONE
 // launch of the einsum kernel: unit u = half * 3B + map * B + b computes rows [128 * half, 128 * half + 128) of
-// W_map . maps[map][b]; conv_split holds the six (half, map) row blocks as bf16 hi / lo planes [6][2][128][256].
+// W_map . maps[map % n_inputs][b]; conv_split holds the six (half, map) row blocks as bf16 hi / lo planes [6][2][128][256].
 // Y: fp32 [6B][ceil(HW/32)][128][32] (pixel-blocked).
 int pf::conv1x1_ctas_per_unit(int B, int HW) {
     const int tile = 64;
@@ -365,17 +365,17 @@ int pf::conv1x1_ctas_per_unit(int B, int HW) {
     return cpu < 1 ? 1 : (cpu > tiles ? tiles : cpu);
 }
 
-int pf::conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y, float2* stats, int B, int HW, int HWp,
-                     void* stream) {
+int pf::conv1x1_maps(const uint16_t* maps, int n_inputs, const uint16_t* conv_split, float* Y, float2* stats, int B, int HW,
+                     int HWp, void* stream) {
     using namespace pf;
     const int n_units = 6 * B;
     CUtensorMap tmap;
-    if (int e = make_tmap_bf16_2d(&tmap, maps, (uint64_t)3 * B * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
+    if (int e = make_tmap_bf16_2d(&tmap, maps, (uint64_t)n_inputs * B * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
     EinsumParams p;
     p.kern = conv_split, p.kbias = nullptr, p.logits = Y, p.bits = nullptr;
     p.N = 128, p.HW = HW, p.words = (HW + 31) / 32, p.B = n_units;
     p.Btot = n_units, p.b0 = 0, p.early_feats = 0, p.unit0 = 0;
-    p.kdiv = B, p.fmod = 3 * B, p.stats = stats;
+    p.kdiv = B, p.fmod = n_inputs * B, p.stats = stats;   // n_inputs = 1: the three convolutions read the same map
     // blocked output: 16 KB [128 rows][32 px] blocks, written whole by the TMA stores (no row-pitch constraint) and
     // read back by head_apply_kernel with a compile-time channel stride
     const int nblk = (HW + 31) / 32;

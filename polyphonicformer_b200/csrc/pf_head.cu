@@ -322,6 +322,45 @@ gn_finalize_kernel(const float2* __restrict__ stats, const float* __restrict__ g
     }
 }
 
+// GroupNorm + ReLU of the blocked conv output -> bf16 maps [3][B][256][HWp] (+ optional fp32 [3][B][256][HW]): the
+// elementwise tail of pf_fpn_pred.  One warp per 16 KB block [128 channels][32 px]: a lane owns 4 consecutive pixels
+// (one float4 in, 8 bytes of bf16 out), 8 lanes a channel row, 4 rows per warp instruction.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ Y, const float2* __restrict__ affine, uint16_t* __restrict__ maps,
+                float* __restrict__ maps32, int B, int HW, int HWp, int nblk) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nblocks = (long long)6 * B * nblk;
+    for (long long blkid = (long long)blockIdx.x * 8 + warp; blkid < nblocks; blkid += (long long)gridDim.x * 8) {
+        const int unit = (int)(blkid / nblk), blk = (int)(blkid - (long long)unit * nblk);
+        const int half = unit / (3 * B), u = unit - half * 3 * B;   // u = map * B + b
+        const float4* src = reinterpret_cast<const float4*>(Y + (size_t)blkid * 4096);
+        const float2* af = affine + (size_t)u * 256 + half * 128;
+        const int px = blk * 32 + (lane & 7) * 4;
+        uint16_t* dst = maps + ((size_t)u * 256 + half * 128) * HWp + px;
+        float* dst32 = maps32 ? maps32 + ((size_t)u * 256 + half * 128) * HW + px : nullptr;
+#pragma unroll 4
+        for (int r0 = 0; r0 < 128; r0 += 4) {
+            const int r = r0 + (lane >> 3);
+            const float4 v = __ldcs(src + r * 8 + (lane & 7));
+            const float2 a = __ldg(af + r);
+            float o[4] = {fmaxf(fmaf(v.x, a.x, a.y), 0.f), fmaxf(fmaf(v.y, a.x, a.y), 0.f), fmaxf(fmaf(v.z, a.x, a.y), 0.f),
+                          fmaxf(fmaf(v.w, a.x, a.y), 0.f)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (px + i >= HW) o[i] = 0.f;   // pad columns [HW, HWp) are zero
+            if (px + 3 < HWp)                   // HWp % 8 == 0 and px % 4 == 0: all four or none
+                *reinterpret_cast<uint2*>(dst + (size_t)r * HWp) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+            if (dst32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (px + i < HW) dst32[(size_t)r * HW + i] = o[i];
+            }
+        }
+    }
+}
+
 }  // namespace pf
 
 extern "C" size_t pf_kernel_head_workspace_bytes(int B, int HW) {
@@ -355,7 +394,7 @@ extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, ui
     float2* stats = affine + (size_t)3 * B * 256;
     const int cpu = conv1x1_ctas_per_unit(B, HW);
     PF_REQUIRE(cpu <= 148, PF_ERR_WORKSPACE, "pf_kernel_head: %d CTAs per unit exceed the statistics scratch", cpu);
-    if (int e = conv1x1_maps(maps, w->conv_split, Y, stats, B, HW, HWp, stream)) return e;
+    if (int e = conv1x1_maps(maps, 3, w->conv_split, Y, stats, B, HW, HWp, stream)) return e;
     if (int e = launch_pdl("gn_finalize_kernel", gn_finalize_kernel, dim3(32, 3 * B), dim3(32), 0, st, (const float2*)stats,
                            w->gn_gamma, w->gn_beta, affine, B, HW, cpu, w->gn_eps))
         return e;
@@ -373,4 +412,34 @@ extern "C" int pf_kernel_head(const pf_head_weights* w, const uint16_t* maps, ui
     int grid = num_sms();
     if (grid * 2 > p.n_tiles) grid = (p.n_tiles + 1) / 2;
     return launch_pdl("head_apply_kernel", head_apply_kernel, dim3(grid), dim3(H_THREADS), H_SMEM, st, tmap_w, p);
+}
+
+extern "C" int pf_fpn_pred(const uint16_t* conv_split, const float* gn_gamma, const float* gn_beta, float gn_eps,
+                           const uint16_t* fused, uint16_t* maps, float* maps32, void* workspace, size_t workspace_bytes,
+                           int B, int HW, int HWp, void* stream) {
+    using namespace pf;
+    if (int e = check_device()) return e;
+    PF_REQUIRE(conv_split && gn_gamma && gn_beta && fused && maps && workspace, PF_ERR_ARG, "pf_fpn_pred: null pointer");
+    PF_REQUIRE(B > 0 && HW > 0 && HWp >= HW && HWp % 8 == 0, PF_ERR_ARG, "pf_fpn_pred: bad shape B=%d HW=%d HWp=%d", B, HW, HWp);
+    PF_REQUIRE(workspace_bytes >= pf_kernel_head_workspace_bytes(B, HW), PF_ERR_WORKSPACE, "pf_fpn_pred: workspace too small");
+    PF_REQUIRE(((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(fused) | reinterpret_cast<uintptr_t>(maps) |
+                 reinterpret_cast<uintptr_t>(conv_split)) & 15) == 0,
+               PF_ERR_ALIGN, "pf_fpn_pred: pointers must be 16-byte aligned");
+    reset_launch_count();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nblk = (HW + 31) / 32;
+    float* Y = static_cast<float*>(workspace);
+    float2* affine = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)6 * B * nblk * 16384);
+    float2* stats = affine + (size_t)3 * B * 256;
+    const int cpu = conv1x1_ctas_per_unit(B, HW);
+    PF_REQUIRE(cpu <= 148, PF_ERR_WORKSPACE, "pf_fpn_pred: %d CTAs per unit exceed the statistics scratch", cpu);
+    if (int e = conv1x1_maps(fused, 1, conv_split, Y, stats, B, HW, HWp, stream)) return e;
+    if (int e = launch_pdl("gn_finalize_kernel", gn_finalize_kernel, dim3(32, 3 * B), dim3(32), 0, st, (const float2*)stats,
+                           gn_gamma, gn_beta, affine, B, HW, cpu, gn_eps))
+        return e;
+    long long nblocks = (long long)6 * B * nblk;
+    int grid = (int)((nblocks + 7) / 8);
+    if (grid > 8 * num_sms()) grid = 8 * num_sms();
+    return launch_pdl("gn_apply_kernel", gn_apply_kernel, dim3(grid), dim3(256), 0, st, (const float*)Y, (const float2*)affine,
+                      maps, maps32, B, HW, HWp, nblk);
 }

@@ -38,8 +38,8 @@ int mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const float*
 // the three 1x1 convolutions of pf_kernel_head as one einsum launch (pf_einsum.cu)
 // stats: [6B][conv1x1_ctas_per_unit][128] per-row (sum, sum of squares) partials for the GroupNorm that follows
 int conv1x1_ctas_per_unit(int B, int HW);
-int conv1x1_maps(const uint16_t* maps, const uint16_t* conv_split, float* Y, float2* stats, int B, int HW, int HWp,
-                 void* stream);
+int conv1x1_maps(const uint16_t* maps, int n_inputs, const uint16_t* conv_split, float* Y, float2* stats, int B, int HW,
+                 int HWp, void* stream);
 
 // Launch with programmatic stream serialization (PDL): the kernel may begin before its predecessor in the stream has
 // finished; it must execute griddepcontrol.wait (pdl_wait) before touching anything the predecessor wrote.

@@ -30,12 +30,7 @@ class PackedKernelHead:
     def __init__(self, sd, device, num_thing_classes=8, gn_eps=1e-5):
         g = lambda k: sd[k].detach().to('cpu', torch.float32)
         conv = [g(f'{m}_convs.0.conv.weight').reshape(PF_C, PF_C) for m in ('loc', 'seg', 'depth')]
-        blocks = []
-        for half in range(2):
-            for m in range(3):
-                hi, lo = _hi_lo(conv[m][128 * half:128 * half + 128])
-                blocks += [hi, lo]
-        self.conv_split = torch.stack(blocks).contiguous().to(device)            # [6*2][128][256]
+        self.conv_split = _conv_split(conv).to(device)                            # [6*2][128][256]
         self.gn_gamma = torch.stack([g(f'{m}_convs.0.gn.weight') for m in ('loc', 'seg', 'depth')]).contiguous().to(device)
         self.gn_beta = torch.stack([g(f'{m}_convs.0.gn.bias') for m in ('loc', 'seg', 'depth')]).contiguous().to(device)
         init_k = g('init_kernels.weight').reshape(-1, PF_C)
@@ -63,6 +58,54 @@ class PackedKernelHead:
                                   gn_beta=self.gn_beta.data_ptr(), head_w=self.head_w.data_ptr(),
                                   head_b=self.head_b.data_ptr(), num_proposals=self.num_proposals,
                                   num_classes=self.num_classes, num_thing_classes=num_thing_classes, gn_eps=gn_eps)
+
+
+def _conv_split(convs):
+    """three fp32 [256][256] 1x1-conv matrices -> bf16 [6*2][128][256]: block (half * 3 + map), hi plane then lo plane"""
+    blocks = []
+    for half in range(2):
+        for m in range(3):
+            hi, lo = _hi_lo(convs[m][128 * half:128 * half + 128])
+            blocks += [hi, lo]
+    return torch.stack(blocks).contiguous()
+
+
+class FpnPred:
+    """The last step of ``SemanticFPNWrapper.forward`` (polyphonic/funcs/semantic_fpn.py:221-229): ``conv_pred`` and the
+    two ``aux_convs`` (1x1 conv + GN32 + ReLU each) on the fused multi-level map -> the three ``localization_feats`` in
+    the bf16 layout ``KernelHeadTail.forward`` consumes.  State-dict keys (prefix ``rpn_head.localization_fpn.``):
+    conv_pred.{conv.weight, gn.weight, gn.bias}, aux_convs.{0,1}.{conv.weight, gn.weight, gn.bias}."""
+    NAMES = ('conv_pred', 'aux_convs.0', 'aux_convs.1')
+
+    def __init__(self, state_dict, device, gn_eps=1e-5):
+        _cabi.load()
+        self.device = torch.device(device)
+        g = lambda k: state_dict[k].detach().to('cpu', torch.float32)
+        self.conv_split = _conv_split([g(n + '.conv.weight').reshape(PF_C, PF_C) for n in self.NAMES]).to(self.device)
+        self.gn_gamma = torch.stack([g(n + '.gn.weight') for n in self.NAMES]).contiguous().to(self.device)
+        self.gn_beta = torch.stack([g(n + '.gn.bias') for n in self.NAMES]).contiguous().to(self.device)
+        self.gn_eps = gn_eps
+        self._ws = None
+
+    def forward(self, fused, want_fp32=False):
+        """fused: fp32 [B,256,H,W] (feature_add_all_level).  Returns (maps bf16 [3][B][256][HWp], maps32 or None)."""
+        lib = _cabi.load()
+        B, _, H, W = fused.shape
+        HW = H * W
+        HWp = round_up(HW, 8)
+        st = _stream_ptr()
+        fused = fused.to(self.device, torch.float32).contiguous()
+        fb = torch.empty((B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
+        _cabi.call('pf_cast_maps', _ptr(fused), _ptr(fb), B * PF_C, HW, HWp, st)
+        maps = torch.empty((3, B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
+        maps32 = torch.empty((3, B, PF_C, H, W), dtype=torch.float32, device=self.device) if want_fp32 else None
+        nbytes = lib.pf_kernel_head_workspace_bytes(B, HW)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _cabi.call('pf_fpn_pred', _ptr(self.conv_split), _ptr(self.gn_gamma), _ptr(self.gn_beta), self.gn_eps, _ptr(fb),
+                   _ptr(maps), _ptr(maps32), _ptr(self._ws), nbytes, B, HW, HWp, st)
+        self.last_launches = lib.pf_last_launch_count()
+        return maps, maps32
 
 
 class KernelHeadTail:

@@ -16,6 +16,13 @@ cap() {  # name, kernel regex, skip, count
     rm -f $OUT/${TAG}_$1.ncu-rep
     tail -1 $OUT/${TAG}_$1.log
 }
+# KernelHead tail (pf_kernel_head): launch list + one full capture of its three kernels
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches_kernel_head.csv \
+    python scripts/head_timing.py 4 > $OUT/${TAG}_launches_kernel_head.log 2>&1
+ncu --set full --clock-control none -k regex:"head_apply|gn_finalize|einsum_kernel" -s 9 -c 3 -o $OUT/${TAG}_kernel_head \
+    python scripts/head_timing.py 4 > $OUT/${TAG}_kernel_head.log 2>&1
+ncu -i $OUT/${TAG}_kernel_head.ncu-rep --page raw --csv > $OUT/${TAG}_kernel_head.raw.csv 2>/dev/null
+rm -f $OUT/${TAG}_kernel_head.ncu-rep
 cap stream "pool_kernel|einsum_kernel|upsample2x|binarise" 9 9
 cap tcgemm "tcgemm" 27 9
 cap helpers "prep_kernel|sumln_kernel|attention_kernel" 9 3

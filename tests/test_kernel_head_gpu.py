@@ -142,3 +142,51 @@ def test_kernel_head_feeds_the_decoder(dev):
         # not the parity gate (that is asserted above on identical inputs): here a 1e-5 difference in an fp32 feature
         # can land on the other side of a bf16 rounding boundary (4e-3 of that element) before the decoder starts
         assert l2 < 3e-3, (k, l2, mx)
+
+
+@pytest.mark.parametrize('name', ['fpn_pred_b2_h16_w24_s0', 'fpn_pred_b1_h10_w13_s1'])
+def test_fpn_pred_matches_reference_golden(dev, name):
+    """pf_fpn_pred against the real SemanticFPNWrapper.conv_pred / aux_convs (semantic_fpn.py:221-229)."""
+    from polyphonicformer_b200.kernel_head import FpnPred
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    B, H, W, seed = int(g['B']), int(g['H']), int(g['W']), int(g['seed'])
+    fp = FpnPred(synth.synth_fpn_pred_state(seed), dev)
+    maps, maps32 = fp.forward(synth.synth_fused_map(B, H, W, seed).to(dev), want_fp32=True)
+    torch.cuda.synchronize()
+    l2, mx = rel_err(maps32.cpu(), g['maps'])
+    assert l2 < TIGHT and mx < TIGHT, (name, l2, mx)
+    HW = H * W
+    assert torch.equal(maps[..., :HW].float(), maps32.reshape(3, B, 256, HW).to(torch.bfloat16).float())
+    assert maps.shape[-1] == HW or float(maps[..., HW:].float().abs().max()) == 0.0
+    assert fp.last_launches == 3   # einsum(conv + statistics), gn_finalize, gn_apply
+
+
+def test_fpn_pred_full_size_and_chain(dev):
+    """1024x2048 frame (128x256 map): pf_fpn_pred against the restatement on the device, then straight into the
+    KernelHead tail (bf16 maps in the layout pf_kernel_head consumes)."""
+    from polyphonicformer_b200.kernel_head import FpnPred, KernelHeadTail
+    B, H, W, seed = 1, 128, 256, 2
+    sd = synth.synth_fpn_pred_state(seed)
+    fused = synth.synth_fused_map(B, H, W, seed)
+    fp = FpnPred(sd, dev)
+    maps, maps32 = fp.forward(fused.to(dev), want_fp32=True)
+    torch.cuda.synchronize()
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = torch.stack(ref.fpn_pred({k: v.to(dev) for k, v in sd.items()}, fused.to(dev)))
+            l2, mx = rel_err(maps32.cpu(), want.cpu())
+            assert l2 < TIGHT and mx < TIGHT, (l2, mx)
+            hsd = synth.synth_kernel_head_state(seed)
+            tail = KernelHeadTail(hsd, dev)
+            out = tail.forward(maps, H, W, want_fp32_feats=True)
+            torch.cuda.synchronize()
+            HW = H * W
+            rounded = [maps[m, :, :, :HW].float().reshape(B, 256, H, W) for m in range(3)]
+            want_t = ref.decode_init_proposals({k: v.to(dev) for k, v in hsd.items()}, rounded)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for k in ('x_feats', 'depth_feats', 'mask_preds', 'seg_preds', 'depth_pred'):
+        l2, mx = rel_err(out[k].cpu(), want_t[k].cpu())
+        assert l2 < TIGHT and mx < TIGHT, (k, l2, mx)

@@ -101,3 +101,15 @@ def test_kernel_head_restatement_matches_reference(name):
         l2, mx = rel_err(out[k], g[k])
         assert l2 < 1e-6 and mx < 1e-6, (name, k, l2, mx)
     assert float(g['margin']) > 5e-5
+
+
+@pytest.mark.parametrize('name', ['fpn_pred_b2_h16_w24_s0', 'fpn_pred_b1_h10_w13_s1'])
+def test_fpn_pred_restatement_matches_reference(name):
+    """oracle/kernel_head_ref.fpn_pred against the real SemanticFPNWrapper conv_pred / aux_convs (semantic_fpn.py:221-229)."""
+    from oracle import kernel_head_ref
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    B, H, W, seed = int(g['B']), int(g['H']), int(g['W']), int(g['seed'])
+    with torch.no_grad():
+        out = torch.stack(kernel_head_ref.fpn_pred(synth.synth_fpn_pred_state(seed), synth.synth_fused_map(B, H, W, seed)))
+    l2, mx = rel_err(out, g['maps'])
+    assert l2 < 1e-6 and mx < 1e-6, (name, l2, mx)
