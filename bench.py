@@ -180,6 +180,50 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
+class NvmlClockSampler:
+    """In-process sampler (a thread polling NVML every ~2 ms between start and stop): every sample lies inside the
+    busy region by construction, however short it is.  `nvidia-smi -lms` (ClockSampler) delivers a sample only every
+    ~100 ms on some boxes, which can miss a 110 ms timed region entirely; it stays as the fallback."""
+    BITS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
+
+    def __init__(self, gpu):
+        import threading
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        self.sm, self.bits, self.run = [], 0, True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        nv = self.nv
+        reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.run:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.bits |= int(reasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self, window=None):
+        self.run = False
+        self.t.join()
+        if not self.sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        sm = sorted(self.sm)
+        return dict(sm_mhz=float(sm[len(sm) // 2]), sm_max_mhz=float(self.max_mhz),
+                    reasons=sorted(n for b, n in self.BITS if self.bits & b), samples=len(sm), source='nvml thread, 2 ms period')
+
+
+def make_clock_sampler(gpu):
+    try:
+        return NvmlClockSampler(gpu)
+    except Exception:
+        return ClockSampler(gpu)
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def flush_l2(buf):
     buf.zero_()
@@ -250,13 +294,13 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # samples span the warm-up and the timed steps
-    if sampler:
-        time.sleep(0.25)                                       # let nvidia-smi start before the GPU gets busy
-    t_busy0 = time.time()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    sampler = make_clock_sampler(local_rank) if rank == 0 else None   # samples the timed steps only
+    if isinstance(sampler, ClockSampler):
+        time.sleep(0.25)                                       # let nvidia-smi start before the GPU gets busy
+    t_busy0 = time.time()
     launches_per_step = eng.last_launches + 2               # + the two 57 KB proposal copies (torch memcpy kernels)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
