@@ -362,6 +362,13 @@ def run_ours(args, rank, world, local_rank):
         if 'cpu_baseline' in line and 'cpu_port_ms_per_frame' in line['postprocess']:
             per_frame = 1e3 / line['cpu_baseline']['value'] + line['postprocess']['cpu_port_ms_per_frame']
             line['e2e_simple_test']['cpu_port_frames_per_s'] = 1e3 / per_frame
+    if not args.no_cpu_baseline and world == 1:
+        torch.cuda.empty_cache()
+        try:
+            line['library_baseline'] = library_baseline(args, B, dev)
+        except Exception as e:   # a baseline, never a reason to lose the line
+            line['library_baseline'] = dict(unavailable=repr(e)[:200])
+        torch.cuda.empty_cache()
     if not args.no_kernel_head and world == 1:
         torch.cuda.empty_cache()
         line['kernel_head'] = kernel_head_timing(args, B, dev, pk['hbm'], cpu=not args.no_cpu_baseline)
@@ -646,6 +653,46 @@ def cpu_baseline(args):
     return dict(value=n / dt, unit='frames/s', cores=cores, kind='port',
                 sample='%d frames of %dx%d, one frame per call, fp32 oracle/decoder_ref.py on %d torch threads' %
                        (n, args.height, args.width, cores))
+
+
+def library_baseline(args, B, dev):
+    """"the same oracle on the B200 via PyTorch as the stronger library-kernels-on-the-same-box
+    baseline" -- oracle/decoder_ref.py (the reference's algorithm as written: fp32 feat_transform convs, einsum
+    pooling, per-image conv2d, nn.MultiheadAttention, ...) on the SAME GPU through cuBLAS / cuDNN, the same B frames
+    per step, inputs resident, CUDA events.  Reported next to `value`; never on the product path."""
+    from oracle import decoder_ref as ref
+    sd, _ = synth_state()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    H, W = args.height // 8, args.width // 8
+    inp = host_inputs(B, H, W, 0)
+    x, d = inp['x'].float().to(dev), inp['d'].float().to(dev)
+    prop = inp['prop'].reshape(B, N_KERNELS, C, 1, 1).to(dev)
+    dprop = inp['dprop'].reshape(B, N_KERNELS, C, 1, 1).to(dev)
+    mask = inp['mask'].to(dev)
+    out = {}
+    for tf32 in (False, True):
+        old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            with torch.no_grad():
+                for _ in range(3):
+                    ref.decoder_forward(sd, x, prop, mask, d, dprop)
+                torch.cuda.synchronize()
+                n = 10
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    ref.decoder_forward(sd, x, prop, mask, d, dprop)
+                b.record()
+                torch.cuda.synchronize()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        ms = a.elapsed_time(b) / n
+        out['tf32' if tf32 else 'fp32'] = dict(ms_per_step=ms, value=B / ms * 1e3)
+    return dict(value=out['fp32']['value'], unit='frames/s', ms_per_step=out['fp32']['ms_per_step'],
+                tf32_value=out['tf32']['value'], tf32_ms_per_step=out['tf32']['ms_per_step'], batch=B,
+                kind='oracle/decoder_ref.py through PyTorch eager (cuBLAS / cuDNN) on the same GPU, fp32 (TF32 off; '
+                     'tf32_* = TF32 allowed, which does not meet the 1e-3 gate), inputs resident')
 
 
 def emit(line):

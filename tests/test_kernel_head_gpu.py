@@ -190,3 +190,23 @@ def test_fpn_pred_full_size_and_chain(dev):
     for k in ('x_feats', 'depth_feats', 'mask_preds', 'seg_preds', 'depth_pred'):
         l2, mx = rel_err(out[k].cpu(), want_t[k].cpu())
         assert l2 < TIGHT and mx < TIGHT, (k, l2, mx)
+
+
+def test_kernel_head_tail_other_head_sizes(dev):
+    """Fewer proposals (P=37 -> N=48) and a ragged batch/map: the row blocks of head_w, the stuff-channel offsets of
+    mask_preds and the sign-bit rows all depend on P."""
+    B, H, W, seed, P = 3, 9, 20, 5, 37
+    sd = synth.synth_kernel_head_state(seed, num_proposals=P)
+    maps = synth.synth_fpn_maps(B, H, W, seed)
+    tail, out = run_tail(dev, sd, maps, H, W)
+    with torch.no_grad():
+        want = ref.decode_init_proposals(sd, maps)
+    assert out['mask_preds'].shape == (B, P + 11, H, W)
+    for k in ('x_feats', 'depth_feats', 'mask_preds', 'seg_preds', 'depth_pred'):
+        l2, mx = rel_err(out[k].cpu(), want[k])
+        assert l2 < TIGHT and mx < TIGHT, (k, l2, mx)
+    got, full = unpack_bits(out['bits'], P, H * W)
+    assert (got != (want['mask_preds'][:, :P].reshape(B, P, -1) > 0).numpy()).mean() < 1e-3
+    assert not full[:, P:].any()
+    l2, mx = rel_err(out['proposal_feats'].cpu()[:, P:], want['proposal_feats'][:, P:])
+    assert l2 == 0.0   # stuff kernels are copies of conv_seg.weight[8:]
