@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "pf_internal.h"
+#include <cstdlib>
 
 namespace pf {
 
@@ -43,6 +44,12 @@ int num_sms() {
     static thread_local int cached_dev = -1, cached_n = 0;
     if (cached_dev == dev) return cached_n;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    // experiment knob ("SM-partitioned batch windows"): size the persistent streaming kernels for
+    // fewer SMs so that another window's small-N block can run beside them
+    if (const char* lim = getenv("PF_SM_LIMIT")) {
+        const int v = atoi(lim);
+        if (v >= 8 && v < n) n = v;
+    }
     cached_dev = dev;
     cached_n = n;
     return n;

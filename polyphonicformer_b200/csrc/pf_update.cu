@@ -175,9 +175,11 @@ __device__ __forceinline__ float4 ln4(float4 v, float mean, float rstd, float4 g
 }
 __device__ __forceinline__ float4 act4(float4 v, int act) {
     if (act == ACT_RELU) return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    // ex2.approx / rcp.approx: ~1e-7 relative on the sigmoid (the exponent's range reduction error is scaled by
+    // (1 - sigmoid) |x| <= 0.3); the IEEE division + expf version made the gate epilogue instruction-bound
     if (act == ACT_SIGMOID)
-        return make_float4(1.f / (1.f + expf(-v.x)), 1.f / (1.f + expf(-v.y)), 1.f / (1.f + expf(-v.z)),
-                           1.f / (1.f + expf(-v.w)));
+        return make_float4(__fdividef(1.f, 1.f + __expf(-v.x)), __fdividef(1.f, 1.f + __expf(-v.y)),
+                           __fdividef(1.f, 1.f + __expf(-v.z)), __fdividef(1.f, 1.f + __expf(-v.w)));
     return v;
 }
 // 4 values -> bf16 hi / lo, 8 contiguous bytes in each plane
@@ -860,6 +862,17 @@ __global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const floa
     pdl_launch_dependents();
     DBG(2);
     const float* qkv = (blockIdx.z == 0 ? qkv0 : qkv1) + (size_t)b * N * 768;
+    // this thread's query row first: its loads are in flight together with the K / V loads below (they used to be
+    // issued after the K / V shared-memory stores: two serialised global latencies)
+    const int n = qblk * ATT_QPC + threadIdx.x / ATT_TPQ, part = threadIdx.x % ATT_TPQ;
+    const int nq = n < N ? n : N - 1;   // keep whole octets alive for the shuffles
+    float q[32];
+    const float scale = 0.17677669529663687f;  // 1/sqrt(32), applied to q before q k^T as torch does
+#pragma unroll
+    for (int d4 = 0; d4 < 8; ++d4) {
+        const float4 t = ld4(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
+        q[d4 * 4] = t.x * scale, q[d4 * 4 + 1] = t.y * scale, q[d4 * 4 + 2] = t.z * scale, q[d4 * 4 + 3] = t.w * scale;
+    }
     {   // K and V of this head: 128 keys x 8 float4 each; all 8 loads of a thread are issued before the first store
         float4 kk[4], vv[4];
 #pragma unroll
@@ -877,15 +890,6 @@ __global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const floa
             s_kt[d4 * 4][n] = kk[j].x, s_kt[d4 * 4 + 1][n] = kk[j].y, s_kt[d4 * 4 + 2][n] = kk[j].z, s_kt[d4 * 4 + 3][n] = kk[j].w;
             *reinterpret_cast<float4*>(&s_v[n][(d4 ^ ((n >> 2) & 7)) * 4]) = vv[j];
         }
-    }
-    const int n = qblk * ATT_QPC + threadIdx.x / ATT_TPQ, part = threadIdx.x % ATT_TPQ;
-    const int nq = n < N ? n : N - 1;   // keep whole octets alive for the shuffles
-    float q[32];
-    const float scale = 0.17677669529663687f;  // 1/sqrt(32), applied to q before q k^T as torch does
-#pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 t = ld4(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
-        q[d4 * 4] = t.x * scale, q[d4 * 4 + 1] = t.y * scale, q[d4 * 4 + 2] = t.z * scale, q[d4 * 4 + 3] = t.w * scale;
     }
     __syncthreads();
     DBG(3);
@@ -915,7 +919,7 @@ __global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const floa
         const int j0 = 4 * (part + ATT_TPQ * i);   // (j0 >> 2) & 7 == part
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float pj = expf(sc[i][e] - mx);   // exp(-inf) = 0 for padded keys (their V rows are zero)
+            const float pj = __expf(sc[i][e] - mx);   // exp(-inf) = 0 for padded keys (their V rows are zero)
             den += pj;
 #pragma unroll
             for (int d4 = 0; d4 < 8; ++d4) {
