@@ -849,11 +849,14 @@ __global__ void __launch_bounds__(256) sumln_kernel(const __grid_constant__ SumL
 // split the queries, so the 64 (image, head) pairs of a batch of 4 spread over 512 CTAs.
 constexpr int ATT_TPQ = 8;                        // threads per query
 constexpr int ATT_NB = PF_MAX_N / (4 * ATT_TPQ);  // key blocks of 4 per thread (4 -> 16 keys per thread)
-constexpr int ATT_QPC = 32;                       // queries per CTA
+constexpr int ATT_QPT = 2;                        // queries per thread: every K / V chunk read from shared memory feeds two
+                                                  // queries (the kernel is bound by LDS.128 quarter-warp phases, not FMAs)
+constexpr int ATT_QPC = 64;                       // queries per CTA
+constexpr int ATT_THREADS = ATT_QPC / ATT_QPT * ATT_TPQ;   // 256
 constexpr int ATT_CPH = PF_MAX_N / ATT_QPC;       // CTAs per (branch, image, head)
-__global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const float* __restrict__ qkv0,
-                                                                      const float* __restrict__ qkv1,
-                                                                      uint16_t* __restrict__ arena, int B, int N) {
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const float* __restrict__ qkv0,
+                                                                const float* __restrict__ qkv1,
+                                                                uint16_t* __restrict__ arena, int B, int N) {
     __shared__ __align__(16) float s_kt[32][PF_MAX_N + 4];   // K transposed: [d][key]
     __shared__ __align__(16) float s_v[PF_MAX_N][32];        // V: 16-byte chunk c of key j stored at chunk c ^ ((j >> 2) & 7)
     const int h = blockIdx.x / ATT_CPH, qblk = blockIdx.x % ATT_CPH, b = blockIdx.y;
@@ -862,22 +865,26 @@ __global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const floa
     pdl_launch_dependents();
     DBG(2);
     const float* qkv = (blockIdx.z == 0 ? qkv0 : qkv1) + (size_t)b * N * 768;
-    // this thread's query row first: its loads are in flight together with the K / V loads below (they used to be
-    // issued after the K / V shared-memory stores: two serialised global latencies)
-    const int n = qblk * ATT_QPC + threadIdx.x / ATT_TPQ, part = threadIdx.x % ATT_TPQ;
-    const int nq = n < N ? n : N - 1;   // keep whole octets alive for the shuffles
-    float q[32];
+    // this thread's two query rows first: their loads are in flight together with the K / V loads below
+    const int part = threadIdx.x % ATT_TPQ;
+    int nrow[ATT_QPT];
+    float q[ATT_QPT][32];
     const float scale = 0.17677669529663687f;  // 1/sqrt(32), applied to q before q k^T as torch does
 #pragma unroll
-    for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 t = ld4(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
-        q[d4 * 4] = t.x * scale, q[d4 * 4 + 1] = t.y * scale, q[d4 * 4 + 2] = t.z * scale, q[d4 * 4 + 3] = t.w * scale;
+    for (int t = 0; t < ATT_QPT; ++t) {
+        nrow[t] = qblk * ATT_QPC + t * (ATT_QPC / ATT_QPT) + threadIdx.x / ATT_TPQ;
+        const int nq = nrow[t] < N ? nrow[t] : N - 1;   // keep whole octets alive for the shuffles
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+            const float4 v = ld4(qkv + (size_t)nq * 768 + h * 32 + d4 * 4);
+            q[t][d4 * 4] = v.x * scale, q[t][d4 * 4 + 1] = v.y * scale, q[t][d4 * 4 + 2] = v.z * scale, q[t][d4 * 4 + 3] = v.w * scale;
+        }
     }
     {   // K and V of this head: 128 keys x 8 float4 each; all 8 loads of a thread are issued before the first store
         float4 kk[4], vv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = threadIdx.x + j * (ATT_QPC * ATT_TPQ);   // 0 .. 1023
+            const int i = threadIdx.x + j * ATT_THREADS;   // 0 .. 1023
             const int n = i >> 3, d4 = i & 7;
             const bool ok = n < N;
             kk[j] = ok ? ld4(qkv + (size_t)n * 768 + 256 + h * 32 + d4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -885,7 +892,7 @@ __global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const floa
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = threadIdx.x + j * (ATT_QPC * ATT_TPQ);
+            const int i = threadIdx.x + j * ATT_THREADS;
             const int n = i >> 3, d4 = i & 7;
             s_kt[d4 * 4][n] = kk[j].x, s_kt[d4 * 4 + 1][n] = kk[j].y, s_kt[d4 * 4 + 2][n] = kk[j].z, s_kt[d4 * 4 + 3][n] = kk[j].w;
             *reinterpret_cast<float4*>(&s_v[n][(d4 ^ ((n >> 2) & 7)) * 4]) = vv[j];
@@ -893,70 +900,97 @@ __global__ void __launch_bounds__(ATT_QPC * ATT_TPQ) attention_kernel(const floa
     }
     __syncthreads();
     DBG(3);
-    float sc[ATT_NB][4];
-    float mx = -INFINITY;
+    float sc[ATT_QPT][ATT_NB][4];
+    float mx[ATT_QPT];
+#pragma unroll
+    for (int t = 0; t < ATT_QPT; ++t) mx[t] = -INFINITY;
 #pragma unroll
     for (int i = 0; i < ATT_NB; ++i) {
         const int j0 = 4 * (part + ATT_TPQ * i);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a[ATT_QPT];
+#pragma unroll
+        for (int t = 0; t < ATT_QPT; ++t) a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int d = 0; d < 32; ++d) {
             const float4 kk = *reinterpret_cast<const float4*>(&s_kt[d][j0]);
-            a.x += q[d] * kk.x, a.y += q[d] * kk.y, a.z += q[d] * kk.z, a.w += q[d] * kk.w;
+#pragma unroll
+            for (int t = 0; t < ATT_QPT; ++t)
+                a[t].x += q[t][d] * kk.x, a[t].y += q[t][d] * kk.y, a[t].z += q[t][d] * kk.z, a[t].w += q[t][d] * kk.w;
         }
-        sc[i][0] = j0 < N ? a.x : -INFINITY, sc[i][1] = j0 + 1 < N ? a.y : -INFINITY;
-        sc[i][2] = j0 + 2 < N ? a.z : -INFINITY, sc[i][3] = j0 + 3 < N ? a.w : -INFINITY;
-        mx = fmaxf(fmaxf(mx, fmaxf(sc[i][0], sc[i][1])), fmaxf(sc[i][2], sc[i][3]));
+#pragma unroll
+        for (int t = 0; t < ATT_QPT; ++t) {
+            sc[t][i][0] = j0 < N ? a[t].x : -INFINITY, sc[t][i][1] = j0 + 1 < N ? a[t].y : -INFINITY;
+            sc[t][i][2] = j0 + 2 < N ? a[t].z : -INFINITY, sc[t][i][3] = j0 + 3 < N ? a[t].w : -INFINITY;
+            mx[t] = fmaxf(fmaxf(mx[t], fmaxf(sc[t][i][0], sc[t][i][1])), fmaxf(sc[t][i][2], sc[t][i][3]));
+        }
     }
 #pragma unroll
-    for (int o = 1; o < ATT_TPQ; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    DBG(4);
-    float o[32], den = 0.f;
+    for (int t = 0; t < ATT_QPT; ++t)
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+        for (int o = 1; o < ATT_TPQ; o <<= 1) mx[t] = fmaxf(mx[t], __shfl_xor_sync(0xffffffffu, mx[t], o));
+    DBG(4);
+    float o[ATT_QPT][32], den[ATT_QPT];
+#pragma unroll
+    for (int t = 0; t < ATT_QPT; ++t) {
+        den[t] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[t][d] = 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < ATT_NB; ++i) {
         const int j0 = 4 * (part + ATT_TPQ * i);   // (j0 >> 2) & 7 == part
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float pj = __expf(sc[i][e] - mx);   // exp(-inf) = 0 for padded keys (their V rows are zero)
-            den += pj;
+            float pj[ATT_QPT];
+#pragma unroll
+            for (int t = 0; t < ATT_QPT; ++t) {
+                pj[t] = __expf(sc[t][i][e] - mx[t]);   // exp(-inf) = 0 for padded keys (their V rows are zero)
+                den[t] += pj[t];
+            }
 #pragma unroll
             for (int d4 = 0; d4 < 8; ++d4) {
                 const float4 vv = *reinterpret_cast<const float4*>(&s_v[j0 + e][(d4 ^ part) * 4]);
-                o[d4 * 4] += pj * vv.x, o[d4 * 4 + 1] += pj * vv.y, o[d4 * 4 + 2] += pj * vv.z, o[d4 * 4 + 3] += pj * vv.w;
+#pragma unroll
+                for (int t = 0; t < ATT_QPT; ++t)
+                    o[t][d4 * 4] += pj[t] * vv.x, o[t][d4 * 4 + 1] += pj[t] * vv.y, o[t][d4 * 4 + 2] += pj[t] * vv.z,
+                        o[t][d4 * 4 + 3] += pj[t] * vv.w;
             }
         }
     }
-#pragma unroll
-    for (int s2 = 1; s2 < ATT_TPQ; s2 <<= 1) den += __shfl_xor_sync(0xffffffffu, den, s2);
-    const float inv = 1.f / den;
-    // octet reduce-scatter: after 3 halving steps lane `part` holds the full sums of dims [4 part, 4 part + 4)
-    float r16[16], r8[8], r4[4];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const float send = (part & 4) ? o[k] : o[16 + k];
-        const float keep = (part & 4) ? o[16 + k] : o[k];
-        r16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float send = (part & 2) ? r16[k] : r16[8 + k];
-        const float keep = (part & 2) ? r16[8 + k] : r16[k];
-        r8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float send = (part & 1) ? r8[k] : r8[4 + k];
-        const float keep = (part & 1) ? r8[4 + k] : r8[k];
-        r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-    // lane `part` writes dims [4 part, 4 part + 4) of query row n as bf16 hi / lo (rows >= N: zeros)
-    const bool ok = n < N;
     const int unit = blockIdx.z * B + b;
-    store_planes4(ok ? make_float4(r4[0] * inv, r4[1] * inv, r4[2] * inv, r4[3] * inv) : make_float4(0.f, 0.f, 0.f, 0.f),
-                  arena_row(arena, unit, SLOT_ATT, 0, n) + h * 32 + part * 4,
-                  arena_row(arena, unit, SLOT_ATT, 1, n) + h * 32 + part * 4);
+#pragma unroll
+    for (int t = 0; t < ATT_QPT; ++t) {
+        float dn = den[t];
+#pragma unroll
+        for (int s2 = 1; s2 < ATT_TPQ; s2 <<= 1) dn += __shfl_xor_sync(0xffffffffu, dn, s2);
+        const float inv = 1.f / dn;
+        // octet reduce-scatter: after 3 halving steps lane `part` holds the full sums of dims [4 part, 4 part + 4)
+        float r16[16], r8[8], r4[4];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float send = (part & 4) ? o[t][k] : o[t][16 + k];
+            const float keep = (part & 4) ? o[t][16 + k] : o[t][k];
+            r16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = (part & 2) ? r16[k] : r16[8 + k];
+            const float keep = (part & 2) ? r16[8 + k] : r16[k];
+            r8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = (part & 1) ? r8[k] : r8[4 + k];
+            const float keep = (part & 1) ? r8[4 + k] : r8[k];
+            r4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        // lane `part` writes dims [4 part, 4 part + 4) of query row n as bf16 hi / lo (rows >= N: zeros)
+        const int n = nrow[t];
+        const bool ok = n < N;
+        store_planes4(ok ? make_float4(r4[0] * inv, r4[1] * inv, r4[2] * inv, r4[3] * inv) : make_float4(0.f, 0.f, 0.f, 0.f),
+                      arena_row(arena, unit, SLOT_ATT, 0, n) + h * 32 + part * 4,
+                      arena_row(arena, unit, SLOT_ATT, 1, n) + h * 32 + part * 4);
+    }
     DBG(13);
 }
 
@@ -1036,7 +1070,7 @@ static int launch_attention(const float* q0, const float* q1, uint16_t* arena, i
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(PF_HEADS * ATT_CPH, B, nbranch);
-    cfg.blockDim = dim3(ATT_QPC * ATT_TPQ);
+    cfg.blockDim = dim3(ATT_THREADS);
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
