@@ -7,10 +7,11 @@
 //        bf16 per 32-bit column), written once by the epilogue warps with tcgen05.st.  With A in shared memory
 //        (SS mode) every MMA re-read 4 KB of A and the kernel was paced by those reads (~87 cycles per
 //        128x64x16 MMA, in-kernel timeline), not by HBM; TS mode reads only the 2 KB feature slice per MMA;
-//   B  = feats[g][:, hw0:hw0+64] bf16, TMA-loaded as a [256 c][64 hw] box = MN-major operand, 6-stage ring
+//   B  = feats[g][:, hw0:hw0+128] bf16, TMA-loaded as two [256 c][64 hw] boxes = MN-major operand, 3-stage ring
 //        (192 KB in flight per SM);
-//   D  = [128 lanes][64 | 128 columns] fp32 in TMEM, 4 | 2 accumulator buffers so the epilogue overlaps the next
-//        tiles (128-pixel tiles = MMA N 128 when only sign bits are emitted: half the MMA issues per pixel);
+//   D  = [128 lanes][128 columns] fp32 in TMEM, 2 accumulator buffers so the epilogue overlaps the next tile.  The
+//        128-pixel tile = MMA N 128 halves the MMA issues per pixel against 64-pixel tiles (an issued MMA costs ~48
+//        cycles whatever its N: with N = 64 the logits variant was issue-bound at 0.70 of the HBM peak);
 //   epilogue: tcgen05.ld -> + bias -> the packed sign bits consumed by the next stage's pooling (thread = kernel row
 //             n, 32 consecutive pixels = one u32 word) and/or fp32 logits.  Logits leave through shared memory:
 //             each thread writes its 32 pixels into a 128-byte-swizzled [128 rows][32 px] tile, one thread issues a
@@ -27,8 +28,7 @@ namespace pf {
 
 constexpr int E_C = PF_C;            // 256 = K of the GEMM
 constexpr int E_BHW = 64;            // pixels per tile (= N of the MMA, one 128-byte swizzle atom of bf16)
-constexpr int E_STAGES = 6;          // feature ring depth without the logits staging tiles
-constexpr int E_STAGES_TMA = 5;      // ... with them
+constexpr int E_STAGES = 6;          // feature ring depth in 64-pixel boxes (3 stages of 128-pixel tiles)
 constexpr int E_OUT_BYTES = 128 * 32 * 4;   // one staged half tile: [128 rows][32 px] fp32
 constexpr int E_ACC = 2;             // 2 * E_ACC * 64 = 256 TMEM columns of accumulators: 4 buffers of 64-pixel tiles
                                      // or 2 buffers of 128-pixel tiles
@@ -36,8 +36,8 @@ constexpr int E_TMEM_A = 2 * E_ACC * E_BHW; // first TMEM column of A hi; A lo f
 constexpr int E_TMEM_COLS = 512;            // 256 accumulator + 2 x 128 A columns: the whole tensor memory
 constexpr int E_B_BYTES = E_C * E_BHW * 2;  // 32768 per stage
 constexpr int E_THREADS = 192;
-constexpr int E_SMEM = E_STAGES * E_B_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
-static_assert(E_STAGES_TMA * E_B_BYTES + 2 * E_OUT_BYTES <= E_STAGES * E_B_BYTES, "staging tiles must fit in the ring");
+constexpr int E_SMEM = E_STAGES * E_B_BYTES + 2 * E_OUT_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+static_assert(E_SMEM <= 232448, "shared memory budget of one CTA");
 
 struct EinsumParams {
     const uint16_t* kern;   // [G][2][N][256] bf16 hi / lo planes
@@ -65,24 +65,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void epi_bar4() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
 // TMA_OUT: fp32 logits leave as TMA tensor stores of staged tiles (tmap_out over [units][N][HW]).
-// Tile width: 128 pixels (two TMA boxes, MMA N = 128) when only the sign bits are emitted -- half as many MMA
-// issues per pixel, which is what bounds that variant -- and 64 pixels with the logits staging tiles.
+// Tile width: 128 pixels (two TMA boxes, MMA N = 128); the two logits staging tiles sit behind the ring.
 // STATS (pf_kernel_head's convolutions): every epilogue thread also accumulates the sum and the sum of squares of its
 // row over the CTA's pixels -- the GroupNorm statistics, without a second pass over the output.
 template <bool TMA_OUT, bool STATS = false>
 __global__ void __launch_bounds__(E_THREADS, 1)
 einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_constant__ CUtensorMap tmap_out,
               const EinsumParams p) {
-    constexpr int TILE = TMA_OUT ? 64 : 128;                         // pixels per tile = MMA N = accumulator columns
+    constexpr int TILE = 128;                                        // pixels per tile = MMA N = accumulator columns
     constexpr int NBOX = TILE / E_BHW;
     constexpr int STAGE_BYTES = NBOX * E_B_BYTES;
-    constexpr int STAGES = TMA_OUT ? E_STAGES_TMA : E_STAGES / NBOX;
+    constexpr int STAGES = E_STAGES / NBOX;
     constexpr int NACC = (2 * E_ACC * E_BHW) / TILE;                 // accumulator buffers in 256 TMEM columns
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
-    uint8_t* sOut = sB + E_STAGES_TMA * E_B_BYTES;   // TMA_OUT only: 2 x [128][32] fp32, 1024-byte aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + E_STAGES * E_B_BYTES);
+    uint8_t* sOut = sB + E_STAGES * E_B_BYTES;       // TMA_OUT only: 2 x [128][32] fp32, 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * E_OUT_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + E_STAGES;
     uint64_t* tfull = bars + 2 * E_STAGES;
@@ -228,7 +227,7 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                 if (brow) brow[(size_t)(hwb >> 5) * 128] = word;
                 if (TMA_OUT) {
                     // staged tile (2*i + h) & 1: wait until the store issued two half tiles ago has read it
-                    uint8_t* tile = sOut + ((2 * i + h) & 1) * E_OUT_BYTES;
+                    uint8_t* tile = sOut + (h & 1) * E_OUT_BYTES;   // TILE / 32 is even: the two tiles alternate across tiles too
                     if (threadIdx.x == 64) tma_store_wait_read<1>();
                     epi_bar4();
 #pragma unroll
@@ -337,7 +336,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     p.kdiv = 1, p.fmod = 0x7fffffff, p.stats = nullptr, p.out_blocked = 0;
     // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
     const bool tma_out = logits && (HW % 4) == 0;
-    const int tile = tma_out ? 64 : 128;   // must match einsum_kernel<TMA_OUT>::TILE
+    const int tile = 128;   // must match einsum_kernel::TILE
     p.tiles_per_unit = (HW + tile - 1) / tile;
     int cpu = num_sms() / n_units;
     if (cpu < 1) cpu = 1;
@@ -359,7 +358,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
 // W_map . maps[map % n_inputs][b]; conv_split holds the six (half, map) row blocks as bf16 hi / lo planes [6][2][128][256].
 // Y: fp32 [6B][ceil(HW/32)][128][32] (pixel-blocked).
 int pf::conv1x1_ctas_per_unit(int B, int HW) {
-    const int tile = 64;
+    const int tile = 128;
     int cpu = num_sms() / (6 * B);
     const int tiles = (HW + tile - 1) / tile;
     return cpu < 1 ? 1 : (cpu > tiles ? tiles : cpu);
@@ -380,7 +379,7 @@ int pf::conv1x1_maps(const uint16_t* maps, int n_inputs, const uint16_t* conv_sp
     // read back by head_apply_kernel with a compile-time channel stride
     const int nblk = (HW + 31) / 32;
     p.out_blocked = nblk;
-    const int tile = 64;
+    const int tile = 128;
     p.tiles_per_unit = (HW + tile - 1) / tile;
     const int cpu = conv1x1_ctas_per_unit(B, HW);
     p.ctas_per_unit = cpu;
