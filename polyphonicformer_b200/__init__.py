@@ -8,10 +8,10 @@ lib/libpf_decoder.so) with a Python host mirror of the reference's mmdet-registr
 from . import registry
 from .registry import (DETECTORS, HEADS, MODELS, TRANSFORMER_LAYER, ConfigDict, Registry, build_head,
                        build_transformer_layer, load_config, register_all)
-from .modules import KernelUpdateHead, KernelUpdateIterHead, KernelUpdator
+from .modules import KernelHead, KernelUpdateHead, KernelUpdateIterHead, KernelUpdator
 
 register_all()
 
-__all__ = ['KernelUpdator', 'KernelUpdateHead', 'KernelUpdateIterHead', 'build_head', 'build_transformer_layer',
+__all__ = ['KernelUpdator', 'KernelUpdateHead', 'KernelUpdateIterHead', 'KernelHead', 'build_head', 'build_transformer_layer',
            'load_config', 'register_all', 'Registry', 'ConfigDict', 'MODELS', 'HEADS', 'DETECTORS',
            'TRANSFORMER_LAYER', 'registry']

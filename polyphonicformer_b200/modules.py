@@ -1,6 +1,6 @@
 """Drop-in modules for the decoder hot path, registered under the reference's names.
 
-``KernelUpdator``, ``KernelUpdateHead`` and ``KernelUpdateIterHead`` take the reference's constructor kwargs
+``KernelUpdator``, ``KernelUpdateHead``, ``KernelUpdateIterHead`` and ``KernelHead`` take the reference's constructor kwargs
 (``configs/_base_/models/polyphonic_former.py:99-164``), expose the reference's ``state_dict`` keys and shapes
  so its checkpoints load with ``strict=True``, and keep the reference's forward signatures:
 
@@ -8,6 +8,7 @@
   KernelUpdateHead.forward(x, proposal_feat, mask_preds, ...)    polyphonic/kernel_update_head.py:212-353
   KernelUpdateIterHead._mask_forward / simple_test_mask_preds / simple_test
                                                                   polyphonic/kernel_update.py:125-157, 282-401
+  KernelHead._decode_init_proposals / simple_test_rpn             polyphonic/kernel_head.py:240-347, 700-706
 
 The ``nn`` layers below only HOLD parameters.  All forward arithmetic runs in libpf_decoder.so (sm_100a CUDA) through
 ``DecoderEngine``; there is no PyTorch fallback -- on a non-CUDA tensor, or an unsupported configuration, the modules
@@ -20,9 +21,9 @@ import torch.nn as nn
 
 from . import _cabi
 from .decoder import DecoderEngine
-from .registry import ConfigDict, build_head, build_transformer_layer, to_config
+from .registry import ConfigDict, build_head, build_neck, build_transformer_layer, to_config
 
-__all__ = ['KernelUpdator', 'KernelUpdateHead', 'KernelUpdateIterHead']
+__all__ = ['KernelUpdator', 'KernelUpdateHead', 'KernelUpdateIterHead', 'KernelHead']
 
 
 def _unsupported(what):
@@ -229,6 +230,9 @@ class KernelUpdateHead(nn.Module):
         return self._engine[1]
 
     def _prepared_feats(self, x, depth_feats):
+        shared = getattr(x, '_pf_feats', None)   # produced by KernelHead below: already in the decoder's layout
+        if shared is not None and getattr(depth_feats, '_pf_feats', None) is shared:
+            return shared
         key = (x.data_ptr(), x._version, depth_feats.data_ptr(), depth_feats._version, tuple(x.shape), x.dtype)
         if self._feats_cache is None or self._feats_cache[0] != key:
             self._feats_cache = (key, self.engine(x.device).prepare_feats(x, depth_feats))
@@ -342,7 +346,7 @@ class KernelUpdateIterHead(nn.Module):
         if mask_preds.shape[-2:] != (H, W):
             _unsupported('mask_preds at a different resolution than the feature map')
         eng = self.engine(x.device)
-        feats = eng.prepare_feats(x, depth_feats)
+        feats = self.mask_head[0]._prepared_feats(x, depth_feats)
         out = eng.decode(feats, mask_preds.float(), proposal_feats.reshape(B, N, -1).float(),
                          depth_proposal.reshape(B, N, -1).float(), H, W,
                          upsample=head.mask_upsample_stride == 2, all_stage_outputs=all_stage_outputs)
@@ -383,3 +387,156 @@ class KernelUpdateIterHead(nn.Module):
 
     def aug_test(self, features, proposal_list, img_metas, rescale=False):
         raise NotImplementedError('SparseMask does not support `aug_test`')
+
+
+class _ConvGN(nn.Module):
+    """Parameters of an mmcv ``ConvModule(C, C, 1, norm_cfg=GN)``: ``conv.weight`` (no bias), ``gn.weight``, ``gn.bias``."""
+
+    def __init__(self, channels, num_groups):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 1, bias=False)
+        self.gn = nn.GroupNorm(num_groups, channels)
+
+
+class KernelHead(nn.Module):
+    """The proposal stage (reference: polyphonic/kernel_head.py:16-347, 700-706), inference only.
+
+    ``localization_fpn`` (SemanticFPNWrapper) is built through the reference's NECKS registry and runs as the
+    reference's PyTorch module (not rebuilt); everything after it -- kernel_head.py:250-336
+    -- runs in ``pf_kernel_head`` / ``pf_mask_pool`` / ``pf_init_proposals``.  When the neck exposes the reference's
+    ``convs_all_levels`` / ``conv_pred`` / two ``aux_convs`` its last step (semantic_fpn.py:221-229) runs in
+    ``pf_fpn_pred`` as well.  ``x_feats`` / ``depth_feats`` are returned as bf16 views of the decoder's feature buffer
+    (tagged so that KernelUpdateIterHead uses that buffer directly instead of casting them again)."""
+
+    def __init__(self, num_proposals=100, num_classes=133, num_thing_classes=80, num_stuff_classes=53, in_channels=256,
+                 out_channels=256, num_heads=8, num_cls_fcs=1, num_seg_convs=1, num_loc_convs=1, att_dropout=False,
+                 localization_fpn=None, conv_kernel_size=1, norm_cfg=dict(type='GN', num_groups=32), semantic_fpn=True,
+                 train_cfg=None, xavier_init_kernel=False, kernel_init_std=0.01, use_binary=False,
+                 proposal_feats_with_obj=False, loss_mask=None, loss_seg=None, loss_cls=None, loss_dice=None,
+                 loss_rank=None, loss_depth=None, feat_downsample_stride=1, feat_refine_stride=1, feat_refine=True,
+                 conv_normal_init=False, mask_out_stride=4, hard_target=False, ignore_label=255, cat_stuff_mask=False,
+                 with_depth=True, num_depth_convs=1, semantic_out_cfg=None, loss_semantic_seg=None, **kwargs):
+        super().__init__()
+        self.num_proposals, self.num_classes = num_proposals, num_classes
+        self.num_thing_classes, self.num_stuff_classes = num_thing_classes, num_stuff_classes
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_heads, self.num_cls_fcs, self.att_dropout = num_heads, num_cls_fcs, att_dropout
+        self.num_loc_convs, self.num_seg_convs, self.num_depth_convs = num_loc_convs, num_seg_convs, num_depth_convs
+        self.conv_kernel_size, self.norm_cfg, self.semantic_fpn = conv_kernel_size, norm_cfg, semantic_fpn
+        self.train_cfg, self.test_cfg = train_cfg, kwargs.get('test_cfg')
+        self.xavier_init_kernel, self.kernel_init_std = xavier_init_kernel, kernel_init_std
+        self.use_binary, self.proposal_feats_with_obj = use_binary, proposal_feats_with_obj
+        self.feat_downsample_stride, self.feat_refine_stride, self.feat_refine = feat_downsample_stride, feat_refine_stride, feat_refine
+        self.conv_normal_init, self.mask_out_stride, self.hard_target = conv_normal_init, mask_out_stride, hard_target
+        self.ignore_label, self.cat_stuff_mask, self.with_depth = ignore_label, cat_stuff_mask, with_depth
+        self.semantic_out_cfg = semantic_out_cfg
+        for name, cfg in (('loss_mask', loss_mask), ('loss_seg', loss_seg), ('loss_cls', loss_cls), ('loss_dice', loss_dice),
+                          ('loss_rank', loss_rank), ('loss_depth', loss_depth), ('loss_semantic_seg', loss_semantic_seg)):
+            setattr(self, name, _LossCfg(cfg) if cfg is not None else None)   # inference reads .use_sigmoid only
+        if (in_channels, out_channels, conv_kernel_size) != (256, 256, 1):
+            _unsupported('KernelHead with in/out channels %d/%d, conv_kernel_size %d' % (in_channels, out_channels, conv_kernel_size))
+        if (num_loc_convs, num_seg_convs, num_depth_convs) != (1, 1, 1) or not (semantic_fpn and with_depth):
+            _unsupported('KernelHead without exactly one loc / seg / depth conv')
+        if feat_downsample_stride > 1 and feat_refine:
+            _unsupported('feat_refine (ins_downsample / seg_downsample)')
+        if semantic_out_cfg is not None:
+            _unsupported('semantic_out_cfg (semantic_aspp)')
+        if not (cat_stuff_mask and use_binary and proposal_feats_with_obj):
+            _unsupported('KernelHead without cat_stuff_mask / use_binary / proposal_feats_with_obj')
+        if norm_cfg.get('type') != 'GN':
+            _unsupported('norm_cfg %r' % (norm_cfg,))
+        seg_sigmoid = bool(getattr(self.loss_seg, 'use_sigmoid', True)) if self.loss_seg is not None else True
+        self.localization_fpn = build_neck(localization_fpn)
+        groups = norm_cfg.get('num_groups', 32)
+        self.init_kernels = nn.Conv2d(out_channels, num_proposals, 1, bias=False)
+        self.conv_seg = nn.Conv2d(out_channels, num_classes if seg_sigmoid else num_classes + 1, 1)
+        self.loc_convs = nn.ModuleList([_ConvGN(in_channels, groups)])
+        self.seg_convs = nn.ModuleList([_ConvGN(in_channels, groups)])
+        self.depth_convs = nn.ModuleList([_ConvGN(in_channels, groups)])
+        self.conv_direct_depth = nn.Conv2d(out_channels, 1, 1)
+        self._tail = None
+        self._fpn_pred = None
+
+    def init_weights(self):
+        """kernel_head.py:214-238."""
+        if hasattr(self.localization_fpn, 'init_weights'):
+            self.localization_fpn.init_weights()
+        if self.conv_normal_init:
+            for m in (self.loc_convs[0].conv, self.seg_convs[0].conv):
+                nn.init.normal_(m.weight, std=0.01)
+        prior = -math.log((1 - 0.01) / 0.01)
+        nn.init.normal_(self.conv_seg.weight, std=0.01)
+        nn.init.constant_(self.conv_seg.bias, prior if self.conv_seg.out_channels == self.num_classes else 0.0)
+        if self.xavier_init_kernel:
+            nn.init.xavier_uniform_(self.init_kernels.weight)
+        else:
+            nn.init.normal_(self.init_kernels.weight, mean=0, std=self.kernel_init_std)
+
+    def _own_state(self):
+        return {k: v for k, v in self.state_dict().items() if not k.startswith('localization_fpn.')}
+
+    def tail(self, device):
+        from .kernel_head import KernelHeadTail
+        own = [p for n, p in self.named_parameters() if not n.startswith('localization_fpn.')]
+        key = (tuple((p.data_ptr(), p._version) for p in own), str(device))
+        if self._tail is None or self._tail[0] != key:
+            self._tail = (key, KernelHeadTail(self._own_state(), device, self.num_thing_classes))
+        return self._tail[1]
+
+    def _localization_maps(self, img, tail):
+        """The three SemanticFPN outputs as bf16 [3][B][256][HWp].  With the reference's SemanticFPNWrapper the pyramid
+        (semantic_fpn.py:198-219) stays its PyTorch code and only conv_pred / aux_convs (:221-229) run here."""
+        fpn = self.localization_fpn
+        fused_ok = (all(hasattr(fpn, a) for a in ('convs_all_levels', 'conv_pred', 'aux_convs', 'start_level', 'end_level'))
+                    and len(fpn.aux_convs) == 2 and not getattr(fpn, 'fuse_by_cat', False) and getattr(fpn, 'with_pred', True))
+        if not fused_ok:
+            feats = fpn(img)
+            if not isinstance(feats, (list, tuple)) or len(feats) != 3:
+                _unsupported('a localization_fpn that does not return [loc, semantic, depth] maps')
+            return tail.cast_maps(list(feats)), feats[0].shape[-2:]
+        from .kernel_head import FpnPred
+        levels = []
+        for i in range(fpn.start_level, fpn.end_level + 1):
+            inp = img[i]
+            if i == fpn.cat_coors_level:
+                if fpn.positional_encoding is not None:
+                    inp = inp + fpn.positional_encoding(inp.new_zeros((inp.shape[0],) + inp.shape[-2:], dtype=torch.bool))
+                if fpn.cat_coors:
+                    inp = torch.cat([inp, fpn.generate_coord(inp)], 1)
+            levels.append(fpn.convs_all_levels[i](inp))
+        fused = sum(levels)
+        pred_params = [p for m in (fpn.conv_pred, fpn.aux_convs) for p in m.parameters()]
+        key = (tuple((p.data_ptr(), p._version) for p in pred_params), str(fused.device))
+        if self._fpn_pred is None or self._fpn_pred[0] != key:
+            sd = {k: v for k, v in fpn.state_dict().items() if k.startswith('conv_pred.') or k.startswith('aux_convs.')}
+            self._fpn_pred = (key, FpnPred(sd, fused.device))
+        maps, _ = self._fpn_pred[1].forward(fused)
+        return maps, fused.shape[-2:]
+
+    def _decode_init_proposals(self, img, img_metas, train_tracking=False):
+        """kernel_head.py:240-347 (eval).  Returns the reference's 9-tuple."""
+        if self.training:
+            _unsupported('KernelHead in training mode')
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            _unsupported('KernelHead on a %s device' % dev.type)
+        tail = self.tail(dev)
+        maps, (H, W) = self._localization_maps(img, tail)
+        out = tail.forward(maps, H, W)
+        feats = out['feats']
+        B, HW = feats.shape[1], H * W
+        x_feats = feats[0][..., :HW].reshape(B, 256, H, W)
+        depth_feats = feats[1][..., :HW].reshape(B, 256, H, W)
+        x_feats._pf_feats = depth_feats._pf_feats = feats
+        return (out['proposal_feats'], x_feats, out['mask_preds'], None, out['seg_preds'], depth_feats,
+                out['depth_proposal'], out['depth_pred'], None)
+
+    def simple_test_rpn(self, img, img_metas, train_tracking=False):
+        """kernel_head.py:700-706."""
+        return self._decode_init_proposals(img, img_metas, train_tracking)
+
+    def forward_dummy(self, img, img_metas):
+        return self._decode_init_proposals(img, img_metas)
+
+    def forward_train(self, *args, **kwargs):
+        _unsupported('KernelHead.forward_train (training is out of scope)')

@@ -119,6 +119,18 @@ def build_head(cfg):
     return MODELS.build(cfg)
 
 
+def build_neck(cfg):
+    """SemanticFPNWrapper is NOT rebuilt here: it comes from the reference's own NECKS
+    registry when a reference checkout + mmcv are importable, else from this registry if someone registered the type."""
+    if cfg is None or not isinstance(cfg, dict):
+        return cfg                       # an already-built module (tests, custom pipelines) or None
+    try:
+        from mmdet.models.builder import build_neck as mm_build_neck
+        return mm_build_neck(cfg)
+    except ImportError:
+        return MODELS.build(cfg)
+
+
 def build_transformer_layer(cfg):
     return TRANSFORMER_LAYER.build(cfg)
 
@@ -126,7 +138,8 @@ def build_transformer_layer(cfg):
 def register_all(force=True):
     """Register the B200 modules under the reference's names; into mmcv/mmdet's registries when those import."""
     from . import modules as m
-    pairs = [(MODELS, m.KernelUpdateHead), (MODELS, m.KernelUpdateIterHead), (TRANSFORMER_LAYER, m.KernelUpdator)]
+    pairs = [(MODELS, m.KernelUpdateHead), (MODELS, m.KernelUpdateIterHead), (MODELS, m.KernelHead),
+             (TRANSFORMER_LAYER, m.KernelUpdator)]
     for reg, cls in pairs:
         reg.register_module(force=True, module=cls)
     try:   # the reference's own registries (drop-in when a reference checkout + mmcv are installed)
@@ -136,5 +149,6 @@ def register_all(force=True):
         return False
     MM_HEADS.register_module(force=force, module=m.KernelUpdateHead)
     MM_HEADS.register_module(force=force, module=m.KernelUpdateIterHead)
+    MM_HEADS.register_module(force=force, module=m.KernelHead)
     MM_TL.register_module(force=force, module=m.KernelUpdator)
     return True

@@ -210,3 +210,47 @@ def test_kernel_head_tail_other_head_sizes(dev):
     assert not full[:, P:].any()
     l2, mx = rel_err(out['proposal_feats'].cpu()[:, P:], want['proposal_feats'][:, P:])
     assert l2 == 0.0   # stuff kernels are copies of conv_seg.weight[8:]
+
+
+class _MapsNeck(torch.nn.Module):
+    def forward(self, img):
+        return img
+
+
+def test_kernel_head_module_matches_reference_and_feeds_iter_head(dev):
+    """The registered drop-in `KernelHead.simple_test_rpn` against the golden 9-tuple of the real KernelHead, and its
+    bf16 feature views going into `KernelUpdateIterHead` without another cast."""
+    import json
+    import polyphonicformer_b200 as pf
+    name = 'kernel_head_b2_h16_w24'
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    B, H, W, seed = int(g['B']), int(g['H']), int(g['W']), int(g['seed'])
+    d = json.load(open(os.path.join(GOLDEN, 'rpn_head_cfg.json')))
+    head = pf.KernelHead(**dict(d['rpn_head'], train_cfg=None, test_cfg=d['test_cfg'], localization_fpn=_MapsNeck()))
+    head.load_state_dict(synth.synth_kernel_head_state(seed), strict=True)
+    head = head.to(dev).eval()
+    maps = [m.to(dev) for m in synth.synth_fpn_maps(B, H, W, seed)]
+    out = head.simple_test_rpn(maps, [{}] * B)
+    torch.cuda.synchronize()
+    names = ('proposal_feats', 'x_feats', 'mask_preds', 'cls_scores', 'seg_preds', 'depth_feats', 'depth_proposal',
+             'depth_pred', 'semantic_aspp_out')
+    got = dict(zip(names, out))
+    assert got['cls_scores'] is None and got['semantic_aspp_out'] is None
+    for k in ('mask_preds', 'seg_preds', 'depth_pred', 'depth_proposal'):
+        l2, mx = rel_err(got[k].cpu(), g[k])
+        assert l2 < TIGHT and mx < TIGHT, (k, l2, mx)
+    for k in ('x_feats', 'depth_feats'):   # bf16 views of the decoder's buffer: the exact rounding of the fp32 values
+        assert got[k].dtype == torch.bfloat16 and got[k].shape == (B, 256, H, W)
+        l2, mx = rel_err(got[k].float().cpu(), synth.bf16_round(torch.from_numpy(g[k])))
+        assert l2 < 3e-4, (k, l2, mx)     # a 1e-5 fp32 difference occasionally lands on the other side of a rounding boundary
+    l2, mx = rel_err(got['proposal_feats'].cpu(), g['proposal_feats'])
+    assert l2 < GATE and mx < GATE
+    # into the decoder drop-in: the tagged views make it reuse the buffer
+    rd = json.load(open(os.path.join(GOLDEN, 'roi_head_cfg.json')))
+    roi = pf.build_head(dict(rd['roi_head'], train_cfg=None, test_cfg=rd['test_cfg']))
+    roi.load_state_dict(synth.synth_decoder_state(3, seed), strict=True)
+    roi = roi.to(dev).eval()
+    assert roi.mask_head[0]._prepared_feats(got['x_feats'], got['depth_feats']) is got['x_feats']._pf_feats
+    res = roi.decode(got['x_feats'], got['proposal_feats'], got['mask_preds'], got['depth_feats'], got['depth_proposal'])
+    torch.cuda.synchronize()
+    assert res['scaled_mask_preds'].shape == (B, 111, 2 * H, 2 * W) and torch.isfinite(res['scaled_mask_preds']).all()

@@ -78,3 +78,51 @@ def test_config_loader_merges_bases(tmp_path):
     (tmp_path / 'child.py').write_text("_base_ = ['./base.py']\na = dict(y=dict(z=5), q=dict(_delete_=True, k=1))\n")
     cfg = pf.load_config(str(tmp_path / 'child.py'))
     assert cfg.a.x == 1 and cfg.a.y.z == 5 and cfg.a.y.w == 3 and cfg.a.q == dict(k=1) and cfg.b == [1, 2]
+
+
+RPN_HEAD_JSON = os.path.join(GOLDEN, 'rpn_head_cfg.json')   # cfg.model.rpn_head dumped from the reference's config
+
+
+class _FakeNeck(torch.nn.Module):
+    """Stands in for the reference's SemanticFPNWrapper (not rebuilt): accepts its config kwargs."""
+
+    def __init__(self, **cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, img):
+        return img
+
+
+def rpn_head_cfg():
+    if os.path.exists(REF_CFG):
+        cfg = pf.load_config(REF_CFG)
+        assert json.loads(json.dumps(cfg.model.rpn_head)) == json.load(open(RPN_HEAD_JSON))['rpn_head'], \
+            'tests/golden/rpn_head_cfg.json is stale'
+    d = json.load(open(RPN_HEAD_JSON))
+    return dict(d['rpn_head'], train_cfg=None, test_cfg=d['test_cfg'])
+
+
+def test_kernel_head_builds_from_reference_config():
+    """`KernelHead` under the reference's name, with every kwarg of configs/_base_/models/polyphonic_former.py:30-97,
+    exposes the reference's state-dict keys and refuses what the kernels do not cover."""
+    assert 'KernelHead' in pf.MODELS
+    pf.MODELS.register_module(name='SemanticFPNWrapper', force=True, module=_FakeNeck)
+    try:
+        head = pf.build_head(rpn_head_cfg())
+    finally:
+        pf.MODELS._modules.pop('SemanticFPNWrapper', None)
+    assert isinstance(head, pf.KernelHead) and head.num_proposals == 100
+    assert head.localization_fpn.cfg['num_aux_convs'] == 2
+    own = {k: tuple(v.shape) for k, v in head.state_dict().items() if not k.startswith('localization_fpn.')}
+    assert own == {k: tuple(v) for k, v in synth.kernel_head_state_shapes().items()}
+    missing = head.load_state_dict(synth.synth_kernel_head_state(0), strict=False)
+    assert not missing.unexpected_keys and all(k.startswith('localization_fpn.') for k in missing.missing_keys)
+    head.init_weights()
+    with pytest.raises(NotImplementedError):
+        head.eval()._decode_init_proposals([torch.zeros(1, 256, 4, 4)] * 3, [{}])      # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        pf.KernelHead(**dict(rpn_head_cfg(), localization_fpn=_FakeNeck(), feat_refine=True))
+    with pytest.raises(NotImplementedError):
+        pf.KernelHead(**dict(rpn_head_cfg(), localization_fpn=_FakeNeck(), cat_stuff_mask=False))
