@@ -180,6 +180,18 @@ def run_fpn_pred_case(rpn, B, H, W, seed):
     return dict(maps=torch.stack(outs).numpy().astype(np.float32))
 
 
+SEMANTIC_FPN_CASES = [('semantic_fpn_b1_h16_w24_s0', 1, 16, 24, 0)]
+
+
+def run_semantic_fpn_case(rpn, B, H, W, seed):
+    """semantic_fpn.py:198-235 -- the reference's own SemanticFPNWrapper.forward on synthetic FPN levels."""
+    fpn = rpn.localization_fpn
+    fpn.load_state_dict(synth.synth_semantic_fpn_state(seed), strict=True)
+    with torch.no_grad():
+        outs = fpn(synth.synth_fpn_inputs(B, H, W, seed))
+    return dict(maps=torch.stack(outs).numpy().astype(np.float32))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -196,6 +208,10 @@ def main():
         np.savez_compressed(os.path.join(GOLD, name + '.npz'), h=h, w=w, seed=seed, **out)
         print(name, out['panoptic'].shape, 'segments', len(out['seg']), np.unique(out['panoptic']))
     rpn = build_reference_rpn_head()
+    for name, B, H, W, seed in SEMANTIC_FPN_CASES:
+        out = run_semantic_fpn_case(rpn, B, H, W, seed)
+        np.savez_compressed(os.path.join(GOLD, name + '.npz'), B=B, H=H, W=W, seed=seed, **out)
+        print(name, out['maps'].shape)
     for name, B, H, W, seed in FPN_PRED_CASES:   # before the kernel-head cases replace localization_fpn
         out = run_fpn_pred_case(rpn, B, H, W, seed)
         np.savez_compressed(os.path.join(GOLD, name + '.npz'), B=B, H=H, W=W, seed=seed, **out)

@@ -205,3 +205,21 @@ def synth_fused_map(B, H, W, seed=0):
     g = _gen(f'fused.{B}.{H}.{W}', seed)
     t = sum(torch.relu(torch.randn(B, C, H, W, generator=g) * s) for s in (1.0, 0.7, 0.5, 0.4))
     return bf16_round(t)
+
+
+def synth_semantic_fpn_state(seed=0):
+    """All 30 tensors of SemanticFPNWrapper (semantic_fpn.py:74-178 with the shipped config)."""
+    out = synth_fpn_pred_state(seed)
+    for lvl, n in ((0, 1), (1, 1), (2, 2), (3, 3)):
+        for j in range(n):
+            p = f'convs_all_levels.{lvl}.conv{j}'
+            out[p + '.conv.weight'] = synth_tensor('fpn.' + p + '.conv.weight', (C, C, 3, 3), seed)
+            out[p + '.gn.weight'] = synth_tensor('fpn.' + p + '.gn.weight', (C,), seed)
+            out[p + '.gn.bias'] = synth_tensor('fpn.' + p + '.gn.bias', (C,), seed)
+    return out
+
+
+def synth_fpn_inputs(B, H, W, seed=0):
+    """The four FPN levels (strides 4, 8, 16, 32 of the frame) for a decoder map of H x W (stride 8)."""
+    g = _gen(f'fpnin.{B}.{H}.{W}', seed)
+    return [torch.randn(B, C, h, w, generator=g) for h, w in ((2 * H, 2 * W), (H, W), (H // 2, W // 2), (H // 4, W // 4))]

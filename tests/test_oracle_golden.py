@@ -113,3 +113,18 @@ def test_fpn_pred_restatement_matches_reference(name):
         out = torch.stack(kernel_head_ref.fpn_pred(synth.synth_fpn_pred_state(seed), synth.synth_fused_map(B, H, W, seed)))
     l2, mx = rel_err(out, g['maps'])
     assert l2 < 1e-6 and mx < 1e-6, (name, l2, mx)
+
+
+def test_semantic_fpn_restatement_matches_reference():
+    """oracle/semantic_fpn_ref.py (the oracle of the next row) against the real
+    SemanticFPNWrapper.forward (semantic_fpn.py:198-235): sine positional encoding, the 3x3 conv + GN + ReLU pyramid
+    with its bilinear x2 steps, sum fusion, conv_pred + aux_convs."""
+    from oracle import semantic_fpn_ref
+    name = 'semantic_fpn_b1_h16_w24_s0'
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    B, H, W, seed = int(g['B']), int(g['H']), int(g['W']), int(g['seed'])
+    with torch.no_grad():
+        _, maps = semantic_fpn_ref.semantic_fpn_forward(synth.synth_semantic_fpn_state(seed),
+                                                        synth.synth_fpn_inputs(B, H, W, seed))
+    l2, mx = rel_err(torch.stack(maps), g['maps'])
+    assert l2 < 1e-6 and mx < 1e-6, (l2, mx)
