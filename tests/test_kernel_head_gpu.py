@@ -254,3 +254,30 @@ def test_kernel_head_module_matches_reference_and_feeds_iter_head(dev):
     res = roi.decode(got['x_feats'], got['proposal_feats'], got['mask_preds'], got['depth_feats'], got['depth_proposal'])
     torch.cuda.synchronize()
     assert res['scaled_mask_preds'].shape == (B, 111, 2 * H, 2 * W) and torch.isfinite(res['scaled_mask_preds']).all()
+
+
+def test_kernel_head_tail_edge_cases(dev):
+    """(a) a map smaller than one 32-pixel block / one 128-pixel tile with an odd batch; (b) constant input maps: every
+    GroupNorm group of the conv output is constant over the pixels but not over its 8 channels, and an all-zero map
+    makes the variance exactly 0 (rstd = 1/sqrt(eps), output = ReLU(beta))."""
+    seed = 4
+    sd = synth.synth_kernel_head_state(seed)
+    B, H, W = 5, 4, 6
+    maps = synth.synth_fpn_maps(B, H, W, seed)
+    tail, out = run_tail(dev, sd, maps, H, W)
+    with torch.no_grad():
+        want = ref.decode_init_proposals(sd, maps)
+    for k in ('x_feats', 'depth_feats', 'mask_preds', 'seg_preds', 'depth_pred'):
+        l2, mx = rel_err(out[k].cpu(), want[k])
+        assert l2 < TIGHT and mx < TIGHT, ('tiny', k, l2, mx)
+    B, H, W = 2, 8, 12
+    const = [torch.full((B, 256, H, W), 0.75), torch.zeros(B, 256, H, W), torch.full((B, 256, H, W), 2.0)]
+    const[0][1] = 0.0                                    # image 1 of the first map: all zero as well
+    tail, out = run_tail(dev, sd, const, H, W)
+    with torch.no_grad():
+        want = ref.decode_init_proposals(sd, const)
+    for k in ('x_feats', 'depth_feats', 'seg_preds', 'depth_pred', 'mask_preds'):
+        a, b = out[k].cpu(), want[k]
+        assert torch.isfinite(a).all(), k
+        # a constant map is the worst case for E[y^2] - mean^2: compare absolutely, at the scale of the outputs
+        assert (a - b).abs().max() < 2e-4 * max(1.0, b.abs().max().item()), ('const', k, (a - b).abs().max().item())
