@@ -192,6 +192,43 @@ def run_semantic_fpn_case(rpn, B, H, W, seed):
     return dict(maps=torch.stack(outs).numpy().astype(np.float32))
 
 
+def run_tracking_case(seed=0):
+    """polyphonic_former_video.py:364-403 + :408-419 on a synthetic clip: the reference's own track_roi_extractor
+    (SingleRoIExtractor + RoIAlign), track head, mask -> box helpers and QuasiDenseEmbedTracker, called in the
+    reference's order (the detector around them is not needed for this path)."""
+    shim.install()
+    import polyphonic  # noqa: F401
+    from mmdet.models.builder import build_head, build_roi_extractor
+    from polyphonic.funcs.utils import tensor_mask2box
+    from polyphonic.video.qdtrack.builder import build_tracker
+    from polyphonic.video.utils import batch_mask2boxlist, bboxlist2roi
+    cfg = shim.load_config('/root/reference/configs/polyphonic_video/poly_r50_cityscapes_1x.py')
+    extractor = build_roi_extractor(cfg.model.bbox_roi_extractor)
+    head = build_head(cfg.model.track_head)
+    head.load_state_dict(synth.synth_track_head_state(seed), strict=True)
+    head.eval()
+    tracker = build_tracker(cfg.model.tracker)
+    out = {}
+    with torch.no_grad():
+        for t, fr in enumerate(synth.synth_clip(seed=seed)):
+            masks = fr['masks'].float()
+            rois = bboxlist2roi(batch_mask2boxlist([masks])).clamp(min=0.0)                     # :412-415
+            embeds = head(extractor(fr['feats'][:extractor.num_inputs], rois))                  # :416-417
+            boxes = torch.zeros((masks.shape[0], 5))
+            boxes[:, 4] = fr['scores']
+            boxes[:, :4] = torch.tensor(tensor_mask2box(masks))                                 # :386-389
+            kept, labels, ids = tracker.match(bboxes=boxes, labels=fr['labels'].long(), track_feats=embeds,
+                                              frame_id=t + 1)                                   # :391-396 (cnt starts at 1)
+            ids = ids + 1
+            ids[ids == -1] = 0                                                                  # :398-399
+            out[f'f{t}.rois'] = rois.numpy()
+            out[f'f{t}.embeds'] = embeds.numpy()
+            out[f'f{t}.boxes'] = kept.numpy()
+            out[f'f{t}.labels'] = labels.numpy()
+            out[f'f{t}.ids'] = ids.numpy()
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -222,6 +259,9 @@ def main():
         np.savez_compressed(path, B=B, H=H, W=W, seed=seed, margin=np.float32(margin), **out)
         print(name, 'seed', seed, 'margin', margin, {k: v.shape for k, v in out.items()},
               f'{os.path.getsize(path) / 1e6:.2f} MB')
+    trk = run_tracking_case(0)
+    np.savez_compressed(os.path.join(GOLD, 'tracking_clip_s0.npz'), seed=0, **trk)
+    print('tracking', {k: v.tolist() for k, v in trk.items() if k.endswith('.ids')})
     u = run_updator_case(head)
     np.savez_compressed(os.path.join(GOLD, 'updator_r37_s0.npz'), **u)
     print('updator', u['out'].shape)

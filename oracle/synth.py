@@ -223,3 +223,44 @@ def synth_fpn_inputs(B, H, W, seed=0):
     """The four FPN levels (strides 4, 8, 16, 32 of the frame) for a decoder map of H x W (stride 8)."""
     g = _gen(f'fpnin.{B}.{H}.{W}', seed)
     return [torch.randn(B, C, h, w, generator=g) for h, w in ((2 * H, 2 * W), (H, W), (H // 2, W // 2), (H // 4, W // 4))]
+
+
+def synth_track_head_state(seed=0):
+    """QuasiDenseMaskEmbedHeadGTMask (track_heads.py:14-76 with configs/polyphonic_video/poly_r50_cityscapes_1x.py:38-52):
+    4 x (3x3 conv + GN), FC 12544 -> 1024, FC 1024 -> 256.  fc_embed is scaled up so that the bi-softmax association of
+    the tracker is decisive on random weights."""
+    out = {}
+    for i in range(4):
+        out[f'convs.{i}.conv.weight'] = synth_tensor(f'track.convs.{i}.conv.weight', (C, C, 3, 3), seed)
+        out[f'convs.{i}.gn.weight'] = synth_tensor(f'track.convs.{i}.gn.weight', (C,), seed)
+        out[f'convs.{i}.gn.bias'] = synth_tensor(f'track.convs.{i}.gn.bias', (C,), seed)
+    out['fcs.0.weight'] = synth_tensor('track.fcs.0.weight', (1024, C * 49), seed)
+    out['fcs.0.bias'] = synth_tensor('track.fcs.0.bias', (1024,), seed)
+    out['fc_embed.weight'] = synth_tensor('track.fc_embed.weight', (C, 1024), seed) * 4.0
+    out['fc_embed.bias'] = synth_tensor('track.fc_embed.bias', (C,), seed)
+    return out
+
+
+def synth_clip(n_frames=4, H=128, W=192, seed=0):
+    """A synthetic clip for the tracking path: per frame the four FPN levels (a static texture plus a little noise, so
+    that the same object embeds alike in neighbouring frames) and K thing masks [K,H,W] drifting across the frame,
+    with class labels and scores.  Object 1 overlaps object 0 almost completely (duplicate removal), object 3 has a low
+    score, object 4 appears in frame 1 only from the second frame on, object 5 is always empty."""
+    g = _gen(f'clip.{n_frames}.{H}.{W}', seed)
+    base = [torch.randn(1, C, H // s, W // s, generator=g) for s in (4, 8, 16, 32)]
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+    frames = []
+    for t in range(n_frames):
+        feats = [b + 0.05 * torch.randn(b.shape, generator=g) for b in base]
+        objs = [  # cy, cx, ry, rx, label, score
+            (30 + 3 * t, 40 + 5 * t, 14, 22, 2, 0.92), (31 + 3 * t, 42 + 5 * t, 13, 21, 2, 0.71),
+            (90 - 2 * t, 120 + 4 * t, 20, 16, 5, 0.64), (60, 150 - 6 * t, 9, 9, 5, 0.22),
+            (100, 30 + 8 * t, 12, 18, 0, 0.55), (0, 0, 0, 0, 1, 0.40)]
+        masks, labels, scores = [], [], []
+        for k, (cy, cx, ry, rx, lab, sc) in enumerate(objs):
+            if k == 4 and t == 0:
+                continue
+            m = ((yy - cy).float() / max(ry, 1)) ** 2 + ((xx - cx).float() / max(rx, 1)) ** 2 <= 1.0 if ry else torch.zeros(H, W, dtype=torch.bool)
+            masks.append(m), labels.append(lab), scores.append(sc)
+        frames.append(dict(feats=feats, masks=torch.stack(masks), labels=torch.tensor(labels), scores=torch.tensor(scores)))
+    return frames

@@ -128,3 +128,28 @@ def test_semantic_fpn_restatement_matches_reference():
                                                         synth.synth_fpn_inputs(B, H, W, seed))
     l2, mx = rel_err(torch.stack(maps), g['maps'])
     assert l2 < 1e-6 and mx < 1e-6, (l2, mx)
+
+
+def test_tracking_restatement_matches_reference():
+    """oracle/tracking_ref.py (the oracle of a row that is not built yet) against the reference's own
+    SingleRoIExtractor + RoIAlign, QuasiDenseMaskEmbedHeadGTMask, mask -> box helpers and QuasiDenseEmbedTracker on a
+    synthetic 4-frame clip (polyphonic_former_video.py:364-419): RoIs, embeddings, surviving boxes and track ids."""
+    from oracle import tracking_ref
+    g = np.load(os.path.join(GOLDEN, 'tracking_clip_s0.npz'))
+    sd = synth.synth_track_head_state(int(g['seed']))
+    tracker = tracking_ref.QuasiDenseTracker()
+    seen = set()
+    with torch.no_grad():
+        for t, fr in enumerate(synth.synth_clip(seed=int(g['seed']))):
+            fm = fr['masks'].float()
+            boxes = torch.stack([tracking_ref.roi_box_of_mask(m) for m in fm])
+            rois = torch.cat([boxes.new_zeros((len(boxes), 1)), boxes], 1).clamp(min=0)
+            assert np.allclose(rois.numpy(), g[f'f{t}.rois'], rtol=0, atol=1e-5)
+            emb = tracking_ref.track_forward(sd, fr['feats'], fm)
+            l2, mx = rel_err(emb, g[f'f{t}.embeds'])
+            assert l2 < 1e-6 and mx < 1e-6, (t, l2, mx)
+            ids, kept = tracking_ref.track_frame(sd, tracker, fr['feats'], fr['masks'], fr['labels'], fr['scores'], t + 1)
+            assert ids.tolist() == g[f'f{t}.ids'].tolist(), (t, ids.tolist(), g[f'f{t}.ids'].tolist())
+            assert np.allclose(kept.numpy(), g[f'f{t}.boxes'], rtol=0, atol=1e-5)
+            seen.update(ids.tolist())
+    assert 0 in seen and len(seen) >= 6     # backdrops, persistent tracks and new tracks all occur in the clip
