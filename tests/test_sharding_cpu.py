@@ -76,3 +76,53 @@ def test_gather_frame_records_world2_gloo():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def _tracking_worker(rank, world, port, q):
+    """Video mode end to end on CPU: the frames of a clip are dealt to the ranks, every rank computes the per-frame
+    records of ITS frames (here with the oracle standing in for the device path), one all_gather, then every rank
+    replays the association in frame order."""
+    import numpy as np
+    from conftest import GOLDEN
+    from oracle import synth, tracking_ref
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        gold = np.load(os.path.join(GOLDEN, 'tracking_clip_s0.npz'))
+        clip = synth.synth_clip(seed=0)
+        sd = synth.synth_track_head_state(0)
+        mine = []
+        with torch.no_grad():
+            for f in sharding.shard_indices(len(clip), rank, world):
+                fr = clip[f]
+                fm = fr['masks'].float()
+                boxes = torch.cat([torch.stack([tracking_ref.tight_box_of_mask(m) for m in fm]),
+                                   fr['scores'].view(-1, 1).float()], dim=1)
+                mine.append((f, boxes, fr['labels'], tracking_ref.track_forward(sd, fr['feats'], fm)))
+        recs = sharding.gather_frame_records(mine, len(clip), max_k=8)
+        tracker = tracking_ref.QuasiDenseTracker()
+        ok = len(recs) == len(clip)
+        for f, boxes, labels, embeds in recs:
+            _, _, ids = tracker.match(boxes, labels, embeds, f + 1)
+            ids = ids + 1
+            ids[ids == -1] = 0
+            ok = ok and ids.tolist() == gold[f'f{f}.ids'].tolist()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_clip_tracking_matches_reference_world2_gloo():
+    """Frame-sharded video mode reproduces the track ids of the reference's sequential loop (the golden of
+    polyphonic_former_video.py:364-403 run on the same synthetic clip) on both ranks."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tracking_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
