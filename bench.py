@@ -110,7 +110,10 @@ def run_reference(args, rank, world):
     line = dict(impl='reference', metric='decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)',
                 value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=1e3 * dt / steps,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=workload_config(args, 1),
+                # the SAME workload description as our arm (the driver compares the two lines); what this arm actually
+                # ran per step is a bounded sample of it and is stated in `sample`
+                config=dict(workload_config(args, args.batch), launch='host cores (PyTorch CPU)',
+                            reference_sample='one frame of the batch per step'),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
