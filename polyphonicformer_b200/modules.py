@@ -257,7 +257,20 @@ class KernelUpdateHead(nn.Module):
             depth_proposal.reshape(B, N, C).float(), H, W)
         return (cls, logits[0], obj.reshape(B, N, C, 1, 1), logits[1], dep.reshape(B, N, C, 1, 1))
 
-    # post-processing helpers used by KernelUpdateIterHead.get_panoptic live in postprocess.py ("next")
+    # The reference's KernelUpdateIterHead.get_panoptic calls three helpers on the last stage head
+    # (kernel_update.py:423-442 -> kernel_update_head.py:593-650).  Here they are fused into pf_panoptic
+    # (postprocess.get_panoptic, called by this package's KernelUpdateIterHead), which never materialises the x4
+    # up-sampled maps they return; a caller that mixes the reference's iter head with this stage head gets a clear error.
+    def rescale_masks(self, masks_per_img, img_meta):
+        _unsupported('KernelUpdateHead.rescale_masks outside polyphonicformer_b200.postprocess.get_panoptic '
+                     '(use this package\'s KernelUpdateIterHead, which fuses it into pf_panoptic)')
+
+    def rescale_depth(self, depth, img_meta):
+        _unsupported('KernelUpdateHead.rescale_depth outside polyphonicformer_b200.postprocess.get_panoptic '
+                     '(use this package\'s KernelUpdateIterHead, which fuses it into pf_panoptic)')
+
+    def segm2result(self, mask_preds, det_labels, cls_scores, depth_preds):
+        _unsupported('KernelUpdateHead.segm2result (the non-panoptic result format)')
 
 
 class KernelUpdateIterHead(nn.Module):
