@@ -13,6 +13,8 @@ ranks.  `e2e` = same metric through DecoderEngine with pinned HOST buffers: H2D 
 step's results inside the timed region.  `roofline` = dominant kernel against MEASURED_PEAKS.json; `kernels` lists
 every kernel of the step.  `cpu_baseline` / `--impl reference` = the CPU oracle (oracle/decoder_ref.py, a pinned
 restatement of the reference's forward; the reference itself needs mmcv, absent on the box) on the host cores.
+Non-headline extras on rank 0 at N=1: `library_baseline` (the same oracle through PyTorch eager on the same GPU),
+`postprocess` / `e2e_simple_test` (pf_panoptic), `kernel_head` (the KernelHead tail that produces the decoder's inputs).
 """
 import argparse
 import ctypes
