@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 C, N_KERNELS, STAGES, NUM_CLASSES = 256, 111, 3, 19
+METRIC = 'decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)'
 
 
 def parse():
@@ -46,6 +47,7 @@ def parse():
                     help='also materialise the (unobservable) fp32 logits + depth einsum of stages 0..S-2')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-check', action='store_true', help='skip the oracle check of one frame of the timed batch')
     ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
     ap.add_argument('--no-kernel-head', action='store_true', help='skip the (non-headline) KernelHead-tail timing')
     ap.add_argument('--no-graph', action='store_true', help='launch every step from the host instead of replaying a CUDA graph')
@@ -85,51 +87,60 @@ def host_inputs(B, H, W, seed):
 
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
-    """The reference's own algorithm on the host cores: oracle/decoder_ref.py (pinned against the real reference's
-    outputs by tests/test_oracle_golden.py).  Each step = ONE frame (bounded sample of the batch-4 workload)."""
+    """The reference's own algorithm on the host cores: oracle/decoder_ref.py, a restatement pinned to the REAL
+    reference's outputs by tests/test_oracle_golden.py (the reference itself needs mmcv, absent on the box).  Same
+    workload as our arm: every step decodes the same batch of `--batch` frames, `--steps` steps after `--warmup`."""
     if rank != 0:
         return
     from oracle import decoder_ref as ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd, _ = synth_state()
-    H, W = args.height // 8, args.width // 8
-    inp = host_inputs(1, H, W, 0)
+    B, H, W = args.batch, args.height // 8, args.width // 8
+    inp = host_inputs(B, H, W, 0)
     x, d = inp['x'].float(), inp['d'].float()
-    prop, dprop = inp['prop'].reshape(1, N_KERNELS, C, 1, 1), inp['dprop'].reshape(1, N_KERNELS, C, 1, 1)
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
+    prop, dprop = inp['prop'].reshape(B, N_KERNELS, C, 1, 1), inp['dprop'].reshape(B, N_KERNELS, C, 1, 1)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+
+    def one_step():   # frame by frame: the reference's own test loop runs samples_per_gpu=1 (configs/_base_/datasets)
+        for b in range(B):
+            ref.decoder_forward(sd, x[b:b + 1], prop[b:b + 1], inp['mask'][b:b + 1], d[b:b + 1], dprop[b:b + 1])
+
     with torch.no_grad():
         for _ in range(warm):
-            ref.decoder_forward(sd, x, prop, inp['mask'], d, dprop)
+            one_step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            ref.decoder_forward(sd, x, prop, inp['mask'], d, dprop)
+            one_step()
         dt = time.perf_counter() - t0
-    fps = steps / dt
-    sample = '%d steps x 1 frame of %dx%d (decoder map %dx%d), fp32, torch %d threads' % (
-        steps, args.height, args.width, H, W, cores)
-    line = dict(impl='reference', metric='decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)',
-                value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=1e3 * dt / steps,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                # the SAME workload description as our arm (the driver compares the two lines); what this arm actually
-                # ran per step is a bounded sample of it and is stated in `sample`
-                config=dict(workload_config(args, args.batch), launch='host cores (PyTorch CPU)',
-                            reference_sample='one frame of the batch per step'),
-                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample),
+    fps = steps * B / dt
+    sample = '%d steps x %d frames of %dx%d (decoder map %dx%d), fp32, torch %d threads' % (
+        steps, B, args.height, args.width, H, W, cores)
+    line = dict(impl='reference', metric=METRIC, value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', config=workload_config(args, B),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample,
+                                  pinned='oracle/decoder_ref.py is pinned to the unmodified reference by '
+                                         'tests/test_oracle_golden.py (fixtures regenerated bit-identically from '
+                                         '/root/reference by oracle/make_golden.py)'),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
 
 def workload_config(args, B):
+    """The workload only -- identical for both arms (the driver compares the two lines)."""
     return dict(workload='poly_r50 image decoder, %dx%d synthetic Cityscapes-shape frames, batch=%d per GPU, '
                          'N=111 kernels (100 queries + 11 stuff), C=256, 3 stages, bf16 feature maps' %
                          (args.height, args.width, B),
                 global_batch=B * args.gpus, decoder_map='%dx%d' % (args.height // 8, args.width // 8),
                 parallelism='dp%d (batch-sharded frames, no collective)' % args.gpus,
                 l2='per-step working set %.0f MB > 126 MB L2 (no flush needed)' % working_set_mb(args, B)
-                if working_set_mb(args, B) > 126 else 'L2 flushed between timed iterations',
-                stage_outputs='all' if args.all_stage_outputs else 'observable-only',
+                if working_set_mb(args, B) > 126 else 'L2 flushed between timed iterations')
+
+
+def launch_info(args, B):
+    """How OUR arm runs the workload (not part of `config`)."""
+    return dict(stage_outputs='all' if args.all_stage_outputs else 'observable-only',
                 batch_windows=args.splits if args.splits else 1,
                 launch='eager' if args.no_graph else 'cuda-graph replay')
 
@@ -324,6 +335,13 @@ def run_ours(args, rank, world, local_rank):
     ms_total = t.item()
     value = world * B * args.steps / (ms_total / 1e3)
 
+    # ---------------- parity of the step that was just timed (outside the timed region): frame 0 against the oracle
+    check = None
+    if rank == 0 and not args.no_check:
+        step()
+        torch.cuda.synchronize()
+        check = parity_check(sd, hin, buf, args.all_stage_outputs)
+
     # ---------------- per-kernel timing (same arguments as inside the step), CUDA events on the launching stream
     kernels = kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, dev) if rank == 0 else None
 
@@ -349,12 +367,14 @@ def run_ours(args, rank, world, local_rank):
                     ms_single_launch_l2_flushed=dom['ms_single_launch_l2_flushed'],
                     traffic_source='profiles/r1_traffic.json (ncu --set full, dram__bytes_read.sum + '
                                    'dram__bytes_write.sum per launch)' if dom['traffic'] else None)
-    line = dict(metric='decoder frames/sec (1024x2048, 100 queries -> 111 kernels, 3 stages)', value=value,
+    line = dict(metric=METRIC, value=value,
                 unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='bf16', data='synthetic', config=workload_config(args, B), clocks=clocks,
+                dtype='bf16', data='synthetic', config=workload_config(args, B), launch=launch_info(args, B), clocks=clocks,
                 gpu_launches=launches_per_step * args.steps, launches_per_step=launches_per_step,
                 roofline=roofline, kernels=kernels, ms_per_stage=ms_total / args.steps / STAGES)
+    if check:
+        line['check'] = check
     if e2e:
         if numa_cpus:
             e2e['host_cpus_bound_per_rank'] = numa_cpus
@@ -378,6 +398,32 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         line['kernel_head'] = kernel_head_timing(args, B, dev, pk['hbm'], cpu=not args.no_cpu_baseline)
     emit(line)
+
+
+def parity_check(sd, hin, buf, all_stage_outputs):
+    """Frame 0 of the batch the timed steps decoded, against oracle/decoder_ref.py (fp32, host) on the same bf16-rounded
+    feature maps: norm-wise relative error of every output of the step and the number of final mask bits
+    (logit > 0) that differ.  The north-star gate is 1e-3 on the mask and depth logits."""
+    from oracle import decoder_ref as ref
+    x, d = hin['x'][:1].float(), hin['d'][:1].float()
+    prop, dprop = hin['prop'][:1].reshape(1, N_KERNELS, C, 1, 1), hin['dprop'][:1].reshape(1, N_KERNELS, C, 1, 1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        want = ref.decoder_forward(sd, x, prop, hin['mask'][:1], d, dprop, return_all_stages=True)
+    got = dict(cls_score=buf['cls'][:1], mask_preds=buf['logits'][0, :1], depth_preds=buf['logits'][1, :1],
+               scaled_mask_preds=buf['scaled'][0, :1], scaled_depth_preds=buf['scaled'][1, :1],
+               object_feats=buf['obj'][:1].reshape(1, N_KERNELS, C, 1, 1),
+               depth_proposal=buf['dep'][:1].reshape(1, N_KERNELS, C, 1, 1))
+    rel = {}
+    for k, v in got.items():
+        a, b = v.detach().cpu().double().flatten(), want[k].double().flatten()
+        rel[k] = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    m_got, m_ref = got['mask_preds'].cpu() > 0, want['mask_preds'] > 0
+    near = [float((st['mask_preds'].abs() < 1e-4).sum()) for st in want['stages']]
+    return dict(frame=0, oracle='oracle/decoder_ref.py (fp32, host) on the same bf16-rounded feature maps',
+                rel_l2=rel, worst_rel_l2=max(rel.values()), gate=1e-3, passed=max(rel.values()) < 1e-3,
+                final_mask_bits=int(m_ref.numel()), final_mask_bits_flipped=int((m_got != m_ref).sum()),
+                oracle_logits_within_1e4_of_0_per_stage=near)
 
 
 def kernel_head_timing(args, B, dev, peak_gbs, cpu=True):

@@ -1025,11 +1025,18 @@ struct Maps {
 
 template <int MODE>
 static int launch_tc(const Maps& mp, const TcArgs& a, int tiles, int njobs, int cluster, cudaStream_t st) {
-    static bool attr_done = false;   // per-process; the attribute is a property of the function
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tcgemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-        if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "tcgemm smem attribute: %s", cudaGetErrorString(e));
-        attr_done = true;
+    // the attribute is per (function, device): remember which devices have it (a process may drive several GPUs)
+    static std::mutex attr_mu;
+    static bool attr_done[64] = {};
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(attr_mu);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(tcgemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+            if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "tcgemm smem attribute: %s", cudaGetErrorString(e));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -15,6 +15,7 @@ The ``nn`` layers below only HOLD parameters.  All forward arithmetic runs in li
 raise.  Inference only (``forward_train`` / losses are out of scope).
 """
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -34,6 +35,33 @@ def _unsupported(what):
 
 def _version_key(module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class _SharedFeats:
+    """Explicit side channel between ``KernelHead`` (producer) and ``KernelUpdateIterHead`` / ``KernelUpdateHead``
+    (consumers): the feature maps ``KernelHead`` returns are views of (or fp32 copies next to) the decoder's bf16 feature
+    buffer ``[2][B][256][HWp]``; this table maps the IDENTITY of those two returned tensor objects to that buffer, so a
+    consumer that receives exactly those objects skips the re-cast.  Entries hold weak references only: when the
+    returned tensors die the entry dies with them, and a tensor that merely reuses the address (the next frame through
+    the caching allocator), or any derived tensor (``.float()``, ``.contiguous()``, a slice), never matches -- it takes
+    the cast path, which is correct for any input."""
+
+    def __init__(self):
+        self._by_id = {}
+
+    def publish(self, x, depth, feats):
+        key = id(x)
+        self._by_id[key] = (weakref.ref(x, lambda _r, k=key: self._by_id.pop(k, None)), weakref.ref(depth), feats,
+                            x._version, depth._version)
+
+    def lookup(self, x, depth):
+        e = self._by_id.get(id(x))
+        if e is None or e[0]() is not x or e[1]() is not depth or e[3] != x._version or e[4] != depth._version:
+            return None
+        return e[2]
+
+
+SHARED_FEATS = _SharedFeats()
 
 
 class KernelUpdator(nn.Module):
@@ -124,7 +152,13 @@ class _LossCfg(ConfigDict):
 
 
 class KernelUpdateHead(nn.Module):
-    """One decoder stage (reference: polyphonic/kernel_update_head.py:18-353)."""
+    """One decoder stage (reference: polyphonic/kernel_update_head.py:18-353).
+
+    The constructor DEFAULTS are the reference's (num_mask_fcs=3, conv_kernel_size=3, a 'DynamicConv' updator with 64
+    feature channels) so that configs which rely on them mean the same thing here -- but the sm_100a kernels implement
+    the configuration the shipped configs select (configs/_base_/models/polyphonic_former.py:111-164: num_mask_fcs=1,
+    conv_kernel_size=1, kernel_updator_cfg type 'KernelUpdator' with 256 channels), and anything else raises in the
+    constructor: ``KernelUpdateHead()`` with no arguments is therefore an error, as documented in INTEGRATION.md."""
 
     def __init__(self, num_classes=80, num_thing_classes=80, num_stuff_classes=53, num_ffn_fcs=2, num_heads=8,
                  num_cls_fcs=1, num_mask_fcs=3, feedforward_channels=2048, in_channels=256, out_channels=256,
@@ -230,13 +264,18 @@ class KernelUpdateHead(nn.Module):
         return self._engine[1]
 
     def _prepared_feats(self, x, depth_feats):
-        shared = getattr(x, '_pf_feats', None)   # produced by KernelHead below: already in the decoder's layout
-        if shared is not None and getattr(depth_feats, '_pf_feats', None) is shared:
+        """The decoder-layout bf16 copy of (x, depth_feats).  Reused only for the very same tensor OBJECTS at the same
+        version: via SHARED_FEATS when KernelHead produced them, else via a one-entry cache that holds weak references
+        (an address recycled by the caching allocator for the next frame is a different object and misses)."""
+        shared = SHARED_FEATS.lookup(x, depth_feats)
+        if shared is not None:
             return shared
-        key = (x.data_ptr(), x._version, depth_feats.data_ptr(), depth_feats._version, tuple(x.shape), x.dtype)
-        if self._feats_cache is None or self._feats_cache[0] != key:
-            self._feats_cache = (key, self.engine(x.device).prepare_feats(x, depth_feats))
-        return self._feats_cache[1]
+        c = self._feats_cache
+        if c is not None and c[0]() is x and c[1]() is depth_feats and c[2] == (x._version, depth_feats._version):
+            return c[3]
+        feats = self.engine(x.device).prepare_feats(x, depth_feats)
+        self._feats_cache = (weakref.ref(x), weakref.ref(depth_feats), (x._version, depth_feats._version), feats)
+        return feats
 
     def forward(self, x, proposal_feat, mask_preds, prev_cls_score=None, mask_shape=None, img_metas=None,
                 depth_preds=None, depth_proposal=None, depth_feats=None, _feats=None):
@@ -443,6 +482,10 @@ class KernelHead(nn.Module):
         self.conv_normal_init, self.mask_out_stride, self.hard_target = conv_normal_init, mask_out_stride, hard_target
         self.ignore_label, self.cat_stuff_mask, self.with_depth = ignore_label, cat_stuff_mask, with_depth
         self.semantic_out_cfg = semantic_out_cfg
+        # reference: x_feats / depth_feats are fp32 NCHW.  Default here: bf16 views of the decoder's feature buffer (the
+        # storage precision of the decoder); return_fp32_feats=True returns fp32 tensors instead
+        # (the decoder still consumes the shared bf16 buffer through SHARED_FEATS)
+        self.return_fp32_feats = bool(kwargs.pop('return_fp32_feats', False))
         for name, cfg in (('loss_mask', loss_mask), ('loss_seg', loss_seg), ('loss_cls', loss_cls), ('loss_dice', loss_dice),
                           ('loss_rank', loss_rank), ('loss_depth', loss_depth), ('loss_semantic_seg', loss_semantic_seg)):
             setattr(self, name, _LossCfg(cfg) if cfg is not None else None)   # inference reads .use_sigmoid only
@@ -461,6 +504,8 @@ class KernelHead(nn.Module):
         seg_sigmoid = bool(getattr(self.loss_seg, 'use_sigmoid', True)) if self.loss_seg is not None else True
         self.localization_fpn = build_neck(localization_fpn)
         groups = norm_cfg.get('num_groups', 32)
+        if groups != 32:
+            _unsupported('GroupNorm with num_groups=%d (pf_kernel_head / pf_fpn_pred implement 32 groups of 8 channels)' % groups)
         self.init_kernels = nn.Conv2d(out_channels, num_proposals, 1, bias=False)
         self.conv_seg = nn.Conv2d(out_channels, num_classes if seg_sigmoid else num_classes + 1, 1)
         self.loc_convs = nn.ModuleList([_ConvGN(in_channels, groups)])
@@ -500,8 +545,17 @@ class KernelHead(nn.Module):
         """The three SemanticFPN outputs as bf16 [3][B][256][HWp].  With the reference's SemanticFPNWrapper the pyramid
         (semantic_fpn.py:198-219) stays its PyTorch code and only conv_pred / aux_convs (:221-229) run here."""
         fpn = self.localization_fpn
+        def conv_gn_relu_1x1(m):
+            """what pf_fpn_pred implements: ConvModule(256, 256, 1, bias=False) + GroupNorm(32, eps=1e-5) + ReLU"""
+            conv, gn, act = getattr(m, 'conv', None), getattr(m, 'gn', None), getattr(m, 'activate', None)
+            return (isinstance(conv, nn.Conv2d) and tuple(conv.kernel_size) == (1, 1) and conv.bias is None
+                    and conv.in_channels == conv.out_channels == 256 and tuple(conv.stride) == (1, 1)
+                    and isinstance(gn, nn.GroupNorm) and gn.num_groups == 32 and abs(gn.eps - 1e-5) < 1e-12
+                    and isinstance(act, nn.ReLU))
+
         fused_ok = (all(hasattr(fpn, a) for a in ('convs_all_levels', 'conv_pred', 'aux_convs', 'start_level', 'end_level'))
-                    and len(fpn.aux_convs) == 2 and not getattr(fpn, 'fuse_by_cat', False) and getattr(fpn, 'with_pred', True))
+                    and len(fpn.aux_convs) == 2 and not getattr(fpn, 'fuse_by_cat', False) and getattr(fpn, 'with_pred', True)
+                    and all(conv_gn_relu_1x1(m) for m in (fpn.conv_pred, fpn.aux_convs[0], fpn.aux_convs[1])))
         if not fused_ok:
             feats = fpn(img)
             if not isinstance(feats, (list, tuple)) or len(feats) != 3:
@@ -535,12 +589,15 @@ class KernelHead(nn.Module):
             _unsupported('KernelHead on a %s device' % dev.type)
         tail = self.tail(dev)
         maps, (H, W) = self._localization_maps(img, tail)
-        out = tail.forward(maps, H, W)
+        out = tail.forward(maps, H, W, want_fp32_feats=self.return_fp32_feats)
         feats = out['feats']
         B, HW = feats.shape[1], H * W
-        x_feats = feats[0][..., :HW].reshape(B, 256, H, W)
-        depth_feats = feats[1][..., :HW].reshape(B, 256, H, W)
-        x_feats._pf_feats = depth_feats._pf_feats = feats
+        if self.return_fp32_feats:
+            x_feats, depth_feats = out['x_feats'], out['depth_feats']
+        else:
+            x_feats = feats[0][..., :HW].reshape(B, 256, H, W)
+            depth_feats = feats[1][..., :HW].reshape(B, 256, H, W)
+        SHARED_FEATS.publish(x_feats, depth_feats, feats)
         return (out['proposal_feats'], x_feats, out['mask_preds'], None, out['seg_preds'], depth_feats,
                 out['depth_proposal'], out['depth_pred'], None)
 

@@ -86,9 +86,10 @@ def test_decode_loop_matches_reference_golden(dev, name, all_outputs):
         assert l2 < GATE and mx < GATE, (name, k, l2, mx)
 
 
-@pytest.mark.parametrize('B,H,W', [(1, 32, 64), (1, 48, 156), (2, 128, 256)])
+@pytest.mark.parametrize('B,H,W', [(1, 32, 64), (1, 48, 156), (2, 128, 256), (4, 128, 256)])
 def test_decode_matches_oracle_at_config_shapes(dev, B, H, W):
-    """BASELINE.json configs A (256x512), E (384x1248) and B-shape (1024x2048) against the CPU oracle."""
+    """BASELINE.json configs A (256x512), E (384x1248), the B-shape (1024x2048) and the HEADLINE configuration itself
+    (configs[1]: batch 4 of 1024x2048, what bench.py times) against the CPU oracle."""
     seed = 2
     eng, sd = make_engine(seed, dev)
     inp = synth.synth_decoder_inputs(B, H, W, seed)

@@ -126,3 +126,25 @@ def test_kernel_head_builds_from_reference_config():
         pf.KernelHead(**dict(rpn_head_cfg(), localization_fpn=_FakeNeck(), feat_refine=True))
     with pytest.raises(NotImplementedError):
         pf.KernelHead(**dict(rpn_head_cfg(), localization_fpn=_FakeNeck(), cat_stuff_mask=False))
+
+
+def test_shared_feats_channel_is_identity_keyed():
+    """The KernelHead -> decoder side channel matches tensor OBJECTS (weak references), never addresses: a derived
+    tensor, a modified tensor, or a new tensor at a recycled address misses and takes the cast path."""
+    import gc
+    from polyphonicformer_b200.modules import _SharedFeats
+    reg = _SharedFeats()
+    x, d, feats = torch.zeros(2, 3), torch.zeros(2, 3), torch.ones(4)
+    reg.publish(x, d, feats)
+    assert reg.lookup(x, d) is feats
+    assert reg.lookup(x.float(), d) is feats        # .float() on fp32 returns the same object ...
+    assert reg.lookup(x.clone(), d) is None          # ... a copy does not
+    assert reg.lookup(x[:], d) is None and reg.lookup(x, d.contiguous().view(2, 3)) is None
+    x.add_(1)                                        # in-place change: version moved on
+    assert reg.lookup(x, d) is None
+    y = torch.zeros(2, 3)
+    reg.publish(y, d, feats)
+    key = id(y)
+    del y
+    gc.collect()
+    assert key not in reg._by_id                     # entry died with the tensor

@@ -105,3 +105,74 @@ def test_simple_test_mask_preds_and_simple_test(dev):
         assert r[3].shape == (8 * H, 8 * W) and r[4].shape == (8 * H, 8 * W)
         assert sorted(s['id'] for s in segs) == list(range(1, len(segs) + 1))
         assert set(np.unique(pan)) <= set([0] + [s['id'] for s in segs])
+
+
+def test_two_frames_through_recycled_addresses(dev):
+    """frame 2's feature maps come back from the caching allocator at frame 1's addresses with
+    ``_version`` 0 again.  The prepared-feature cache must not mistake them for frame 1's (it compares object identity
+    through weak references), so each frame's result equals the result of decoding that frame alone."""
+    B, H, W, seed = 1, 16, 24, 0
+    head = build_roi_head(dev, seed)
+    frames = [synth.synth_decoder_inputs(B, H, W, s) for s in (0, 1)]
+    want = []
+    for f in frames:                        # each frame alone, fresh module state
+        solo = build_roi_head(dev, seed)
+        inp = {k: v.to(dev) for k, v in f.items()}
+        with torch.no_grad():
+            want.append(solo.decode(inp['x_feats'], inp['proposal_feats'], inp['mask_preds'], inp['depth_feats'],
+                                    inp['depth_proposal'])['scaled_mask_preds'].clone())
+        del inp, solo
+    got, addrs = [], []
+    for f in frames:                        # the frame loop of a video / dataset run: inputs freed between frames
+        x, d = f['x_feats'].to(dev), f['depth_feats'].to(dev)
+        addrs.append((x.data_ptr(), d.data_ptr()))
+        with torch.no_grad():
+            out = head.decode(x, f['proposal_feats'].to(dev), f['mask_preds'].to(dev), d, f['depth_proposal'].to(dev))
+        got.append(out['scaled_mask_preds'].clone())
+        torch.cuda.synchronize()
+        del x, d, out
+    # (the allocator normally hands the same blocks back; the assertion below holds either way)
+    for i in range(2):
+        assert torch.equal(got[i], want[i]), 'frame %d decoded from stale features (addresses %r)' % (i, addrs)
+    assert not torch.equal(got[0], got[1])
+
+
+def test_unselected_seeds_flip_count_and_effect(dev):
+    """the un-teacher-forced loop on seeds that were NOT chosen for their margin from 0.  A mask
+    logit within rounding of 0 may binarise differently than in the fp32 oracle; here the flips are COUNTED per stage and
+    their effect on the final logits is bounded, instead of being avoided by seed selection."""
+    from oracle import decoder_ref as ref
+    from polyphonicformer_b200.decoder import DecoderEngine
+    B, H, W = 1, 16, 24
+    report = []
+    for seed in range(4):
+        sd = synth.synth_decoder_state(3, seed)
+        stage_dicts = [{k[len('mask_head.%d.' % s):]: v for k, v in sd.items() if k.startswith('mask_head.%d.' % s)}
+                       for s in range(3)]
+        eng = DecoderEngine(stage_dicts, dev)
+        inp = synth.synth_decoder_inputs(B, H, W, seed)
+        with torch.no_grad():
+            want = ref.decoder_forward(sd, inp['x_feats'], inp['proposal_feats'], inp['mask_preds'], inp['depth_feats'],
+                                       inp['depth_proposal'], return_all_stages=True)
+        feats = eng.prepare_feats(inp['x_feats'].to(dev), inp['depth_feats'].to(dev))
+        mask = inp['mask_preds'].to(dev)
+        obj = inp['proposal_feats'].reshape(B, -1, 256).to(dev)
+        dep = inp['depth_proposal'].reshape(B, -1, 256).to(dev)
+        nflip, nbits = [], mask.numel()
+        for s in range(3):                  # feeding OUR outputs forward (no teacher forcing)
+            cls, logits, obj, dep = eng.stage_forward(s, feats, mask, obj, dep, H, W)
+            mask = logits[0]
+            nflip.append(int(((mask.cpu() > 0) != (want['stages'][s]['mask_preds'] > 0)).sum()))
+        l2, mx = rel_err(mask.cpu(), want['stages'][2]['mask_preds'])
+        margin = min(float(st['mask_preds'].abs().min()) for st in want['stages'][:2])
+        report.append((seed, nflip, margin, l2))
+        # every flip of stages 0/1 moves one pooled row by one pixel's feature vector; with 384-pixel maps that is a
+        # ~1e-2 perturbation of that row, so the final error may exceed the 1e-3 gate on such seeds -- but stays small
+        assert all(n <= 1e-3 * nbits for n in nflip), report      # flips are rare (a few bits of 42 624) ...
+        if nflip[0] == 0 and nflip[1] == 0:
+            assert l2 < GATE, report                              # ... without one the loop meets the gate
+        else:
+            assert l2 < 0.2, report                               # ... with one the error is bounded, and reported
+    print('seed, flipped mask bits per stage (of %d), min |logit| of stages 0/1, final rel err:' % nbits)
+    for r in report:
+        print('  ', r)

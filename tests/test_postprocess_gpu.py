@@ -62,9 +62,14 @@ def test_panoptic_matches_reference_golden(dev, name):
     assert np.all(np.abs(got[stuff, 4] - want[stuff, 4]) <= np.maximum(2, 0.002 * want[stuff, 4]))
     scores = np.array([s.get('score', -1.0) for s in info])
     assert np.allclose(scores, g['seg_score'], rtol=0, atol=1e-7)
-    mismatch = (pan != g['panoptic']).mean()
-    assert mismatch <= 1e-3, mismatch
-    assert near_tie_fraction(inp, meta, pan, g['panoptic'], cfg, roi) == 1.0
+    ndiff, npix = int((pan != g['panoptic']).sum()), pan.size
+    ties = near_tie_fraction(inp, meta, pan, g['panoptic'], cfg, roi)
+    # first-max tie-breaking (lowest entry index wins an exact tie, as torch.argmax does) is what pp_argmax_kernel
+    # implements; what remains are products that differ in the last bits between ATen-CPU and device arithmetic
+    print('%s: %d of %d panoptic pixels differ from the reference (%.4f %%), %.0f %% of them near-ties (top-2 within 1e-5)'
+          % (name, ndiff, npix, 100.0 * ndiff / npix, 100 * ties))
+    assert ndiff <= 1e-3 * npix, (ndiff, npix)
+    assert ties == 1.0, (ndiff, ties)
     same = pan == g['panoptic']
     assert np.allclose(dbasic, g['depth_basic'], rtol=1e-5, atol=1e-6)
     assert np.allclose(dfinal[same], g['depth_final'][same], rtol=1e-5, atol=1e-6)
@@ -85,6 +90,7 @@ def test_panoptic_full_size_against_restatement_on_device(dev):
     assert len(info) == len(info_r) >= 5
     got, want = segments_as_array(info), segments_as_array(info_r)
     assert np.array_equal(got[:, :4], want[:, :4])
+    print('full size: %d of %d panoptic pixels differ from the restatement on the device' % (int((pan != pan_r).sum()), pan.size))
     assert (pan != pan_r).mean() <= 1e-4
     same = pan == pan_r
     assert np.allclose(dbasic, dbasic_r, rtol=1e-5, atol=1e-6)
