@@ -51,6 +51,8 @@ def parse():
     ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
     ap.add_argument('--no-kernel-head', action='store_true', help='skip the (non-headline) KernelHead-tail timing')
     ap.add_argument('--no-graph', action='store_true', help='launch every step from the host instead of replaying a CUDA graph')
+    ap.add_argument('--per-layer-update', action='store_true',
+                    help='A/B: run the small-N block as 12 per-layer launches (csrc/pf_update.cu) instead of the fused cluster kernel')
     ap.add_argument('--splits', type=int, default=None, help='batch windows decoded concurrently (default: 1)')
     return ap.parse_args()
 
@@ -142,6 +144,7 @@ def launch_info(args, B):
     """How OUR arm runs the workload (not part of `config`)."""
     return dict(stage_outputs='all' if args.all_stage_outputs else 'observable-only',
                 batch_windows=args.splits if args.splits else 1,
+                small_n_block='12 per-layer launches' if args.per_layer_update else 'fused 8-CTA-cluster kernel (1 launch per stage)',
                 launch='eager' if args.no_graph else 'cuda-graph replay')
 
 
@@ -269,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
     from polyphonicformer_b200 import _cabi
     from polyphonicformer_b200.decoder import DecoderEngine, _ptr, _stream_ptr
     lib = _cabi.load()
+    lib.pf_set_fused_update(0 if args.per_layer_update else 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
@@ -506,7 +510,8 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
          2 * 2 * B * N * C * HW,
          lambda i: _cabi.call('pf_mask_pool', _ptr(featsR[i]), _ptr(bitsR[i]), _ptr(partial), _ptr(cntp), B, N, HW, HWp,
                               2, S, st)),
-        ('kernel_update (small-N block, 12 launches)', STAGES, 'latency', 0, 0,
+        ('kernel_update (small-N block, %s)' % ('12 per-layer launches' if args.per_layer_update else 'fused cluster kernel, 1 launch'),
+         STAGES, 'latency', 0, 0,
          lambda i: _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[i % STAGES].struct), _ptr(partial), _ptr(cntp),
                               S, _ptr(obj), _ptr(dep), _ptr(obj_o), _ptr(dep_o), _ptr(cls), None, _ptr(kern),
                               _ptr(kbias), _ptr(ws), wsb, B, N, 0, st)),
@@ -567,8 +572,16 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
         t = traffic.get(nm[0]) if nm else None
         k['traffic'] = (t['dram_read_bytes'] + t['dram_write_bytes']) * nm[1] if t else None
         if k['bound'] == 'latency':
-            k['note'] = ('latency / weight-streaming bound (0.88 GFLOP and 16 MB of bf16 hi+lo weights per image-stage '
-                         'over 12 dependent launches): reported in ms only, no roofline fraction')
+            # what the block must move whatever its schedule: the stage's weights (bf16 hi + lo) once from L2/HBM per
+            # launch; 3-MMA split of 2 * rows * params FLOP per unit
+            wbytes = 2 * 4.02e6 * 2 * 2 / 2   # 4.02 M params per stage (both branches), hi + lo bf16 planes
+            k['weight_bytes'] = wbytes
+            k['weight_stream_GBps'] = wbytes / (k['ms'] * 1e-3) / 1e9
+            k['tensor_TFLOPs_issued'] = 3 * 2 * 128 * 4.02e6 * B / (k['ms'] * 1e-3) / 1e12
+            k['note'] = ('a chain of ten dependent layers on 128 rows per image: latency-bound, not roofline-bound; the '
+                         'stage\'s weights (%.1f MB of bf16 hi + lo) streamed once per launch = %.0f GB/s, issued MMA work '
+                         '(3-way split, rows padded to 128) = %.1f TFLOP/s' %
+                         (wbytes / 1e6, k['weight_stream_GBps'], k['tensor_TFLOPs_issued']))
     return out
 
 

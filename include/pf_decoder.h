@@ -155,6 +155,13 @@ int pf_kernel_update(const pf_stage_weights* w_host, const float* partial, const
                      float* kern, uint16_t* kern_split, float* kbias, void* workspace, size_t workspace_bytes, int B,
                      int N, int cls_sigmoid, void* stream);
 
+/* pf_kernel_update has two implementations with the same results (tests/test_stage_fused_gpu.py):
+ *   fused (default): ONE launch, an 8-CTA thread-block cluster per (image, branch) keeps the 128 x 256 activation block
+ *                    on chip across the ten layers (csrc/pf_stage.cu);
+ *   per-layer:       12 dependent launches (csrc/pf_update.cu), also what pf_kernel_updator uses.
+ * Returns the previous setting.  Process-wide; meant for A/B measurements and tests. */
+int pf_set_fused_update(int on);
+
 /* fp32 kernels [n_units][N][256] -> kern_split (for callers that produce the dynamic kernels themselves) */
 int pf_split_kernels(const float* kern, uint16_t* kern_split, int n_units, int N, void* stream);
 

@@ -78,6 +78,7 @@ _SIGS = {
     'pf_kernel_update': (c_int, [POINTER(StageWeights), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
                                  c_int, c_void_p]),
+    'pf_set_fused_update': (c_int, [c_int]),
     'pf_split_kernels': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'pf_updator_workspace_bytes': (c_size_t, [c_int]),
     'pf_kernel_updator': (c_int, [POINTER(StageWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,

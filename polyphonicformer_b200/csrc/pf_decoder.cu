@@ -11,6 +11,7 @@ struct DecoderScratch {
     float *partial, *cntp, *kbias;
     uint16_t* kern;
     void* update_ws;
+    float *pp_obj[2], *pp_dep[2];   // ping-pong kernels between stages (the fused small-N kernel must not run in place)
     size_t update_ws_bytes, total;
 };
 
@@ -31,6 +32,10 @@ static DecoderScratch carve(void* base, int B, int N, int HW, int ffn) {
     s.kbias = static_cast<float*>(take((size_t)2 * B * N * 4));
     s.update_ws_bytes = pf_update_workspace_bytes(B, N, ffn);
     s.update_ws = take(s.update_ws_bytes);
+    for (int i = 0; i < 2; ++i) {
+        s.pp_obj[i] = static_cast<float*>(take((size_t)B * N * PF_C * 4));
+        s.pp_dep[i] = static_cast<float*>(take((size_t)B * N * PF_C * 4));
+    }
     s.total = off;
     return s;
 }
@@ -78,8 +83,13 @@ extern "C" int pf_decoder_forward_slice(const pf_stage_weights* stages, int n_st
     for (int st = 0; st < n_stages; ++st) {
         const bool last = st == n_stages - 1;
         if (int e = mask_pool_window(feats, s.bits, s.partial, s.cntp, B_total, b0, B, N, HW, HWp, 2, S, 1, stream)) return e;
-        if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj, dep, obj, dep, cls_out, nullptr, s.kern, s.kbias,
-                                     s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
+        // stage st reads the kernels stage st-1 wrote and writes the other buffer; the last stage writes obj / dep
+        const float* obj_i = st == 0 ? obj : s.pp_obj[(st - 1) & 1];
+        const float* dep_i = st == 0 ? dep : s.pp_dep[(st - 1) & 1];
+        float* obj_o = last ? obj : s.pp_obj[st & 1];
+        float* dep_o = last ? dep : s.pp_dep[st & 1];
+        if (int e = pf_kernel_update(&stages[st], s.partial, s.cntp, S, obj_i, dep_i, obj_o, dep_o, cls_out, nullptr, s.kern,
+                                     s.kbias, s.update_ws, s.update_ws_bytes, B, N, last ? 1 : 0, stream))
             return e;
         int e = PF_OK;
         if (last && scaled_out && !(flags & PF_FWD_ALL_STAGE_OUTPUTS)) {

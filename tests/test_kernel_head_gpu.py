@@ -250,7 +250,12 @@ def test_kernel_head_module_matches_reference_and_feeds_iter_head(dev):
     roi = pf.build_head(dict(rd['roi_head'], train_cfg=None, test_cfg=rd['test_cfg']))
     roi.load_state_dict(synth.synth_decoder_state(3, seed), strict=True)
     roi = roi.to(dev).eval()
-    assert roi.mask_head[0]._prepared_feats(got['x_feats'], got['depth_feats']) is got['x_feats']._pf_feats
+    from polyphonicformer_b200.modules import SHARED_FEATS
+    shared = SHARED_FEATS.lookup(got['x_feats'], got['depth_feats'])
+    assert shared is not None and shared.dtype == torch.bfloat16 and shared.shape[:3] == (2, B, 256)
+    assert roi.mask_head[0]._prepared_feats(got['x_feats'], got['depth_feats']) is shared
+    # a derived tensor is a different object: it must NOT hit the shared buffer (it is re-cast, which is always correct)
+    assert SHARED_FEATS.lookup(got['x_feats'].clone(), got['depth_feats']) is None
     res = roi.decode(got['x_feats'], got['proposal_feats'], got['mask_preds'], got['depth_feats'], got['depth_proposal'])
     torch.cuda.synchronize()
     assert res['scaled_mask_preds'].shape == (B, 111, 2 * H, 2 * W) and torch.isfinite(res['scaled_mask_preds']).all()
