@@ -115,7 +115,16 @@ typedef struct pf_stage_weights {
     int wstack256_rows, wstack_ffn_rows;
     int ffn_channels;          /* 2048 */
     int num_classes;           /* 19 */
+    const float* vec_slices;   /* optional: the vectors above re-gathered per (branch, 32-column slice) for the fused
+                                * small-N kernel, pf_vec_slices_bytes() bytes written by pf_pack_vec_slices(); NULL: the
+                                * kernel launch gathers them into its workspace first (one extra small launch per call) */
 } pf_stage_weights;
+
+/* gather the per-(branch, column slice) copies of a stage's fp32 vectors (biases, LayerNorm gamma | beta) that the fused
+ * small-N kernel bulk-copies into shared memory: out = device buffer of pf_vec_slices_bytes() bytes, 16-byte aligned;
+ * w->vec_slices itself is ignored.  Call once per set of weights and store `out` in pf_stage_weights.vec_slices. */
+size_t pf_vec_slices_bytes(void);
+int pf_pack_vec_slices(const pf_stage_weights* w_host, float* out, void* stream);
 
 /* fp32 NCHW feature maps -> the bf16 [2][B][256][HWp] layout.  Replaces nothing in the reference (storage cast). */
 int pf_cast_feats(const float* x_feats, const float* depth_feats, uint16_t* feats, int B, int HW, int HWp,

@@ -42,7 +42,8 @@ class BranchWeights(Structure):
 class StageWeights(Structure):
     """struct pf_stage_weights."""
     _fields_ = [('br', BranchWeights * 2), ('wstack256', c_void_p), ('wstack_ffn', c_void_p),
-                ('wstack256_rows', c_int), ('wstack_ffn_rows', c_int), ('ffn_channels', c_int), ('num_classes', c_int)]
+                ('wstack256_rows', c_int), ('wstack_ffn_rows', c_int), ('ffn_channels', c_int), ('num_classes', c_int),
+                ('vec_slices', c_void_p)]
 
 
 class HeadWeights(Structure):
@@ -79,6 +80,8 @@ _SIGS = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
                                  c_int, c_void_p]),
     'pf_set_fused_update': (c_int, [c_int]),
+    'pf_vec_slices_bytes': (c_size_t, []),
+    'pf_pack_vec_slices': (c_int, [POINTER(StageWeights), c_void_p, c_void_p]),
     'pf_split_kernels': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'pf_updator_workspace_bytes': (c_size_t, [c_int]),
     'pf_kernel_updator': (c_int, [POINTER(StageWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,

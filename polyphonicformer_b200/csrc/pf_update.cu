@@ -1001,9 +1001,11 @@ PF_DEFINE_DBG_SETTER(set_dbg_update)
 namespace pf {
 int set_dbg_pool(long long* p);
 int set_dbg_einsum(long long* p);
+int set_dbg_stage(long long* p);
 }
 extern "C" int pf_debug_timeline(long long* device_buffer) {
-    const int e = pf::set_dbg_update(device_buffer) | pf::set_dbg_pool(device_buffer) | pf::set_dbg_einsum(device_buffer);
+    const int e = pf::set_dbg_update(device_buffer) | pf::set_dbg_pool(device_buffer) | pf::set_dbg_einsum(device_buffer) |
+                  pf::set_dbg_stage(device_buffer);
     return e == 0 ? PF_OK : pf::set_error(PF_ERR_CUDA, "pf_debug_timeline: cudaMemcpyToSymbol failed (%d)", e);
 }
 

@@ -182,6 +182,15 @@ class PackedStage:
             for name in BranchWeights._PTRS:
                 setattr(bw, name, base + 4 * vecs[(bi, name)] if (bi, name) in vecs else None)
             bw.head_relu = 1 if bi == 0 else 0
+        # per-(branch, column slice) copies of the vectors for the fused small-N kernel (gathered on the device, once);
+        # a host-only packing (the CPU algebra test) leaves the field NULL
+        self.vec_slices = None
+        if torch.device(device).type == 'cuda':
+            lib = _cabi.load()
+            self.vec_slices = torch.empty(lib.pf_vec_slices_bytes() // 4, dtype=torch.float32, device=device)
+            with torch.cuda.device(device):
+                _cabi.call('pf_pack_vec_slices', ctypes.byref(self.struct), _ptr(self.vec_slices), _stream_ptr())
+            self.struct.vec_slices = self.vec_slices.data_ptr()
 
 
 class PackedUpdator:

@@ -42,7 +42,7 @@ def test_struct_layout_matches_header():
     assert ints == _cabi.BranchWeights._ROWS + ['head_relu']
     assert ptrs == _cabi.BranchWeights._PTRS
     assert ctypes.sizeof(_cabi.BranchWeights) == 4 * 13 + 4 + 8 * len(ptrs)    # 13 ints, pad to 8, pointers
-    assert ctypes.sizeof(_cabi.StageWeights) == 2 * ctypes.sizeof(_cabi.BranchWeights) + 16 + 16
+    assert ctypes.sizeof(_cabi.StageWeights) == 2 * ctypes.sizeof(_cabi.BranchWeights) + 16 + 16 + 8   # + vec_slices
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
