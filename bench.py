@@ -51,8 +51,9 @@ def parse():
     ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
     ap.add_argument('--no-kernel-head', action='store_true', help='skip the (non-headline) KernelHead-tail timing')
     ap.add_argument('--no-graph', action='store_true', help='launch every step from the host instead of replaying a CUDA graph')
-    ap.add_argument('--per-layer-update', action='store_true',
-                    help='A/B: run the small-N block as 12 per-layer launches (csrc/pf_update.cu) instead of the fused cluster kernel')
+    ap.add_argument('--update-mode', default='default', choices=['default', 'fused', 'per-layer'],
+                    help='A/B: small-N block as ONE fused cluster kernel (csrc/pf_stage.cu) or as 12 per-layer launches '
+                         '(csrc/pf_update.cu); default = the library default')
     ap.add_argument('--splits', type=int, default=None, help='batch windows decoded concurrently (default: 1)')
     return ap.parse_args()
 
@@ -144,7 +145,7 @@ def launch_info(args, B):
     """How OUR arm runs the workload (not part of `config`)."""
     return dict(stage_outputs='all' if args.all_stage_outputs else 'observable-only',
                 batch_windows=args.splits if args.splits else 1,
-                small_n_block='12 per-layer launches' if args.per_layer_update else 'fused 8-CTA-cluster kernel (1 launch per stage)',
+                small_n_block='fused 8-CTA-cluster kernel (1 launch per stage)' if getattr(args, 'fused', False) else '12 per-layer launches',
                 launch='eager' if args.no_graph else 'cuda-graph replay')
 
 
@@ -272,7 +273,11 @@ def run_ours(args, rank, world, local_rank):
     from polyphonicformer_b200 import _cabi
     from polyphonicformer_b200.decoder import DecoderEngine, _ptr, _stream_ptr
     lib = _cabi.load()
-    lib.pf_set_fused_update(0 if args.per_layer_update else 1)
+    if args.update_mode != 'default':
+        lib.pf_set_fused_update(1 if args.update_mode == 'fused' else 0)
+    fused = bool(lib.pf_set_fused_update(0))     # the setter returns the previous value: read it, then restore it
+    lib.pf_set_fused_update(1 if fused else 0)
+    args.fused = fused
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
@@ -510,7 +515,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
          2 * 2 * B * N * C * HW,
          lambda i: _cabi.call('pf_mask_pool', _ptr(featsR[i]), _ptr(bitsR[i]), _ptr(partial), _ptr(cntp), B, N, HW, HWp,
                               2, S, st)),
-        ('kernel_update (small-N block, %s)' % ('12 per-layer launches' if args.per_layer_update else 'fused cluster kernel, 1 launch'),
+        ('kernel_update (small-N block, %s)' % ('fused cluster kernel, 1 launch' if args.fused else '12 per-layer launches'),
          STAGES, 'latency', 0, 0,
          lambda i: _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[i % STAGES].struct), _ptr(partial), _ptr(cntp),
                               S, _ptr(obj), _ptr(dep), _ptr(obj_o), _ptr(dep_o), _ptr(cls), None, _ptr(kern),

@@ -28,7 +28,10 @@
  *                                    HWp % 8 == 0, HWp >= HW; columns >= HW are never read as data
  *   bits    u32   [B][WORDS][128]    WORDS = ceil(HW/32); bit j of word w of row n = (mask logit[n][32w+j] > 0)
  *                                    == sigmoid(logit) > 0.5 (kernel_update_head.py:236-238); rows >= N are zero
- *   partial f32   [G][S][N][256]     per-split pooled sums, G = n_branch*B units (unit = branch*B + b)
+ *   partial f32   [G][S][64][N][4]   per-split pooled sums, G = n_branch*B units (unit = branch*B + b); element (n, c) of a
+ *                                    split lives at [c / 4][n][c % 4] (column-group-major: a warp of 32 kernel rows reads /
+ *                                    writes 512 contiguous bytes).  Opaque to callers: produced by pf_mask_pool, consumed by
+ *                                    pf_kernel_update / pf_pool_reduce / pf_init_proposals
  *   cntp    f32   [G][S][N]          per-split mask pixel counts
  *   kern    f32   [G][N][256]        dynamic 1x1-conv kernels with feat_transform already folded in
  *   kern_split bf16 [G][2][N][256]   the same kernels as bf16 hi (= bf16(x)) and lo (= bf16(x - hi)) planes: the

@@ -105,6 +105,21 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t 
     return PF_OK;
 }
 
+int make_tmap_bf16_blocked(CUtensorMap* out, const void* base, uint64_t blocks) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(PF_ERR_ALIGN, "TMA base not 16-byte aligned");
+    cuuint64_t dims[3] = {8, 128, blocks};
+    cuuint64_t strides[2] = {16, 2048};
+    cuuint32_t box[3] = {8, 128, 8};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled(blocked) failed with CUresult %d", (int)r);
+    return PF_OK;
+}
+
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
                      uint32_t box0) {
     EncodeTiledFn fn = get_encode_fn();

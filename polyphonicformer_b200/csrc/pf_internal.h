@@ -24,6 +24,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
                       uint32_t box0);
 
+// bf16 "blocked" activation arena: 3-D tensor [blocks][128 rows][8] (dense), box = [8 blocks][128 rows][8], no swizzle:
+// in shared memory the box is the canonical no-swizzle K-major UMMA operand ([8 column groups][128 rows][16 bytes])
+int make_tmap_bf16_blocked(CUtensorMap* out, const void* base, uint64_t blocks);
+
 // 3-D fp32 tensor [d2][d1][d0] (dense); box = [1][box1][box0], 128-byte swizzle (box0 * 4 bytes must be 128)
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
                      uint32_t box0);

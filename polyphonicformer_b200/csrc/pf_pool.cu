@@ -29,7 +29,7 @@ constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + 256 + 1024;
 
 struct PoolParams {
     const uint32_t* bits;  // [B][WORDS][128]
-    float* partial;        // [G][S][N][256]
+    float* partial;        // [G][S][64 column groups][N][4]: column-group-major so that thread = row stores / loads coalesce
     float* cntp;           // [G][S][N]
     int N, HW, words, B, S, tiles_per_unit;
     int Btot, b0;          // batch window: this launch covers images b0 .. b0+B-1 of a [n_branch][Btot] feature tensor
@@ -148,7 +148,9 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
             mbar_wait(accfull, 0);
             tc_fence_after();
         }
-        float* orow = p.partial + (slab * p.N + (r < p.N ? r : 0)) * P_C;
+        // partial[slab][column group of 4][row][4]: the 32 rows of a warp write 512 contiguous bytes per store instruction
+        // (row-major rows of 1 KB made every store touch 32 different 128-byte lines: the epilogue was LSU-bound)
+        float* obase = p.partial + slab * (size_t)p.N * P_C + (size_t)(r < p.N ? r : 0) * 4;
 #pragma unroll 1
         for (int c0 = 0; c0 < P_C; c0 += 32) {
             uint32_t v[32];
@@ -162,7 +164,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
             if (r < p.N) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4)
-                    *reinterpret_cast<uint4*>(orow + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    *reinterpret_cast<uint4*>(obase + (size_t)((c0 + c) >> 2) * p.N * 4) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
             }
         }
     }
@@ -175,17 +177,17 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
 PF_DEFINE_DBG_SETTER(set_dbg_pool)
 namespace pf {
 
-// sum over splits in a fixed order: pooled[g][n][c], count[b][n].  64 threads x float4 per row, 4 rows per block.
+// sum over splits in a fixed order: pooled[g][n][c], count[b][n].  Thread = (unit, column group, row), row fastest: the
+// partials are column-group-major ([G][S][64][N][4]).
 __global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restrict__ partial,
                                                           const float* __restrict__ cntp, float* __restrict__ pooled,
                                                           float* __restrict__ count, int G, int B, int N, int S,
                                                           const float* __restrict__ addend, int out_rows) {
     pdl_wait();
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 6);  // g * N + n
-    if (row >= G * N) return;
-    const int g = row / N, n = row % N;
-    const int c4 = threadIdx.x & 63;
-    const float4* src = reinterpret_cast<const float4*>(partial + (((size_t)g * S) * N + n) * P_C) + c4;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= G * 64 * N) return;
+    const int n = idx % N, cg = (idx / N) & 63, g = idx / (64 * N);
+    const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)g * S) * N * P_C) + (size_t)cg * N + n;
     const size_t stride4 = (size_t)N * P_C / 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int s = 0;
@@ -201,11 +203,11 @@ __global__ void __launch_bounds__(256) pool_reduce_kernel(const float* __restric
         acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
     }
     if (addend) {   // KernelHead: proposal_feats = init_kernels.weight + obj_feats (kernel_head.py:324-326)
-        const float4 a = __ldg(reinterpret_cast<const float4*>(addend + (size_t)n * P_C) + c4);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(addend + (size_t)n * P_C) + cg);
         acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
     }
-    reinterpret_cast<float4*>(pooled + ((size_t)g * out_rows + n) * P_C)[c4] = acc;
-    if (c4 == 0 && g < B && count) {
+    reinterpret_cast<float4*>(pooled + ((size_t)g * out_rows + n) * P_C)[cg] = acc;
+    if (cg == 0 && g < B && count) {
         float k = 0.f;
         for (int s2 = 0; s2 < S; ++s2) k += cntp[((size_t)g * S + s2) * N + n];
         count[g * N + n] = k;
@@ -265,7 +267,7 @@ extern "C" int pf_pool_reduce(const float* partial, const float* cntp, float* po
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(partial && cntp && pooled, PF_ERR_ARG, "pf_pool_reduce: null pointer");
-    return launch_pdl("pool_reduce_kernel", pool_reduce_kernel, dim3((n_branch * B * N + 3) / 4), dim3(256), 0,
+    return launch_pdl("pool_reduce_kernel", pool_reduce_kernel, dim3((n_branch * B * N * 64 + 255) / 256), dim3(256), 0,
                       static_cast<cudaStream_t>(stream), partial, cntp, pooled, count, n_branch * B, B, N, S,
                       (const float*)nullptr, N);
 }
@@ -284,7 +286,7 @@ extern "C" int pf_init_proposals(const float* partial, const float* cntp, const 
     PF_REQUIRE(B > 0 && P > 0 && n_stuff >= 0 && P + n_stuff <= PF_MAX_N && S > 0, PF_ERR_ARG, "pf_init_proposals: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int N = P + n_stuff;
-    if (int e = launch_pdl("pool_reduce_kernel", pool_reduce_kernel, dim3((B * P + 3) / 4), dim3(256), 0, st, partial, cntp,
+    if (int e = launch_pdl("pool_reduce_kernel", pool_reduce_kernel, dim3((B * P * 64 + 255) / 256), dim3(256), 0, st, partial, cntp,
                            proposal_feats, (float*)nullptr, B, B, P, S, init_kernels, N))
         return e;
     for (int b = 0; b < B && n_stuff > 0; ++b) {   // the same stuff kernels for every image

@@ -117,6 +117,19 @@ __device__ __forceinline__ void tma_load_2d_warp(void* smem_dst, const CUtensorM
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_warp(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t hint) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}\n"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "l"(hint)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             uint64_t hint) {
     asm volatile(

@@ -242,6 +242,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_warp(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {   // whole warp, one lane issues
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n" ::"r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&y)[8]) {
     uint32_t v[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -271,23 +279,37 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]), lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// 32 values of one row -> bf16 hi / lo planes of arena slot `slot`, columns col0 ..; rows >= N are written as zeros
+// The fused kernel's arena: per (unit, slot, plane) a block of [32 column groups][128 rows][8] bf16 (column-group-major),
+// so that the 32 rows of a warp store 512 contiguous bytes per instruction and a TMA box [8 groups][128 rows][8] lands in
+// shared memory as the canonical NO-swizzle K-major UMMA layout (core matrix = 8 rows x 16 bytes, contiguous).
+__device__ __forceinline__ uint16_t* arena_blk(uint16_t* arena, int unit, int slot, int plane, int kg, int row) {
+    return arena + ((((size_t)unit * NSLOT + slot) * 2 + plane) * 32 + kg) * 1024 + row * 8;
+}
+// 32 / 8 values of one row -> bf16 hi / lo planes of arena slot `slot`, columns col0 ..; rows >= N are written as zeros
 __device__ __forceinline__ void planes32(const float (&y)[32], bool rok, uint16_t* arena, int unit, int slot, int row, int col0) {
-    uint16_t* hi = arena_row(arena, unit, slot, 0, row) + col0;
-    uint16_t* lo = arena_row(arena, unit, slot, 1, row) + col0;
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
         uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
         if (rok) split8(&y[c], h, l);
-        *reinterpret_cast<uint4*>(hi + c) = h;
-        *reinterpret_cast<uint4*>(lo + c) = l;
+        *reinterpret_cast<uint4*>(arena_blk(arena, unit, slot, 0, (col0 + c) >> 3, row)) = h;
+        *reinterpret_cast<uint4*>(arena_blk(arena, unit, slot, 1, (col0 + c) >> 3, row)) = l;
     }
 }
 __device__ __forceinline__ void planes8(const float (&y)[8], bool rok, uint16_t* arena, int unit, int slot, int row, int col0) {
     uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
     if (rok) split8(&y[0], h, l);
-    *reinterpret_cast<uint4*>(arena_row(arena, unit, slot, 0, row) + col0) = h;
-    *reinterpret_cast<uint4*>(arena_row(arena, unit, slot, 1, row) + col0) = l;
+    *reinterpret_cast<uint4*>(arena_blk(arena, unit, slot, 0, col0 >> 3, row)) = h;
+    *reinterpret_cast<uint4*>(arena_blk(arena, unit, slot, 1, col0 >> 3, row)) = l;
+}
+// shared-memory matrix descriptor without swizzle (layout type 0): core matrices of 8 rows x 16 bytes; lbo = bytes between
+// the two core matrices of one K = 16 step, sbo = bytes between 8-row groups
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
 }
 // 32 values of row `row` -> hi / lo operand planes in shared memory (rows of 128 bytes, 128-byte swizzle), 16-byte chunks
 // chunk0 .. chunk0 + 3 of the row
@@ -380,9 +402,11 @@ stage_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constan
     };
     auto issue_a = [&](const GPass& p, int kb, int s) {
         uint8_t* st = smem + s * G_STAGE;
-        const int row = ((unit * NSLOT + p.a_slot) * 2) * 128;
-        tma_load_2d_warp(st, &tmap_a, &full[s], kb * 64, row, kEvictNormal);
-        tma_load_2d_warp(st + G_PLANE, &tmap_a, &full[s], kb * 64, row + 128, kEvictNormal);
+        // 8 column groups of a plane = 16 KB contiguous in the blocked arena: plain bulk copies (a tensor box with a
+        // 16-byte inner dimension moved the same bytes 3x slower)
+        const uint16_t* src = a.arena + ((((size_t)unit * NSLOT + p.a_slot) * 2) * 32 + kb * 8) * 1024;
+        bulk_g2s_warp(st, src, G_PLANE, &full[s]);
+        bulk_g2s_warp(st + G_PLANE, src + 32 * 1024, G_PLANE, &full[s]);
     };
     // every thread of the cluster passes the same sequence of cluster barriers
     auto csync = [&]() {
@@ -421,7 +445,8 @@ stage_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constan
         for (int i = 0; i < 8; ++i) p8[i] = 0.f, k8[i] = 0.f;
         if (rok) {
             const int S = a.S;
-            const float* src = a.partial + (((size_t)unit * S) * N + row) * 256 + c0;
+            // partials are column-group-major ([unit][S][64][N][4], pf_pool.cu): consecutive rows = consecutive float4
+            const float* src = a.partial + ((size_t)unit * S) * N * 256 + ((size_t)(c0 >> 2) * N + row) * 4;
             const size_t stride = (size_t)N * 256;
 #pragma unroll 1
             for (int s = 0; s < S; s += 8) {   // 16 loads in flight per thread; added in slab order (deterministic)
@@ -430,7 +455,7 @@ stage_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constan
                 for (int i = 0; i < 8; ++i) {
                     const bool ok = s + i < S;
                     u[i] = ok ? ld4(src + (size_t)(s + i) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[i] = ok ? ld4(src + (size_t)(s + i) * stride + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = ok ? ld4(src + (size_t)(s + i) * stride + (size_t)N * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -470,7 +495,8 @@ stage_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constan
             const GStep& S = steps[st];
             if (S.npass) {
                 if (dbg3 && st == ST_FC) dbg3[5] = gtime();
-                fence_proxy_async_all();     // the peers' generic-proxy stores to the arena (acquired at the cluster barrier) -> TMA
+                // (the peers fenced their generic-proxy stores to the arena towards the async proxy BEFORE the cluster barrier
+                // that released them; no second fence on the reading side)
                 const int total = S.npass * 4;
 #pragma unroll 1
                 for (int it = 0; it < total; ++it) {
@@ -522,15 +548,17 @@ stage_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constan
                     if (dbg3 && st == ST_FC) dbg3[kb] = gtime();
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * G_STAGE);
-                    const uint64_t dah = make_smem_desc_sw128(sa, 16, 1024), dal = make_smem_desc_sw128(sa + G_PLANE, 16, 1024);
+                    // A: [8 column groups][128 rows][16 bytes], no swizzle: K = 16 step = two groups = 4096 bytes;
+                    // W: rows of 128 bytes, 128-byte swizzle: K = 16 step = 32 bytes
+                    const uint64_t dah = make_smem_desc_nosw(sa, 2048, 128), dal = make_smem_desc_nosw(sa + G_PLANE, 2048, 128);
                     const uint64_t dwh = make_smem_desc_sw128(sa + 2 * G_PLANE, 16, 1024);
                     const uint64_t dwl = make_smem_desc_sw128(sa + 3 * G_PLANE, 16, 1024);
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
-                        const uint64_t o = (uint64_t)(k16 * 2);
-                        umma_bf16_ss_warp(d, dal + o, dwh + o, idesc, (kb | k16) != 0);
-                        umma_bf16_ss_warp(d, dah + o, dwl + o, idesc, 1);
-                        umma_bf16_ss_warp(d, dah + o, dwh + o, idesc, 1);
+                        const uint64_t oa = (uint64_t)(k16 * 256), o = (uint64_t)(k16 * 2);
+                        umma_bf16_ss_warp(d, dal + oa, dwh + o, idesc, (kb | k16) != 0);
+                        umma_bf16_ss_warp(d, dah + oa, dwl + o, idesc, 1);
+                        umma_bf16_ss_warp(d, dah + oa, dwh + o, idesc, 1);
                     }
                     umma_commit_warp(&empty[s]);
                 }
@@ -648,19 +676,22 @@ stage_kernel(const __grid_constant__ CUtensorMap tmap_w256, const __grid_constan
                 // ---- split-K partial of FFN layer 2: this CTA's 256 hidden channels, all 256 output columns
                 const int oc = 128 * (st - ST_FFN2A) + 32 * chunk;
                 tmem_ld32f(tlane + oc, y);
-                store32(a.part + (((size_t)unit * G_CL + rank) * 128 + row) * 256 + oc, y);
+                float* pb = a.part + ((size_t)unit * G_CL + rank) * 128 * 256 + (size_t)row * 4;   // [64 column groups][128 rows][4]
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<float4*>(pb + (size_t)((oc + c) >> 2) * 512) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
             } else if (st == ST_REDUCE) {
                 // ---- ffn_norm(x + sum of partials + b2)   (:271-272); thread = (row, 8 columns)
                 const int c0 = c32 + 8 * chunk;
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = 0.f;
-                const float* pp = a.part + (((size_t)unit * G_CL) * 128 + row) * 256 + c0;
+                const float* pp = a.part + ((size_t)unit * G_CL) * 128 * 256 + (size_t)(c0 >> 2) * 512 + (size_t)row * 4;
                 float4 u[G_CL], v[G_CL];
 #pragma unroll
                 for (int j = 0; j < G_CL; ++j) {   // written by the peers during THIS launch: coherent (L2) loads, not the read-only path
                     u[j] = __ldcg(reinterpret_cast<const float4*>(pp + (size_t)j * 128 * 256));
-                    v[j] = __ldcg(reinterpret_cast<const float4*>(pp + (size_t)j * 128 * 256 + 4));
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(pp + (size_t)j * 128 * 256 + 512));
                 }
 #pragma unroll
                 for (int j = 0; j < G_CL; ++j) {
@@ -894,7 +925,18 @@ int launch_stage_fused(const pf_stage_weights* w, const float* partial, const fl
     CUtensorMap mw, mf, ma;
     if (int e = cached_tmap_2d(&mw, w->wstack256, (uint64_t)w->wstack256_rows, 256, 32)) return e;
     if (int e = cached_tmap_2d(&mf, w->wstack_ffn, (uint64_t)w->wstack_ffn_rows, (uint64_t)w->ffn_channels, 32)) return e;
-    if (int e = cached_tmap_2d(&ma, arena, (uint64_t)2 * B * NSLOT * 256, 256, 128)) return e;
+    {   // the blocked arena as a 3-D tensor [blocks = units * slots * 2 planes * 32 column groups][128 rows][8]; box = 8 groups
+        static std::mutex mu;
+        static const void* c_base = nullptr;
+        static int c_B = 0;
+        static CUtensorMap c_map;
+        std::lock_guard<std::mutex> lock(mu);
+        if (c_base != arena || c_B != B) {
+            if (int e = make_tmap_bf16_blocked(&c_map, arena, (uint64_t)2 * B * NSLOT * 2 * 32)) return e;
+            c_base = arena, c_B = B;
+        }
+        ma = c_map;
+    }
     StageArgs a;
     memset(&a, 0, sizeof(a));
     a.w = *w;

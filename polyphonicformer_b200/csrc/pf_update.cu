@@ -537,14 +537,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepA
     pdl_launch_dependents();
     DBG(2);
     const int job = blockIdx.y;
-    const int idx = blockIdx.x * 256 + threadIdx.x;   // (b, r, c4) with r < 128
-    const int c4 = idx & 63, r = (idx >> 6) & 127, b = idx >> 13;
+    const int idx = blockIdx.x * 256 + threadIdx.x;   // (b, c4, r) with r < 128 fastest: the pooling partials are
+    const int r = idx & 127, c4 = (idx >> 7) & 63, b = idx >> 13;   // column-group-major ([unit][S][64][N][4], pf_pool.cu)
     if (b >= a.B) return;
     const int N = a.N, S = a.S[job];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < N) {
         if (S > 0) {
-            const float4* src = reinterpret_cast<const float4*>(a.src[job] + (((size_t)b * S) * N + r) * 256) + c4;
+            const float4* src = reinterpret_cast<const float4*>(a.src[job] + ((size_t)b * S) * N * 256) + (size_t)c4 * N + r;
             const size_t stride4 = (size_t)N * 64;
             int s = 0;
             for (; s + 6 <= S; s += 6) {

@@ -12,6 +12,7 @@ from polyphonicformer_b200 import _cabi  # noqa: E402
 sys.argv = [sys.argv[0]] + (sys.argv[1:] or ['4', '128', '256', '3'])
 tbuf = torch.zeros(16 + 16 * 16384, dtype=torch.int64, device='cuda:0')
 _cabi.call('pf_debug_timeline', tbuf.data_ptr())
+_cabi.load().pf_set_fused_update(1)
 exec(open(os.path.join(ROOT, 'scripts', 'run_stage.py')).read())
 torch.cuda.synchronize()
 _cabi.call('pf_debug_timeline', None)

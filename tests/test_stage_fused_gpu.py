@@ -40,7 +40,11 @@ def run_update(eng, stage, partial, cntp, S, obj, dep, B, N, fused, cls_sigmoid=
                    _ptr(out['kbias']), _ptr(ws), nbytes, B, N, cls_sigmoid, _stream_ptr())
         torch.cuda.synchronize()
         out['launches'] = lib.pf_last_launch_count() - before
-        arena = ws[:2 * B * len(SLOTS) * 2 * 128 * 256 * 2].view(torch.bfloat16).view(2 * B, len(SLOTS), 2, 128, 256)
+        arena = ws[:2 * B * len(SLOTS) * 2 * 128 * 256 * 2].view(torch.bfloat16)
+        if fused:    # column-group-major blocks [32 groups][128 rows][8] per (unit, slot, plane) -> [128][256]
+            arena = arena.view(2 * B, len(SLOTS), 2, 32, 128, 8).permute(0, 1, 2, 4, 3, 5).reshape(2 * B, len(SLOTS), 2, 128, 256)
+        else:
+            arena = arena.view(2 * B, len(SLOTS), 2, 128, 256)
         out['arena'] = (arena[:, :, 0].float() + arena[:, :, 1].float())[:, :, :N].clone()   # hi + lo, valid rows
         return out
     finally:
@@ -111,7 +115,13 @@ def test_fused_stage_in_place_and_deterministic(dev):
     ks = torch.empty((2 * B, 2, N, 256), dtype=torch.bfloat16, device=dev)
     kb = torch.empty((2, B, N), dtype=torch.float32, device=dev)
     cls = torch.empty((B, N, 19), dtype=torch.float32, device=dev)
-    _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[1].struct), _ptr(partial), _ptr(cntp), S, _ptr(o), _ptr(d), _ptr(o),
-               _ptr(d), _ptr(cls), None, _ptr(ks), _ptr(kb), _ptr(ws), nbytes, B, N, 0, _stream_ptr())
-    torch.cuda.synchronize()
-    assert torch.equal(o, ref['obj']) and torch.equal(d, ref['dep']) and torch.equal(ks, ref['ksplit'])
+    old = lib.pf_set_fused_update(1)
+    try:
+        _cabi.call('pf_kernel_update', ctypes.byref(eng.stages[1].struct), _ptr(partial), _ptr(cntp), S, _ptr(o), _ptr(d), _ptr(o),
+                   _ptr(d), _ptr(cls), None, _ptr(ks), _ptr(kb), _ptr(ws), nbytes, B, N, 0, _stream_ptr())
+        torch.cuda.synchronize()
+    finally:
+        lib.pf_set_fused_update(old)
+    assert torch.equal(o, ref['obj']), (o - ref['obj']).abs().max()
+    assert torch.equal(d, ref['dep']), (d - ref['dep']).abs().max()
+    assert torch.equal(ks, ref['ksplit'])
