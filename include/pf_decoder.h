@@ -241,6 +241,18 @@ int pf_panoptic(const float* cls_scores, const float* mask_logits, const float* 
                 float* depth_final, float* depth_basic, pf_segment* segments, int* n_segments, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* The same for B frames in one set of launches (frame f at offset f * (frame size) in every tensor; `segments` holds
+ * `segment_stride` records per frame; `workspace` = B * pf_panoptic_workspace_bytes(H0, W0) bytes).
+ * in_stride2 != 0: mask_logits / depth_logits / depth_init are the decoder's OWN maps [..][h/2][w/2] (stride 8) and the x2
+ * bilinear up-sampling of kernel_update.py:131-143 / :302-307 is evaluated on the fly with pf_upsample2x's arithmetic, so
+ * the 4x larger scaled_mask_preds / scaled_depth_preds are never written or read; results are bit-identical to
+ * pf_upsample2x followed by pf_panoptic. */
+int pf_panoptic_batch(const float* cls_scores, const float* mask_logits, const float* depth_logits, const float* depth_init,
+                      int B, int N, int num_proposals, int num_thing_classes, int num_classes, int h, int w, int H0, int W0,
+                      int max_per_img, float instance_score_thr, float overlap_thr, int depth_mode, int in_stride2,
+                      int32_t* panoptic, float* depth_final, float* depth_basic, pf_segment* segments, int segment_stride,
+                      int* n_segments, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the producer of the decoder's inputs -----------------------------------------
  * The tail of KernelHead._decode_init_proposals (polyphonic/kernel_head.py:250-336) after SemanticFPN:
  *   loc / sem / dep = ReLU(GroupNorm32(conv1x1(maps[0 / 1 / 2])))       kernel_head.py:250-251, 264-265, 277-278

@@ -67,6 +67,9 @@ _SIGS = {
     'pf_panoptic': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_size_t, c_void_p]),
+    'pf_panoptic_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'pf_debug_timeline': (c_int, [c_void_p]),
     'pf_cast_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_binarise': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

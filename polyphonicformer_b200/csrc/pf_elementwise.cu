@@ -1,6 +1,7 @@
 // Streaming (HBM-bound) helper kernels of the decoder: storage cast, mask binarisation, x2 bilinear upsampling.
 #include "pf_internal.h"
 #include "pf_sm100.cuh"
+#include "pf_up2.cuh"
 
 namespace pf {
 
@@ -87,10 +88,11 @@ __device__ __forceinline__ void up_hrow(const float* __restrict__ row, int x, in
     const int c0 = max(x - 1, 0), c2 = min(x + 1, W - 1), c3 = min(x + 2, W - 1);
     const float a0 = __ldg(row + c0), a1 = __ldg(row + x), a2 = __ldg(row + c2), a3 = __ldg(row + c3);
     // out col 2x   : src = x - 0.25 -> (x-1, x) weights (0.25, 0.75); at x == 0 the source clamps to column 0
-    h[0] = (x == 0) ? (1.f * a1 + 0.f * a2) : (0.25f * a0 + 0.75f * a1);
-    h[1] = 0.75f * a1 + 0.25f * a2;   // src = x + 0.25
-    h[2] = 0.25f * a1 + 0.75f * a2;   // src = x + 0.75
-    h[3] = 0.75f * a2 + 0.25f * a3;   // src = x + 1.25 -> (x+1, x+2)
+    // (up2_mix: the rounding order pf_panoptic's on-the-fly sampling uses too, pf_up2.cuh)
+    h[0] = (x == 0) ? a1 : up2_mix(0.25f, a0, 0.75f, a1);
+    h[1] = up2_mix(0.75f, a1, 0.25f, a2);   // src = x + 0.25
+    h[2] = up2_mix(0.25f, a1, 0.75f, a2);   // src = x + 0.75
+    h[3] = up2_mix(0.75f, a2, 0.25f, a3);   // src = x + 1.25 -> (x+1, x+2)
 }
 
 __global__ void __launch_bounds__(128) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
@@ -118,8 +120,8 @@ __global__ void __launch_bounds__(128) upsample2x_kernel(const float* __restrict
         float o0[4], o1[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            o0[k] = (y == 0) ? (1.f * hB[k] + 0.f * hC[k]) : (0.25f * hA[k] + 0.75f * hB[k]);
-            o1[k] = 0.75f * hB[k] + 0.25f * hC[k];
+            o0[k] = (y == 0) ? hB[k] : up2_mix(0.25f, hA[k], 0.75f, hB[k]);
+            o1[k] = up2_mix(0.75f, hB[k], 0.25f, hC[k]);
         }
         float* d0 = dst + (size_t)(2 * y) * W2 + 2 * x;
         float* d1 = d0 + W2;

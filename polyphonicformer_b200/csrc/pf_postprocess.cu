@@ -24,6 +24,7 @@
 
 #include "pf_internal.h"
 #include "pf_sm100.cuh"
+#include "pf_up2.cuh"
 
 namespace pf {
 
@@ -72,8 +73,11 @@ __device__ __forceinline__ Tap make_tap(int dst, int in_size) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) pp_select_kernel(const float* __restrict__ cls, PpTables* __restrict__ tb, int N,
-                                                         int P, int T, int ncls, int max_per_img) {
+// one CTA per frame (blockIdx.x); tables of frame f at tb_base + f * ws_stride bytes
+__global__ void __launch_bounds__(1024) pp_select_kernel(const float* __restrict__ cls_all, uint8_t* __restrict__ tb_base,
+                                                         size_t ws_stride, int N, int P, int T, int ncls, int max_per_img) {
+    const float* cls = cls_all + (size_t)blockIdx.x * N * ncls;
+    PpTables* tb = reinterpret_cast<PpTables*>(tb_base + (size_t)blockIdx.x * ws_stride);
     __shared__ float s_key[1024];
     __shared__ int s_idx[1024];
     const int t = threadIdx.x;
@@ -140,9 +144,15 @@ __global__ void __launch_bounds__(1024) pp_select_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __restrict__ mask_logits,
-                                                               PpTables* __restrict__ tb, uint8_t* __restrict__ ids,
-                                                               int N, int h, int w, int H0, int W0) {
+// in_stride2: mask_logits are [N][h/2][w/2] (the decoder's own resolution) and their x2 bilinear up-sampling
+// (kernel_update.py:133-143) is evaluated on the fly with pf_upsample2x's arithmetic instead of being read from memory
+__global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __restrict__ mask_all, uint8_t* __restrict__ ws_base,
+                                                               size_t ws_stride, size_t tb_bytes, int N, int h, int w, int H0,
+                                                               int W0, int in_stride2) {
+    const int hs = in_stride2 ? h / 2 : h, wsrc = in_stride2 ? w / 2 : w;
+    const float* mask_logits = mask_all + (size_t)blockIdx.z * N * hs * wsrc;
+    PpTables* tb = reinterpret_cast<PpTables*>(ws_base + (size_t)blockIdx.z * ws_stride);
+    uint8_t* ids = ws_base + (size_t)blockIdx.z * ws_stride + tb_bytes;
     extern __shared__ float s_sig[];   // [N][PP_PR][PP_PC] sigmoid of the low-resolution logits under this tile
     __shared__ float s_score[PP_MAXN];
     __shared__ int s_entry[PP_MAXN];
@@ -161,7 +171,8 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
     for (int i = tid; i < N * PATCH; i += PP_THREADS) {
         const int n = i / PATCH, r = (i % PATCH) / PP_PC, c = i % PP_PC;
         const int yy = min(py0 + r, h - 1), xx = min(px0 + c, w - 1);
-        s_sig[i] = sigmoidf_(__ldg(mask_logits + ((size_t)n * h + yy) * w + xx));
+        s_sig[i] = sigmoidf_(in_stride2 ? up2_val(mask_logits + (size_t)n * hs * wsrc, hs, wsrc, yy, xx)
+                                        : __ldg(mask_logits + ((size_t)n * h + yy) * w + xx));
     }
     __syncthreads();
     // Tile-level pruning (exact).  A bilinear sample is a convex combination of patch values, so inside this tile
@@ -249,9 +260,13 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pp_merge_kernel(PpTables* __restrict__ tb, pf_segment* __restrict__ segs,
-                                                       int* __restrict__ n_segs, int T, float instance_score_thr,
+__global__ void __launch_bounds__(128) pp_merge_kernel(uint8_t* __restrict__ tb_base, size_t ws_stride,
+                                                       pf_segment* __restrict__ segs_all, int seg_stride,
+                                                       int* __restrict__ n_segs_all, int T, float instance_score_thr,
                                                        float overlap_thr) {
+    PpTables* tb = reinterpret_cast<PpTables*>(tb_base + (size_t)blockIdx.x * ws_stride);
+    pf_segment* segs = segs_all + (size_t)blockIdx.x * seg_stride;
+    int* n_segs = n_segs_all + blockIdx.x;
     __shared__ float s_score[PP_MAXE];
     __shared__ int s_mask[PP_MAXE], s_label[PP_MAXE], s_champ[PP_MAXN], s_area[PP_MAXN], s_orig[PP_MAXN], s_segid[PP_MAXN];
     __shared__ int s_order[PP_MAXE];
@@ -294,27 +309,34 @@ __global__ void __launch_bounds__(128) pp_merge_kernel(PpTables* __restrict__ tb
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pp_paint_kernel(const float* __restrict__ depth_logits,
-                                                       const float* __restrict__ depth_init,
-                                                       const PpTables* __restrict__ tb, const uint8_t* __restrict__ ids,
-                                                       int32_t* __restrict__ panoptic, float* __restrict__ depth_final,
-                                                       float* __restrict__ depth_basic, int h, int w, int H0, int W0,
-                                                       int depth_mode) {
-    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+__global__ void __launch_bounds__(256) pp_paint_kernel(const float* __restrict__ depth_all, const float* __restrict__ dinit_all,
+                                                       const uint8_t* __restrict__ ws_base, size_t ws_stride, size_t tb_bytes,
+                                                       int32_t* __restrict__ panoptic_all, float* __restrict__ dfinal_all,
+                                                       float* __restrict__ dbasic_all, int N, int h, int w, int H0, int W0,
+                                                       int depth_mode, int in_stride2) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y, f = blockIdx.z;
     if (X >= W0 || Y >= H0) return;
+    const int hs = in_stride2 ? h / 2 : h, wsrc = in_stride2 ? w / 2 : w;
+    const float* depth_logits = depth_all + (size_t)f * N * hs * wsrc;
+    const float* depth_init = dinit_all + (size_t)f * hs * wsrc;
+    const PpTables* tb = reinterpret_cast<const PpTables*>(ws_base + (size_t)f * ws_stride);
+    const uint8_t* ids = ws_base + (size_t)f * ws_stride + tb_bytes;
     const Tap cy = make_tap(Y, h), cx = make_tap(X, w);
+    auto tap = [&](const float* map, int yi, int xi) {   // value of the (h, w) map at (yi, xi)
+        return depth_act_(in_stride2 ? up2_val(map, hs, wsrc, yi, xi) : __ldg(map + yi * w + xi), depth_mode);
+    };
     auto sample = [&](const float* map) {
-        const float a = depth_act_(__ldg(map + cy.i0 * w + cx.i0), depth_mode), b = depth_act_(__ldg(map + cy.i0 * w + cx.i1), depth_mode);
-        const float c = depth_act_(__ldg(map + cy.i1 * w + cx.i0), depth_mode), d = depth_act_(__ldg(map + cy.i1 * w + cx.i1), depth_mode);
+        const float a = tap(map, cy.i0, cx.i0), b = tap(map, cy.i0, cx.i1), c = tap(map, cy.i1, cx.i0), d = tap(map, cy.i1, cx.i1);
         return cy.l0 * (cx.l0 * a + cx.l1 * b) + cy.l1 * (cx.l0 * c + cx.l1 * d);
     };
     const size_t p = (size_t)Y * W0 + X;
+    const size_t fo = (size_t)f * H0 * W0;
     const int n = ids[p];
     const int s = tb->segid[n];
     const float dinit = sample(depth_init);
-    panoptic[p] = s;
-    depth_basic[p] = dinit;
-    depth_final[p] = s > 0 ? sample(depth_logits + (size_t)n * h * w) : dinit;
+    panoptic_all[fo + p] = s;
+    dbasic_all[fo + p] = dinit;
+    dfinal_all[fo + p] = s > 0 ? sample(depth_logits + (size_t)n * hs * wsrc) : dinit;
 }
 
 static size_t pp_align(size_t v) { return (v + 255) / 256 * 256; }
@@ -326,43 +348,57 @@ extern "C" size_t pf_panoptic_workspace_bytes(int H0, int W0) {
     return pf::pp_align(sizeof(pf::PpTables)) + pf::pp_align((size_t)H0 * W0);
 }
 
-extern "C" int pf_panoptic(const float* cls_scores, const float* mask_logits, const float* depth_logits,
-                           const float* depth_init, int N, int num_proposals, int num_thing_classes, int num_classes, int h,
-                           int w, int H0, int W0, int max_per_img, float instance_score_thr, float overlap_thr,
-                           int depth_mode, int32_t* panoptic, float* depth_final, float* depth_basic,
-                           pf_segment* segments, int* n_segments, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int pf_panoptic_batch(const float* cls_scores, const float* mask_logits, const float* depth_logits,
+                                 const float* depth_init, int B, int N, int num_proposals, int num_thing_classes,
+                                 int num_classes, int h, int w, int H0, int W0, int max_per_img, float instance_score_thr,
+                                 float overlap_thr, int depth_mode, int in_stride2, int32_t* panoptic, float* depth_final,
+                                 float* depth_basic, pf_segment* segments, int segment_stride, int* n_segments,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(cls_scores && mask_logits && depth_logits && depth_init && panoptic && depth_final && depth_basic && segments &&
                    n_segments && workspace,
                PF_ERR_ARG, "pf_panoptic: null pointer");
+    PF_REQUIRE(B > 0 && B <= 65535, PF_ERR_ARG, "pf_panoptic: batch %d", B);
     PF_REQUIRE(N > 0 && N <= PP_MAXN && num_proposals > 0 && num_proposals <= N && num_thing_classes > 0 &&
                    num_thing_classes + (N - num_proposals) <= num_classes && num_proposals * num_thing_classes <= 1024,
                PF_ERR_ARG, "pf_panoptic: bad class / proposal counts N=%d P=%d T=%d classes=%d", N, num_proposals,
                num_thing_classes, num_classes);
     PF_REQUIRE(h > 0 && w > 0 && H0 > 0 && W0 > 0 && H0 <= 4 * h && W0 <= 4 * w, PF_ERR_ARG,
                "pf_panoptic: output %dx%d must be a crop of the x4 up-sampled %dx%d predictions", H0, W0, h, w);
+    PF_REQUIRE(!in_stride2 || (h % 2 == 0 && w % 2 == 0), PF_ERR_ARG, "pf_panoptic: in_stride2 needs even h, w (got %dx%d)", h, w);
     PF_REQUIRE(max_per_img > 0 && max_per_img + (N - num_proposals) <= PP_MAXE, PF_ERR_ARG, "pf_panoptic: max_per_img=%d", max_per_img);
+    PF_REQUIRE(segment_stride >= max_per_img + (N - num_proposals) || B == 1, PF_ERR_ARG, "pf_panoptic: segment_stride=%d", segment_stride);
     PF_REQUIRE(depth_mode == 0 || depth_mode == 1, PF_ERR_ARG, "pf_panoptic: depth_mode must be 0 (monodepth) or 1 (sigmoid)");
-    PF_REQUIRE(workspace_bytes >= pf_panoptic_workspace_bytes(H0, W0), PF_ERR_WORKSPACE, "pf_panoptic: workspace %zu < %zu",
-               workspace_bytes, pf_panoptic_workspace_bytes(H0, W0));
+    const size_t per = pf_panoptic_workspace_bytes(H0, W0);
+    PF_REQUIRE(workspace_bytes >= (size_t)B * per, PF_ERR_WORKSPACE, "pf_panoptic: workspace %zu < %zu", workspace_bytes, (size_t)B * per);
     PF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PF_ERR_ALIGN, "pf_panoptic: workspace not 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PpTables* tb = static_cast<PpTables*>(workspace);
-    uint8_t* ids = static_cast<uint8_t*>(workspace) + pp_align(sizeof(PpTables));
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    const size_t tb_bytes = pp_align(sizeof(PpTables));
 
-    pp_select_kernel<<<1, 1024, 0, st>>>(cls_scores, tb, N, num_proposals, num_thing_classes, num_classes, max_per_img);
+    pp_select_kernel<<<B, 1024, 0, st>>>(cls_scores, wsb, per, N, num_proposals, num_thing_classes, num_classes, max_per_img);
     PF_CHECK_LAUNCH("pp_select_kernel");
     const size_t smem = (size_t)N * PP_PR * PP_PC * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(pp_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(PF_ERR_CUDA, "pp_argmax smem attribute: %s", cudaGetErrorString(e));
-    dim3 grid((W0 + PP_TX - 1) / PP_TX, (H0 + PP_TY - 1) / PP_TY);
-    pp_argmax_kernel<<<grid, PP_THREADS, smem, st>>>(mask_logits, tb, ids, N, h, w, H0, W0);
+    dim3 grid((W0 + PP_TX - 1) / PP_TX, (H0 + PP_TY - 1) / PP_TY, B);
+    pp_argmax_kernel<<<grid, PP_THREADS, smem, st>>>(mask_logits, wsb, per, tb_bytes, N, h, w, H0, W0, in_stride2);
     PF_CHECK_LAUNCH("pp_argmax_kernel");
-    pp_merge_kernel<<<1, 128, 0, st>>>(tb, segments, n_segments, num_thing_classes, instance_score_thr, overlap_thr);
+    pp_merge_kernel<<<B, 128, 0, st>>>(wsb, per, segments, segment_stride, n_segments, num_thing_classes, instance_score_thr, overlap_thr);
     PF_CHECK_LAUNCH("pp_merge_kernel");
-    pp_paint_kernel<<<dim3((W0 + 255) / 256, H0), 256, 0, st>>>(depth_logits, depth_init, tb, ids, panoptic, depth_final,
-                                                                 depth_basic, h, w, H0, W0, depth_mode);
+    pp_paint_kernel<<<dim3((W0 + 255) / 256, H0, B), 256, 0, st>>>(depth_logits, depth_init, wsb, per, tb_bytes, panoptic, depth_final,
+                                                                    depth_basic, N, h, w, H0, W0, depth_mode, in_stride2);
     PF_CHECK_LAUNCH("pp_paint_kernel");
     return PF_OK;
+}
+
+extern "C" int pf_panoptic(const float* cls_scores, const float* mask_logits, const float* depth_logits,
+                           const float* depth_init, int N, int num_proposals, int num_thing_classes, int num_classes, int h,
+                           int w, int H0, int W0, int max_per_img, float instance_score_thr, float overlap_thr,
+                           int depth_mode, int32_t* panoptic, float* depth_final, float* depth_basic,
+                           pf_segment* segments, int* n_segments, void* workspace, size_t workspace_bytes, void* stream) {
+    return pf_panoptic_batch(cls_scores, mask_logits, depth_logits, depth_init, 1, N, num_proposals, num_thing_classes,
+                             num_classes, h, w, H0, W0, max_per_img, instance_score_thr, overlap_thr, depth_mode, 0, panoptic,
+                             depth_final, depth_basic, segments, 128, n_segments, workspace, workspace_bytes, stream);
 }

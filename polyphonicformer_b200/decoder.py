@@ -528,22 +528,23 @@ class PanopticPipeline(HostPipeline):
 
     def __init__(self, engine, B, N, H, W, num_proposals=100, num_thing_classes=8, max_per_img=100,
                  instance_score_thr=0.3, overlap_thr=0.6, depth_act_mode='sigmoid', depth=2):
-        super().__init__(engine, B, N, H, W, upsample=True, depth=depth)
+        # upsample=False: the x2 up-sampled logits are never materialised -- pf_panoptic_batch samples the decoder's own
+        # stride-8 maps with the composed taps (bit-identical to pf_upsample2x followed by pf_panoptic)
+        super().__init__(engine, B, N, H, W, upsample=False, depth=depth)
         dev = engine.device
         lib = _cabi.load()
         self.cfg = (num_proposals, num_thing_classes, max_per_img, float(instance_score_thr), float(overlap_thr),
                     {'monodepth': 0, 'sigmoid': 1}[depth_act_mode])
         H0, W0 = 8 * H, 8 * W
-        self.pws_bytes = lib.pf_panoptic_workspace_bytes(H0, W0)
+        self.pws_bytes = B * lib.pf_panoptic_workspace_bytes(H0, W0)
         for s in self.slots:
             s.update(dpred=torch.empty((B, 1, H, W), dtype=torch.float32, device=dev),
-                     dinit=torch.empty((B, 2 * H, 2 * W), dtype=torch.float32, device=dev),
                      pan=torch.empty((B, H0, W0), dtype=torch.int32, device=dev),
                      dfinal=torch.empty((B, H0, W0), dtype=torch.float32, device=dev),
                      dbasic=torch.empty((B, H0, W0), dtype=torch.float32, device=dev),
                      segs=torch.zeros((B, 128, 24), dtype=torch.uint8, device=dev),
                      nseg=torch.zeros(B, dtype=torch.int32, device=dev),
-                     pws=[torch.empty(self.pws_bytes, dtype=torch.uint8, device=dev) for _ in range(B)])
+                     pws=torch.empty(self.pws_bytes, dtype=torch.uint8, device=dev))
 
     def h2d_bytes(self):
         return super().h2d_bytes() + self.slots[0]['dpred'].numel() * 4
@@ -574,14 +575,11 @@ class PanopticPipeline(HostPipeline):
                 s['feats'][0, :, :, :HW].copy_(s['x'].reshape(B, PF_C, HW))
                 s['feats'][1, :, :, :HW].copy_(s['d'].reshape(B, PF_C, HW))
             self.eng.decode_inplace(s['feats'], s['mask'], s['buf'], H, W)
-            st = _stream_ptr()
-            _cabi.call('pf_upsample2x', _ptr(s['dpred']), _ptr(s['dinit']), B, H, W, st)    # kernel_update.py:302-307
-            scaled, cls = s['buf']['scaled'], s['buf']['cls']
-            for b in range(B):
-                _cabi.call('pf_panoptic', _ptr(cls[b]), _ptr(scaled[0, b]), _ptr(scaled[1, b]), _ptr(s['dinit'][b]), N, P,
-                           T, ncls, 2 * H, 2 * W, 8 * H, 8 * W, max_per_img, thr_i, thr_o, dmode, _ptr(s['pan'][b]),
-                           _ptr(s['dfinal'][b]), _ptr(s['dbasic'][b]), _ptr(s['segs'][b]), _ptr(s['nseg'][b:]),
-                           _ptr(s['pws'][b]), self.pws_bytes, st)
+            logits, cls = s['buf']['logits'], s['buf']['cls']
+            _cabi.call('pf_panoptic_batch', _ptr(cls), _ptr(logits[0]), _ptr(logits[1]), _ptr(s['dpred']), B, N, P, T, ncls,
+                       2 * H, 2 * W, 8 * H, 8 * W, max_per_img, thr_i, thr_o, dmode, 1, _ptr(s['pan']), _ptr(s['dfinal']),
+                       _ptr(s['dbasic']), _ptr(s['segs']), 128, _ptr(s['nseg']), _ptr(s['pws']), self.pws_bytes,
+                       _stream_ptr())
             s['ev_run'].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(s['ev_run'])

@@ -385,7 +385,7 @@ class KernelUpdateIterHead(nn.Module):
                     object_feats=object_feats, scaled_depth_preds=scaled_depth_preds, depth_preds=depth_preds,
                     depth_proposal=depth_proposal)
 
-    def decode(self, x, proposal_feats, mask_preds, depth_feats, depth_proposal, all_stage_outputs=False):
+    def decode(self, x, proposal_feats, mask_preds, depth_feats, depth_proposal, all_stage_outputs=False, upsample=None):
         """The fused stage loop of simple_test (kernel_update.py:316-336): one C call, dead intermediate outputs
         skipped unless ``all_stage_outputs``.  Returns the dict of DecoderEngine.decode (cls_score has the sigmoid)."""
         if not x.is_cuda:
@@ -401,7 +401,8 @@ class KernelUpdateIterHead(nn.Module):
         feats = self.mask_head[0]._prepared_feats(x, depth_feats)
         out = eng.decode(feats, mask_preds.float(), proposal_feats.reshape(B, N, -1).float(),
                          depth_proposal.reshape(B, N, -1).float(), H, W,
-                         upsample=head.mask_upsample_stride == 2, all_stage_outputs=all_stage_outputs)
+                         upsample=head.mask_upsample_stride == 2 if upsample is None else upsample,
+                         all_stage_outputs=all_stage_outputs)
         C = proposal_feats.shape[2]
         out['object_feats'] = out['object_feats'].reshape(B, N, C, 1, 1)
         out['depth_proposal'] = out['depth_proposal'].reshape(B, N, C, 1, 1)
@@ -420,19 +421,19 @@ class KernelUpdateIterHead(nn.Module):
         if not self.do_panoptic:
             raise NotImplementedError
         head = self.mask_head[-1]
-        out = self.decode(x, proposal_feats, mask_preds, depth_feats, depth_proposal)
-        depth_initial = depth_preds.clone().detach()
-        if self.mask_head[0].mask_upsample_stride > 1:
-            depth_initial = self.engine(x.device).upsample2x(depth_initial.float())
-            if aspp_semantic is not None:
-                aspp_semantic = self.engine(x.device).upsample2x(aspp_semantic.float())
-        results = []
-        for i in range(len(img_metas)):
-            results.append(postprocess.get_panoptic(
-                self, head, out['cls_score'][i], out['scaled_mask_preds'][i], self.test_cfg, img_metas[i],
-                depth_preds=out['scaled_depth_preds'][i], depth_init=depth_initial[i],
-                aspp_semantic=aspp_semantic[i] if aspp_semantic is not None else None))
-        return results
+        if aspp_semantic is not None:
+            raise NotImplementedError('aspp_semantic is not used by the reference either (kernel_update.py:425-426)')
+        stride2 = self.mask_head[0].mask_upsample_stride == 2 and head.mask_upsample_stride == 2
+        # with the x2 up-sampling on (the shipped configs) the scaled maps are not materialised: pf_panoptic_batch samples
+        # the stride-8 logits with the composed taps, bit-identical to upsample -> get_panoptic (kernel_update.py:131-143)
+        out = self.decode(x, proposal_feats, mask_preds, depth_feats, depth_proposal, upsample=not stride2)
+        depth_initial = depth_preds.detach().float()
+        if not stride2 and self.mask_head[0].mask_upsample_stride > 1:
+            depth_initial = self.engine(x.device).upsample2x(depth_initial)
+        return postprocess.get_panoptic_batch(
+            self, head, out['cls_score'], out['mask_preds' if stride2 else 'scaled_mask_preds'], self.test_cfg, img_metas,
+            depth_preds=out['depth_preds' if stride2 else 'scaled_depth_preds'], depth_init=depth_initial,
+            stride2_inputs=stride2)
 
     def forward_train(self, *args, **kwargs):
         _unsupported('training (forward_train)')

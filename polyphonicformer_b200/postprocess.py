@@ -19,43 +19,17 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def get_panoptic(roi_head, last_head, cls_scores, mask_preds, test_cfg, img_meta, depth_preds, depth_init,
-                 aspp_semantic=None):
-    """Same arguments and return value as the reference's get_panoptic: (None, None, (panoptic int32 [H0,W0],
-    segments_info), depth_basic [H0,W0], depth_final [H0,W0]) as numpy."""
-    if aspp_semantic is not None:
-        raise NotImplementedError('aspp_semantic is not used by the reference either (kernel_update.py:425-426)')
-    if not roi_head.merge_joint:
-        raise NotImplementedError('merge_joint=False is not implemented by the reference (kernel_update.py:467)')
-    if last_head.depth_act_mode not in _DEPTH_MODES:
-        raise NotImplementedError('depth_act_mode=%r' % (last_head.depth_act_mode,))
-    N, h, w = mask_preds.shape
+def _check_geometry(h, w, img_meta):
     H0, W0 = img_meta['img_shape'][:2]
     Hb, Wb = img_meta['batch_input_shape']
     if (Hb, Wb) != (4 * h, 4 * w) or tuple(img_meta['ori_shape'][:2]) != (H0, W0):
         raise NotImplementedError('pf_panoptic covers predictions at 1/4 of the padded input and ori_shape == img_shape '
                                   '(got preds %dx%d, batch_input %dx%d, img %dx%d, ori %s); there is no PyTorch fallback'
                                   % (h, w, Hb, Wb, H0, W0, tuple(img_meta['ori_shape'][:2])))
-    dev = mask_preds.device
-    lib = _cabi.load()
-    merge = test_cfg.merge_stuff_thing
-    cls_scores = cls_scores.float().contiguous()
-    mask_preds, depth_preds = mask_preds.float().contiguous(), depth_preds.float().contiguous()
-    depth_init = depth_init.float().reshape(h, w).contiguous()
-    pan = torch.empty((H0, W0), dtype=torch.int32, device=dev)
-    dfinal = torch.empty((H0, W0), dtype=torch.float32, device=dev)
-    dbasic = torch.empty((H0, W0), dtype=torch.float32, device=dev)
-    segs = torch.zeros((128, _SEG_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    nseg = torch.zeros(1, dtype=torch.int32, device=dev)
-    nbytes = lib.pf_panoptic_workspace_bytes(H0, W0)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _cabi.call('pf_panoptic', _ptr(cls_scores), _ptr(mask_preds), _ptr(depth_preds), _ptr(depth_init), N,
-               roi_head.num_proposals, roi_head.num_thing_classes, cls_scores.shape[1], h, w, H0, W0,
-               int(test_cfg.max_per_img), float(merge.instance_score_thr), float(merge.overlap_thr),
-               _DEPTH_MODES[last_head.depth_act_mode], _ptr(pan), _ptr(dfinal), _ptr(dbasic), _ptr(segs), _ptr(nseg),
-               _ptr(ws), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    n = int(nseg.item())                                   # the one host synchronisation of the post-processing
-    rec = np.frombuffer(segs.cpu().numpy().tobytes(), dtype=_SEG_DTYPE)[:n]
+    return H0, W0
+
+
+def _segments_info(rec):
     info = []
     for r in rec:
         if r['isthing']:
@@ -64,4 +38,70 @@ def get_panoptic(roi_head, last_head, cls_scores, mask_preds, test_cfg, img_meta
         else:
             info.append({'id': int(r['id']), 'isthing': False, 'category_id': int(r['category_id']),
                          'area': int(r['area'])})
-    return None, None, (pan.cpu().numpy(), info), dbasic.cpu().numpy(), dfinal.cpu().numpy()
+    return info
+
+
+def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, img_metas, depth_preds, depth_init,
+                       stride2_inputs=False):
+    """get_panoptic (kernel_update.py:421-469) for the B frames of a batch in ONE set of launches and ONE device->host
+    copy.  cls_scores [B,N,classes]; mask_preds / depth_preds [B,N,h,w]; depth_init [B,h,w] (or [B,1,h,w]).
+
+    ``stride2_inputs``: the three maps are the decoder's OWN stride-8 outputs [.., h/2, w/2] and the x2 bilinear
+    up-sampling of kernel_update.py:131-143 / :302-307 is evaluated inside the kernels (same arithmetic, bit-identical
+    results), so scaled_mask_preds / scaled_depth_preds never exist.  Frames must share one img_shape (a batch does:
+    kernel_update.py:339-351 loops over frames of one padded batch); mixed shapes go frame by frame.
+    Returns the reference's list of (None, None, (panoptic, segments_info), depth_basic, depth_final), numpy."""
+    if not roi_head.merge_joint:
+        raise NotImplementedError('merge_joint=False is not implemented by the reference (kernel_update.py:467)')
+    if last_head.depth_act_mode not in _DEPTH_MODES:
+        raise NotImplementedError('depth_act_mode=%r' % (last_head.depth_act_mode,))
+    B, N = mask_preds.shape[:2]
+    k = 2 if stride2_inputs else 1
+    h, w = k * mask_preds.shape[2], k * mask_preds.shape[3]
+    shapes = {_check_geometry(h, w, m) for m in img_metas}
+    if len(img_metas) != B:
+        raise ValueError('%d img_metas for a batch of %d' % (len(img_metas), B))
+    if len(shapes) > 1:      # ragged crops inside one padded batch: one frame at a time, same kernels
+        out = []
+        for b in range(B):
+            out += get_panoptic_batch(roi_head, last_head, cls_scores[b:b + 1], mask_preds[b:b + 1], test_cfg,
+                                      img_metas[b:b + 1], depth_preds[b:b + 1], depth_init[b:b + 1], stride2_inputs)
+        return out
+    H0, W0 = shapes.pop()
+    dev = mask_preds.device
+    lib = _cabi.load()
+    merge = test_cfg.merge_stuff_thing
+    cls_scores = cls_scores.float().contiguous()
+    mask_preds, depth_preds = mask_preds.float().contiguous(), depth_preds.float().contiguous()
+    depth_init = depth_init.float().reshape(B, h // k, w // k).contiguous()
+    # one output allocation = one read-back: panoptic | depth_final | depth_basic | segment records | counts
+    npx = H0 * W0
+    seg_bytes = 128 * _SEG_DTYPE.itemsize
+    offs = np.cumsum([0, B * npx * 4, B * npx * 4, B * npx * 4, B * seg_bytes, B * 4])
+    out = torch.zeros(int(offs[-1]), dtype=torch.uint8, device=dev)
+    pan, dfinal, dbasic, segs, nseg = (out[int(a):int(b)] for a, b in zip(offs[:-1], offs[1:]))
+    nbytes = B * lib.pf_panoptic_workspace_bytes(H0, W0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _cabi.call('pf_panoptic_batch', _ptr(cls_scores), _ptr(mask_preds), _ptr(depth_preds), _ptr(depth_init), B, N,
+               roi_head.num_proposals, roi_head.num_thing_classes, cls_scores.shape[-1], h, w, H0, W0,
+               int(test_cfg.max_per_img), float(merge.instance_score_thr), float(merge.overlap_thr),
+               _DEPTH_MODES[last_head.depth_act_mode], 1 if stride2_inputs else 0, _ptr(pan), _ptr(dfinal), _ptr(dbasic),
+               _ptr(segs), 128, _ptr(nseg), _ptr(ws), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    host = out.cpu().numpy()                                # the one host synchronisation of the post-processing
+    pan_h = host[offs[0]:offs[1]].view(np.int32).reshape(B, H0, W0)
+    dfinal_h = host[offs[1]:offs[2]].view(np.float32).reshape(B, H0, W0)
+    dbasic_h = host[offs[2]:offs[3]].view(np.float32).reshape(B, H0, W0)
+    rec = host[offs[3]:offs[4]].view(_SEG_DTYPE).reshape(B, 128)
+    n = host[offs[4]:offs[5]].view(np.int32)
+    return [(None, None, (pan_h[b], _segments_info(rec[b, :n[b]])), dbasic_h[b], dfinal_h[b]) for b in range(B)]
+
+
+def get_panoptic(roi_head, last_head, cls_scores, mask_preds, test_cfg, img_meta, depth_preds, depth_init,
+                 aspp_semantic=None):
+    """Same arguments and return value as the reference's get_panoptic: (None, None, (panoptic int32 [H0,W0],
+    segments_info), depth_basic [H0,W0], depth_final [H0,W0]) as numpy."""
+    if aspp_semantic is not None:
+        raise NotImplementedError('aspp_semantic is not used by the reference either (kernel_update.py:425-426)')
+    N, h, w = mask_preds.shape
+    return get_panoptic_batch(roi_head, last_head, cls_scores[None], mask_preds[None], test_cfg, [img_meta],
+                              depth_preds[None], depth_init.reshape(1, h, w))[0]

@@ -150,3 +150,51 @@ def test_panoptic_pipeline_matches_module_simple_test(dev):
             assert np.array_equal(outs[i]['depth_final'][b].numpy(), dfinal)
             assert np.array_equal(outs[i]['depth_basic'][b].numpy(), dbasic)
             assert int(outs[i]['nseg'][b]) == len(info)
+
+
+def test_panoptic_batch_from_stride8_maps_is_bit_identical(dev):
+    """pf_panoptic_batch(in_stride2=1) on the decoder's own stride-8 maps == pf_upsample2x then pf_panoptic per frame
+    (kernel_update.py:131-143, 302-307 -> :421-469), for a batch whose frames also carry different crops."""
+    from polyphonicformer_b200 import postprocess
+    from polyphonicformer_b200.decoder import DecoderEngine
+    B, h2, w2 = 3, 24, 40                                      # stride-8 maps; scaled predictions 48 x 80
+    g = dict(h=2 * h2, w=2 * w2, seed=5, img_hw=np.array([8 * h2, 8 * w2]))
+    roi, last, cfg, meta, _ = panoptic_args(g)
+    frames = [synth.synth_panoptic_inputs(h2, w2, seed) for seed in (5, 6, 7)]     # blobs / bands at stride 8
+    cls = torch.stack([f['cls_scores'] for f in frames]).to(dev)
+    mask = torch.stack([f['mask_preds'] for f in frames]).to(dev)
+    depth = torch.stack([f['depth_preds'] for f in frames]).to(dev)
+    dinit = torch.stack([f['depth_init'] for f in frames]).to(dev)                # [B,1,h2,w2]
+    eng = SimpleNamespaceEngine(dev)
+    mask_up, depth_up, dinit_up = (eng.upsample2x(t) for t in (mask, depth, dinit))
+    metas = [dict(meta), dict(meta, img_shape=(8 * h2 - 5, 8 * w2 - 9, 3), ori_shape=(8 * h2 - 5, 8 * w2 - 9, 3)), dict(meta)]
+    got = postprocess.get_panoptic_batch(roi, last, cls, mask, cfg, metas, depth, dinit, stride2_inputs=True)
+    assert len(got) == B
+    for b in range(B):
+        want = postprocess.get_panoptic(roi, last, cls[b], mask_up[b], cfg, metas[b], depth_up[b], dinit_up[b, 0])
+        assert np.array_equal(got[b][2][0], want[2][0])
+        assert got[b][2][1] == want[2][1] and len(want[2][1]) >= 2
+        assert np.array_equal(got[b][3], want[3]) and np.array_equal(got[b][4], want[4])
+    # two frames of one shape in one call == the same frames one by one
+    pair = postprocess.get_panoptic_batch(roi, last, cls[::2], mask[::2], cfg, [metas[0], metas[2]], depth[::2], dinit[::2],
+                                          stride2_inputs=True)
+    for j, b in enumerate((0, 2)):
+        assert np.array_equal(pair[j][2][0], got[b][2][0]) and pair[j][2][1] == got[b][2][1]
+        assert np.array_equal(pair[j][4], got[b][4])
+
+
+class SimpleNamespaceEngine:
+    """pf_upsample2x without a DecoderEngine (no weights needed)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def upsample2x(self, maps):
+        import ctypes
+        from polyphonicformer_b200 import _cabi
+        maps = maps.float().contiguous()
+        H, W = maps.shape[-2:]
+        out = torch.empty(maps.shape[:-2] + (2 * H, 2 * W), dtype=torch.float32, device=maps.device)
+        _cabi.call('pf_upsample2x', ctypes.c_void_p(maps.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                   maps.numel() // (H * W), H, W, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return out
