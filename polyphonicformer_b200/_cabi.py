@@ -1,4 +1,4 @@
-"""ctypes binding of include/pf_decoder.h (libpf_decoder.so).
+"""ctypes binding of include/pf_decoder.h and include/pf_track.h (libpf_decoder.so).
 
 This is the only place the package touches the native library.  There is NO fallback: if the library is missing or
 a call fails, a ``PFError`` is raised -- nothing in this package computes the decoder with PyTorch ops.
@@ -53,7 +53,37 @@ class HeadWeights(Structure):
                 ('gn_eps', c_float)]
 
 
+class TrackWeights(Structure):
+    """struct pf_track_weights (include/pf_track.h)."""
+    _fields_ = [('conv_w', c_void_p), ('gn_gamma', c_void_p), ('gn_beta', c_void_p), ('fc1_w', c_void_p),
+                ('fc1_b', c_void_p), ('fc2_wt', c_void_p), ('fc2_b', c_void_p), ('gn_eps', c_float)]
+
+
+class TrackerConfig(Structure):
+    """struct pf_tracker_config (include/pf_track.h)."""
+    _FLOATS = ['init_score_thr', 'obj_score_thr', 'match_score_thr', 'memo_momentum', 'nms_conf_thr',
+               'nms_backdrop_iou_thr', 'nms_class_iou_thr']
+    _INTS = ['memo_tracklet_frames', 'memo_backdrop_frames', 'with_cats']
+    _fields_ = [(n, c_float) for n in _FLOATS] + [(n, c_int) for n in _INTS]
+
+
 _SIGS = {
+    # ---- include/pf_track.h
+    'pf_track_boxes_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'pf_track_boxes_from_masks': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'pf_track_boxes_from_panoptic': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_void_p]),
+    'pf_track_embed_workspace_bytes': (c_size_t, [c_int]),
+    'pf_track_embed': (c_int, [POINTER(TrackWeights), POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'pf_track_head': (c_int, [POINTER(TrackWeights), c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'pf_tracker_state_bytes': (c_size_t, []),
+    'pf_tracker_workspace_bytes': (c_size_t, []),
+    'pf_tracker_reset': (c_int, [c_void_p, c_void_p]),
+    'pf_tracker_match': (c_int, [POINTER(TrackerConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'pf_track_paint': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    # ---- include/pf_decoder.h
     'pf_cast_maps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_fpn_pred': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                             c_int, c_int, c_void_p]),

@@ -11,7 +11,7 @@ LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libpf_decoder.so')
 OBJDIR = os.path.join(HERE, 'build')
 SOURCES = ['pf_host.cu', 'pf_elementwise.cu', 'pf_pool.cu', 'pf_update.cu', 'pf_stage.cu', 'pf_einsum.cu', 'pf_decoder.cu',
-           'pf_postprocess.cu', 'pf_head.cu']
+           'pf_postprocess.cu', 'pf_head.cu', 'pf_track.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 
@@ -25,7 +25,8 @@ def _nvcc():
 
 def _deps():
     d = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    d.append(os.path.join(os.path.dirname(HERE), 'include', 'pf_decoder.h'))
+    inc = os.path.join(os.path.dirname(HERE), 'include')
+    d += [os.path.join(inc, f) for f in os.listdir(inc)]
     return d
 
 

@@ -137,6 +137,28 @@ int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d
     return PF_OK;
 }
 
+
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (rank < 2 || rank > 5) return set_error(PF_ERR_ARG, "TMA rank %d", rank);
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(PF_ERR_ALIGN, "TMA base not 16-byte aligned");
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], estr[5];
+    for (int i = 0; i < rank; ++i) d[i] = dims[i], b[i] = box[i], estr[i] = 1;
+    for (int i = 0; i + 1 < rank; ++i) {
+        if (strides_bytes[i] % 16 != 0) return set_error(PF_ERR_ALIGN, "TMA stride %d not a 16-byte multiple", i);
+        st[i] = strides_bytes[i];
+    }
+    if (box[0] * 2 != 128) return set_error(PF_ERR_ARG, "TMA box inner extent must be 128 bytes for the 128-byte swizzle");
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PF_ERR_CUDA, "cuTensorMapEncodeTiled(nd) failed with CUresult %d", (int)r);
+    return PF_OK;
+}
+
 }  // namespace pf
 
 extern "C" int pf_version(void) { return 100; }

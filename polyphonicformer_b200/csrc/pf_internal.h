@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include "../../include/pf_decoder.h"
+#include "../../include/pf_track.h"
 
 namespace pf {
 
@@ -31,6 +32,11 @@ int make_tmap_bf16_blocked(CUtensorMap* out, const void* base, uint64_t blocks);
 // 3-D fp32 tensor [d2][d1][d0] (dense); box = [1][box1][box0], 128-byte swizzle (box0 * 4 bytes must be 128)
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
                      uint32_t box0);
+
+// rank-N bf16 tensor (dims / box innermost first, strides_bytes[i] = byte stride of dimension i + 1), 128-byte swizzle,
+// out-of-range elements (negative coordinates included) read as zero
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
 
 // batch-window variants of the streaming kernels (pf_decoder_forward_slice): feats / logits are full-batch tensors
 int mask_pool_window(const uint16_t* feats, const uint32_t* bits, float* partial, float* cntp, int Btot, int b0, int B,

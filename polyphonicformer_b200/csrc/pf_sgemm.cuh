@@ -1,0 +1,235 @@
+// "Shifted-row" split-bf16 GEMM on the 5th-generation tensor cores: the building block of every convolution / wide FC
+// outside the decoder's stage loop (the tracking head's 3x3 convs and FC, SemanticFPN's 3x3 convs).
+//
+//   D[128 rows][128 cols] (fp32, tensor memory) = sum over k-blocks of  A_kb[128][64] * W_kb[128][64]^T
+//   with fp32-level accuracy from bf16 operands:  A = Ah + Al, W = Wh + Wl,  D += Al*Wh + Ah*Wl + Ah*Wh
+//
+// A 3x3 convolution over a zero-padded row-major grid is nine such GEMMs whose A tiles are the SAME activation rows
+// shifted by dy * pitch + dx: the producer warp just adds the tap's row shift to the TMA coordinate (rows outside the
+// tensor, negative ones included, read as zero), so there is no im2col buffer.  SG_FC walks (position, channel block)
+// pairs of a [item][position][channel] activation instead (the flatten + Linear after the convs).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#pragma once
+#include "pf_internal.h"
+#include "pf_sm100.cuh"
+
+namespace pf {
+
+constexpr int SG_THREADS = 192;
+constexpr int SG_TN = 128;                     // output columns per CTA
+constexpr int SG_KC = 64;                      // K per ring stage
+constexpr int SG_NSTG = 3;
+constexpr int SG_PLANE = 128 * SG_KC * 2;      // one [128][64] bf16 box
+constexpr int SG_STAGE = 4 * SG_PLANE;         // A hi | A lo | W hi | W lo
+constexpr int SG_BAR_OFF = SG_NSTG * SG_STAGE;
+constexpr int SG_STAT_OFF = SG_BAR_OFF + 128;  // [2 passes][4 warps][16 groups] floats
+constexpr int SG_SMEM_USED = SG_STAT_OFF + 2 * 4 * 16 * 4;
+constexpr int SG_SMEM = SG_SMEM_USED + 1024;   // slack for the 1024-byte alignment of the ring
+
+enum { SG_CONV = 0, SG_FC = 1 };
+enum { SG_EPI_GN64 = 0, SG_EPI_PARTIAL = 1 };
+
+struct SgArgs {
+    int mode;              // SG_CONV / SG_FC
+    int n_kb;              // k-blocks per CTA
+    int cin_blocks;        // SG_CONV: input channels / 64 (k-block kb -> tap kb / cin_blocks, channel block kb % cin_blocks)
+    int w_tap_rows;        // SG_CONV: rows of one tap in the weight map (= padded output channels)
+    int w_lo;              // rows from the hi plane to the lo plane in the weight map
+    int fc_pos_per_split;  // SG_FC: grid positions per split (blockIdx.z)
+    int fc_grid, fc_pitch; // SG_FC: valid positions are (y, x) with y, x < fc_grid at row y * fc_pitch + x of an item
+    int shift[9];          // SG_CONV: row shift of tap t
+    // ---- epilogue
+    int n_items;           // GN64: items (RoIs) that exist; rows of later items are written as zeros
+    const float *gamma, *beta;   // GN64: [256] of this layer
+    float eps;
+    uint16_t *out_hi, *out_lo;   // GN64: bf16 planes [rows][256]
+    float* partial;              // PARTIAL: fp32 [split][part_rows][part_ld]
+    int part_rows, part_ld;
+};
+
+__device__ __forceinline__ void sg_named_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ float sg_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void sg_ld32(uint32_t taddr, float (&y)[32]) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
+}
+
+// 32 fp32 values -> bf16 hi / lo (x = hi + lo to 2^-17) -> two 64-byte row segments
+__device__ __forceinline__ void sg_store_split32(uint16_t* hi, uint16_t* lo, const float (&y)[32]) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float a = y[2 * i], b = y[2 * i + 1];
+        const float ah = bf16_round(a), bh = bf16_round(b);
+        h[i] = pack_bf16x2(ah, bh);
+        l[i] = pack_bf16x2(a - ah, b - bh);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+        reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(SG_THREADS, 1)
+sgemm_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_constant__ CUtensorMap tmap_al,
+             const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ SgArgs a) {
+    extern __shared__ uint8_t sg_smem_raw[];
+    uint8_t* smem = sg_smem_raw + ((1024u - (smem_u32(sg_smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SG_BAR_OFF);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + SG_NSTG;
+    uint64_t* accfull = bars + 2 * SG_NSTG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SG_NSTG + 1);
+    float* s_stat = reinterpret_cast<float*>(smem + SG_STAT_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * SG_TN, m0 = blockIdx.y * 128, split = blockIdx.z;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_ah);
+        tma_prefetch_desc(&tmap_al);
+        tma_prefetch_desc(&tmap_w);
+        for (int i = 0; i < SG_NSTG; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(accfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<128>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+    pdl_wait();                 // activations written by the previous kernel of the stream are visible from here on
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ================= TMA producer (whole warp, one elected lane issues) =================
+        for (int it = 0; it < a.n_kb; ++it) {
+            const int s = it % SG_NSTG;
+            if (it >= SG_NSTG) mbar_wait(&empty[s], ((it / SG_NSTG) & 1) ^ 1);
+            int ac0, ac1, ac2, wc0, wr;
+            if (a.mode == SG_CONV) {
+                const int tap = it / a.cin_blocks, cb = it - tap * a.cin_blocks;
+                ac0 = cb * SG_KC, ac1 = m0 + a.shift[tap], ac2 = 0;
+                wc0 = cb * SG_KC, wr = tap * a.w_tap_rows + n0;
+            } else {
+                const int pi = split * a.fc_pos_per_split + (it >> 2), cb = it & 3;
+                ac0 = cb * SG_KC, ac1 = (pi / a.fc_grid) * a.fc_pitch + pi % a.fc_grid, ac2 = m0;
+                wc0 = pi * 256 + cb * SG_KC, wr = n0;
+            }
+            uint8_t* st = smem + s * SG_STAGE;
+            mbar_arrive_expect_tx_warp(&full[s], SG_STAGE);
+            tma_load_3d_warp(st, &tmap_ah, &full[s], ac0, ac1, ac2, kEvictNormal);
+            tma_load_3d_warp(st + SG_PLANE, &tmap_al, &full[s], ac0, ac1, ac2, kEvictNormal);
+            tma_load_2d_warp(st + 2 * SG_PLANE, &tmap_w, &full[s], wc0, wr, kEvictNormal);
+            tma_load_2d_warp(st + 3 * SG_PLANE, &tmap_w, &full[s], wc0, wr + a.w_lo, kEvictNormal);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: D = Al*Wh + Ah*Wl + Ah*Wh =================
+        constexpr uint32_t idesc = make_idesc_bf16(128, SG_TN, 0, 0);
+        for (int it = 0; it < a.n_kb; ++it) {
+            const int s = it % SG_NSTG;
+            mbar_wait(&full[s], (it / SG_NSTG) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * SG_STAGE);
+            const uint64_t dah = make_smem_desc_sw128(st, 16, 1024), dal = make_smem_desc_sw128(st + SG_PLANE, 16, 1024);
+            const uint64_t dwh = make_smem_desc_sw128(st + 2 * SG_PLANE, 16, 1024);
+            const uint64_t dwl = make_smem_desc_sw128(st + 3 * SG_PLANE, 16, 1024);
+#pragma unroll
+            for (int k16 = 0; k16 < SG_KC / 16; ++k16) {
+                const uint64_t o = (uint64_t)(k16 * 2);   // K-major: +32 bytes (>> 4) per K = 16 step
+                umma_bf16_ss_warp(tmem_base, dal + o, dwh + o, idesc, (it | k16) != 0);
+                umma_bf16_ss_warp(tmem_base, dah + o, dwl + o, idesc, 1);
+                umma_bf16_ss_warp(tmem_base, dah + o, dwh + o, idesc, 1);
+            }
+            umma_commit_warp(&empty[s]);
+        }
+        umma_commit_warp(accfull);
+    } else {
+        // ================= epilogue: thread = output row (TMEM lane) =================
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        mbar_wait(accfull, 0);
+        tc_fence_after();
+        if (EPI == SG_EPI_GN64) {
+            // GroupNorm(32 groups of 8 channels) over the 7 x 7 valid positions of one item = 64 consecutive rows
+            // (7 grid rows of pitch 8, column 7 and rows >= 56 are zero padding), then ReLU, then bf16 hi / lo planes.
+            const int item = blockIdx.y * 2 + (r >> 6), p = r & 63;
+            const bool valid = item < a.n_items && p < 56 && (p & 7) < 7;
+            const float inv_n = 1.f / 392.f;
+            float mean[16], rstd[16];
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    float y[32];
+                    sg_ld32(trow + ch * 32, y);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float s = 0.f;
+                        if (valid) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float d = pass ? y[g * 8 + c] - mean[ch * 4 + g] : y[g * 8 + c];
+                                s += pass ? d * d : d;
+                            }
+                        }
+                        s = sg_warp_sum(s);
+                        if (lane == 0) s_stat[(pass * 4 + q) * 16 + ch * 4 + g] = s;
+                    }
+                }
+                sg_named_bar();
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    const float t = (s_stat[(pass * 4 + q) * 16 + g] + s_stat[(pass * 4 + (q ^ 1)) * 16 + g]) * inv_n;
+                    if (pass) rstd[g] = rsqrtf(t + a.eps);
+                    else mean[g] = t;
+                }
+            }
+            const size_t row = (size_t)blockIdx.y * 128 + r;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float y[32];
+                sg_ld32(trow + ch * 32, y);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int col = n0 + ch * 32 + c;
+                    const float v = (y[c] - mean[ch * 4 + (c >> 3)]) * rstd[ch * 4 + (c >> 3)] * __ldg(a.gamma + col) + __ldg(a.beta + col);
+                    y[c] = valid ? fmaxf(v, 0.f) : 0.f;
+                }
+                sg_store_split32(a.out_hi + row * 256 + n0 + ch * 32, a.out_lo + row * 256 + n0 + ch * 32, y);
+            }
+        } else if (EPI == SG_EPI_PARTIAL) {
+            const bool ok = m0 + r < a.part_rows;
+            float* dst = a.partial + ((size_t)split * a.part_rows + m0 + r) * a.part_ld + n0;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                float y[32];
+                sg_ld32(trow + ch * 32, y);     // warp-collective: every lane loads, only rows that exist store
+                if (ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + ch * 32 + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+}  // namespace pf

@@ -22,7 +22,8 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     from polyphonicformer_b200 import _cabi
-    hdr = open(os.path.join(ROOT, 'include', 'pf_decoder.h')).read()
+    inc = os.path.join(ROOT, 'include')
+    hdr = ''.join(open(os.path.join(inc, f)).read() for f in sorted(os.listdir(inc)) if f.endswith('.h'))
     code = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
     declared = set(re.findall(r'^(?:int|size_t|const char\*)\s+(pf_[a-z0-9_]+)\s*\(', code, flags=re.M))
     assert declared, 'no prototypes found'
