@@ -430,10 +430,11 @@ class KernelUpdateIterHead(nn.Module):
         depth_initial = depth_preds.detach().float()
         if not stride2 and self.mask_head[0].mask_upsample_stride > 1:
             depth_initial = self.engine(x.device).upsample2x(depth_initial)
+        self.last_device_results = []          # per frame: the device tensors behind the returned arrays (tracking path)
         return postprocess.get_panoptic_batch(
             self, head, out['cls_score'], out['mask_preds' if stride2 else 'scaled_mask_preds'], self.test_cfg, img_metas,
             depth_preds=out['depth_preds' if stride2 else 'scaled_depth_preds'], depth_init=depth_initial,
-            stride2_inputs=stride2)
+            stride2_inputs=stride2, device_results=self.last_device_results)
 
     def forward_train(self, *args, **kwargs):
         _unsupported('training (forward_train)')

@@ -42,7 +42,7 @@ def _segments_info(rec):
 
 
 def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, img_metas, depth_preds, depth_init,
-                       stride2_inputs=False):
+                       stride2_inputs=False, device_results=None):
     """get_panoptic (kernel_update.py:421-469) for the B frames of a batch in ONE set of launches and ONE device->host
     copy.  cls_scores [B,N,classes]; mask_preds / depth_preds [B,N,h,w]; depth_init [B,h,w] (or [B,1,h,w]).
 
@@ -50,7 +50,9 @@ def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, im
     up-sampling of kernel_update.py:131-143 / :302-307 is evaluated inside the kernels (same arithmetic, bit-identical
     results), so scaled_mask_preds / scaled_depth_preds never exist.  Frames must share one img_shape (a batch does:
     kernel_update.py:339-351 loops over frames of one padded batch); mixed shapes go frame by frame.
-    Returns the reference's list of (None, None, (panoptic, segments_info), depth_basic, depth_final), numpy."""
+    Returns the reference's list of (None, None, (panoptic, segments_info), depth_basic, depth_final), numpy.
+    ``device_results``: an optional list that receives, per frame, a dict of the DEVICE tensors behind those arrays
+    (panoptic int32 [H0,W0], depth_final, depth_basic) -- the video model's tracking path keeps working on them."""
     if not roi_head.merge_joint:
         raise NotImplementedError('merge_joint=False is not implemented by the reference (kernel_update.py:467)')
     if last_head.depth_act_mode not in _DEPTH_MODES:
@@ -65,7 +67,8 @@ def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, im
         out = []
         for b in range(B):
             out += get_panoptic_batch(roi_head, last_head, cls_scores[b:b + 1], mask_preds[b:b + 1], test_cfg,
-                                      img_metas[b:b + 1], depth_preds[b:b + 1], depth_init[b:b + 1], stride2_inputs)
+                                      img_metas[b:b + 1], depth_preds[b:b + 1], depth_init[b:b + 1], stride2_inputs,
+                                      device_results)
         return out
     H0, W0 = shapes.pop()
     dev = mask_preds.device
@@ -87,6 +90,9 @@ def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, im
                int(test_cfg.max_per_img), float(merge.instance_score_thr), float(merge.overlap_thr),
                _DEPTH_MODES[last_head.depth_act_mode], 1 if stride2_inputs else 0, _ptr(pan), _ptr(dfinal), _ptr(dbasic),
                _ptr(segs), 128, _ptr(nseg), _ptr(ws), nbytes, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if device_results is not None:
+        pd, fd, bd = (t.view(torch.int32 if i == 0 else torch.float32).view(B, H0, W0) for i, t in enumerate((pan, dfinal, dbasic)))
+        device_results += [dict(panoptic=pd[b], depth_final=fd[b], depth_basic=bd[b]) for b in range(B)]
     host = out.cpu().numpy()                                # the one host synchronisation of the post-processing
     pan_h = host[offs[0]:offs[1]].view(np.int32).reshape(B, H0, W0)
     dfinal_h = host[offs[1]:offs[2]].view(np.float32).reshape(B, H0, W0)

@@ -113,6 +113,7 @@ class Registry:
 MODELS = Registry('models')          # == HEADS == DETECTORS == ROI heads (one object in mmdet too)
 HEADS = DETECTORS = NECKS = MODELS
 TRANSFORMER_LAYER = Registry('transformer_layer')
+TRACKERS = Registry('tracker')       # polyphonic/video/qdtrack/builder.py
 
 
 def build_head(cfg):
@@ -135,20 +136,43 @@ def build_transformer_layer(cfg):
     return TRANSFORMER_LAYER.build(cfg)
 
 
-def register_all(force=True):
-    """Register the B200 modules under the reference's names; into mmcv/mmdet's registries when those import."""
+def build_detector(cfg, train_cfg=None, test_cfg=None):
+    """mmdet.models.build_detector (builder.py:45-59) on the local registry."""
+    cfg = dict(cfg)
+    if train_cfg is not None:
+        cfg.setdefault('train_cfg', train_cfg)
+    if test_cfg is not None:
+        cfg.setdefault('test_cfg', test_cfg)
+    return MODELS.build(cfg)
+
+
+def register_all(force=True, detectors=False):
+    """Register the B200 modules under the reference's names: always into the registries above; into mmcv/mmdet's and the
+    reference's own (``polyphonic.video.qdtrack.builder.TRACKERS``) when those import.  Returns whether they did.
+    ``detectors``: also replace the reference's ``Polyphonic`` / ``PolyphonicVideo`` in mmdet's registry (by default the
+    reference's own detector classes keep orchestrating this package's heads there)."""
+    from . import detectors as d
     from . import modules as m
-    pairs = [(MODELS, m.KernelUpdateHead), (MODELS, m.KernelUpdateIterHead), (MODELS, m.KernelHead),
-             (TRANSFORMER_LAYER, m.KernelUpdator)]
-    for reg, cls in pairs:
-        reg.register_module(force=True, module=cls)
+    heads = (m.KernelUpdateHead, m.KernelUpdateIterHead, m.KernelHead, d.QuasiDenseMaskEmbedHeadGTMask)
+    for cls in heads + (d.SingleRoIExtractor, d.Polyphonic, d.PolyphonicVideo):
+        MODELS.register_module(force=True, module=cls)
+    TRANSFORMER_LAYER.register_module(force=True, module=m.KernelUpdator)
+    TRACKERS.register_module(force=True, module=d.QuasiDenseEmbedTracker)
     try:   # the reference's own registries (drop-in when a reference checkout + mmcv are installed)
         from mmdet.models.builder import HEADS as MM_HEADS
         from mmcv.cnn.bricks.transformer import TRANSFORMER_LAYER as MM_TL
     except Exception:
         return False
-    MM_HEADS.register_module(force=force, module=m.KernelUpdateHead)
-    MM_HEADS.register_module(force=force, module=m.KernelUpdateIterHead)
-    MM_HEADS.register_module(force=force, module=m.KernelHead)
+    for cls in heads:
+        MM_HEADS.register_module(force=force, module=cls)
     MM_TL.register_module(force=force, module=m.KernelUpdator)
+    try:
+        from polyphonic.video.qdtrack.builder import TRACKERS as REF_TRACKERS
+        REF_TRACKERS.register_module(force=force, module=d.QuasiDenseEmbedTracker)
+    except Exception:
+        pass
+    if detectors:
+        from mmdet.models.builder import DETECTORS as MM_DET
+        MM_DET.register_module(force=force, module=d.Polyphonic)
+        MM_DET.register_module(force=force, module=d.PolyphonicVideo)
     return True

@@ -11,6 +11,7 @@ convs.{0..3}.gn.{weight,bias} [256], fcs.0.{weight [1024,12544], bias}, fc_embed
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _cabi
@@ -180,3 +181,23 @@ class DeviceTracker:
         ids = o[MAX_K:MAX_K + n].long()
         order_d = order.to(bboxes.device)
         return bboxes[order_d], labels[order_d], ids
+
+
+def paint_maps(panoptic_dev, segments_info, seg_ids, ids, default_sem):
+    """generate_track_id_maps + get_semantic_seg (polyphonic_former_video.py:436-451) as two look-up tables over the
+    panoptic map (pf_track_paint).  As in the reference, ids[i] (kept detections, descending score) is painted onto the
+    i-th thing mask in segment order; pixels of no segment get ``default_sem`` / track id 0.  Returns numpy
+    (sem uint8, track float64 -- the reference's np.zeros(shape))."""
+    dev = panoptic_dev.device
+    sem_lut = np.full(256, default_sem, dtype=np.uint8)
+    for s in segments_info:
+        sem_lut[s['id']] = s['category_id']
+    trk_lut = np.zeros(256, dtype=np.int32)
+    for i, tid in enumerate(ids):
+        trk_lut[seg_ids[i]] = int(tid)
+    luts = torch.from_numpy(np.concatenate([trk_lut.view(np.uint8), sem_lut])).to(dev)      # one small upload
+    sem = torch.empty(panoptic_dev.shape, dtype=torch.uint8, device=dev)
+    trk = torch.empty(panoptic_dev.shape, dtype=torch.int32, device=dev)
+    _cabi.call('pf_track_paint', _ptr(panoptic_dev), _ptr(luts[1024:]), _ptr(luts), panoptic_dev.numel(), _ptr(sem), _ptr(trk),
+               _stream())
+    return sem.cpu().numpy(), trk.cpu().numpy().astype(np.float64)

@@ -148,3 +148,70 @@ def test_shared_feats_channel_is_identity_keyed():
     del y
     gc.collect()
     assert key not in reg._by_id                     # entry died with the tensor
+
+
+VIDEO_CFG = '/root/reference/configs/polyphonic_video/poly_r50_cityscapes_1x.py'
+VIDEO_JSON = os.path.join(GOLDEN, 'video_cfg.json')   # the video-specific dicts of cfg.model, dumped from the reference's config
+
+
+def video_cfg():
+    d = json.load(open(VIDEO_JSON))
+    if os.path.exists(VIDEO_CFG):
+        m = pf.load_config(VIDEO_CFG).model
+        for k in ('track_head', 'tracker', 'bbox_roi_extractor', 'track_train_cfg'):
+            assert json.loads(json.dumps(m[k])) == d[k], 'tests/golden/video_cfg.json is stale (%s)' % k
+    return d
+
+
+class _Stub(torch.nn.Module):
+    num_proposals = 100
+
+    def __init__(self, **cfg):
+        super().__init__()
+        self.cfg = cfg
+
+
+def test_detectors_register_and_build_without_mmdet():
+    """`Polyphonic` / `PolyphonicVideo` and the tracking modules exist under the reference's names in the local registry
+    (mmdet is not importable here), take the reference's kwargs, wire train_cfg / test_cfg into the heads the way
+    TwoStageDetector does (two_stage.py:37-50) and expose the reference's state-dict keys."""
+    from polyphonicformer_b200 import registry
+    for name in ('Polyphonic', 'PolyphonicVideo', 'QuasiDenseMaskEmbedHeadGTMask', 'SingleRoIExtractor'):
+        assert name in registry.MODELS, name
+    assert 'QuasiDenseEmbedTracker' in registry.TRACKERS
+    v = video_cfg()
+    rd = json.load(open(ROI_HEAD_JSON))
+    pd = json.load(open(RPN_HEAD_JSON))
+    pf.MODELS.register_module(name='SemanticFPNWrapper', force=True, module=_FakeNeck)
+    try:
+        model = registry.build_detector(dict(
+            type='PolyphonicVideo', backbone=_Stub(), neck=_Stub(), rpn_head=pd['rpn_head'],
+            roi_head=dict(rd['roi_head'], tracking=v['roi_head_tracking']), num_thing_classes=8, num_stuff_classes=11,
+            test_cfg=dict(rpn=pd['test_cfg'], rcnn=rd['test_cfg']), track_head=v['track_head'], tracker=v['tracker'],
+            bbox_roi_extractor=v['bbox_roi_extractor'], track_train_cfg=v['track_train_cfg']))
+    finally:
+        pf.MODELS._modules.pop('SemanticFPNWrapper', None)
+    from polyphonicformer_b200 import detectors as d
+    assert isinstance(model, d.PolyphonicVideo) and isinstance(model, d.Polyphonic)
+    assert isinstance(model.rpn_head, pf.KernelHead) and isinstance(model.roi_head, pf.KernelUpdateIterHead)
+    assert model.roi_head.test_cfg.max_per_img == 100 and model.roi_head.tracking is True and model.num_proposals == 100
+    assert isinstance(model.track_head, d.QuasiDenseMaskEmbedHeadGTMask) and model.track_roi_extractor.num_inputs == 4
+    got = {k[len('track_head.'):]: tuple(t.shape) for k, t in model.state_dict().items() if k.startswith('track_head.')}
+    assert got == {k: tuple(t.shape) for k, t in synth.synth_track_head_state(0).items()}
+    prefixes = {k.split('.')[0] for k in model.state_dict()}
+    assert prefixes == {'rpn_head', 'roi_head', 'track_head'}, prefixes          # + backbone / neck when those have parameters
+    model.init_tracker()
+    assert model.cnt == 1 and isinstance(model.tracker, d.QuasiDenseEmbedTracker) and model.tracker.cfg['memo_tracklet_frames'] == 5
+    with pytest.raises(NotImplementedError):
+        model.forward_train(None, None)
+    with pytest.raises(_cabi_error()):
+        model.eval().track_head(torch.zeros(2, 256, 7, 7))                        # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        d.QuasiDenseMaskEmbedHeadGTMask(**dict(v['track_head'], num_convs=2))
+    with pytest.raises(NotImplementedError):
+        d.QuasiDenseEmbedTracker(**dict({k: x for k, x in v['tracker'].items() if k != 'type'}, match_metric='cosine'))
+
+
+def _cabi_error():
+    from polyphonicformer_b200 import _cabi
+    return _cabi.PFError
