@@ -30,6 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 C, N_KERNELS, STAGES, NUM_CLASSES = 256, 111, 3, 19
@@ -49,6 +50,7 @@ def parse():
                     help='also materialise the (unobservable) fp32 logits + depth einsum of stages 0..S-2')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-video', action='store_true')
     ap.add_argument('--no-check', action='store_true', help='skip the oracle check of one frame of the timed batch')
     ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
     ap.add_argument('--no-kernel-head', action='store_true', help='skip the (non-headline) KernelHead-tail timing')
@@ -361,6 +363,14 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e = run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier)
         e2e_logits = run_e2e_logits(args, eng, hin, B, N, H, W, dev, world, barrier)
+    video = None
+    if not args.no_video:
+        try:
+            video = run_video(args, eng, dev, world, rank, barrier)
+        except Exception as e:       # an extra section, never a reason to lose the headline line
+            if world > 1:
+                raise                # ... but ranks must not diverge around a collective
+            video = dict(unavailable=repr(e)[:300])
 
     if rank != 0:
         return
@@ -392,6 +402,8 @@ def run_ours(args, rank, world, local_rank):
             e2e['host_cpus_bound_per_rank'] = numa_cpus
         line['e2e'] = e2e
         line['e2e_logits'] = e2e_logits
+    if video:
+        line['video'] = video
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(args)
     if not args.no_postprocess and world == 1:
@@ -436,6 +448,94 @@ def parity_check(sd, hin, buf, all_stage_outputs):
                 rel_l2=rel, worst_rel_l2=max(rel.values()), gate=1e-3, passed=max(rel.values()) < 1e-3,
                 final_mask_bits=int(m_ref.numel()), final_mask_bits_flipped=int((m_got != m_ref).sum()),
                 oracle_logits_within_1e4_of_0_per_stage=near)
+
+
+def run_video(args, eng, dev, world, rank, barrier):
+    """Video mode (BASELINE.json config 5: SemKITTI-DVPS-shape 376x1241 frames padded to 384x1248, 5-frame clips), frame
+    sharded: every rank owns 5 frames of each wave of 5 * N consecutive frames (N clips), runs decoder + batched panoptic
+    merge + tracking head (mask -> box, RoIAlign, embedding head) on them, ONE NCCL all_gather of the per-frame records,
+    the association replayed in frame order on every rank (pf_tracker_match, memo reset per clip), track-id / semantic
+    maps painted and read back.  Decoder inputs and the FPN pyramid are synthetic and resident; backbone / FPN / KernelHead
+    are not part of it.  Device time from the first launch to the last read-back, max over ranks (the step has host
+    synchronisations of its own: segment lists after the merge, the record headers, the ids)."""
+    import json as _json
+    from types import SimpleNamespace
+    import torch.distributed as dist
+    from oracle import synth
+    from polyphonicformer_b200.registry import to_config
+    from polyphonicformer_b200.track import TrackHeadEngine
+    from polyphonicformer_b200.video import VideoShardRunner
+    gold = os.path.join(ROOT, 'tests', 'golden')
+    test_cfg = to_config(_json.load(open(os.path.join(gold, 'roi_head_cfg.json')))['test_cfg'])
+    tracker_cfg = _json.load(open(os.path.join(gold, 'video_cfg.json')))['tracker']
+    F, H, W, clip = 5, 48, 156, 5
+    roi = SimpleNamespace(num_proposals=synth.N_PROPOSALS, num_thing_classes=synth.NUM_THING, merge_joint=True)
+    last = SimpleNamespace(depth_act_mode='sigmoid', num_classes=synth.NUM_CLASSES)
+    trk = TrackHeadEngine(synth.synth_track_head_state(0), dev)
+    runner = VideoShardRunner(eng, trk, roi, last, test_cfg, tracker_cfg, synth.NUM_THING, synth.NUM_STUFF, clip_len=clip)
+    hin = host_inputs(F, H, W, 50 + rank)
+    g = torch.Generator().manual_seed(60 + rank)
+    meta = dict(img_shape=(8 * H, 8 * W, 3), ori_shape=(8 * H, 8 * W, 3), pad_shape=(8 * H, 8 * W, 3), scale_factor=1.0,
+                flip=False, batch_input_shape=(8 * H, 8 * W))
+    batch = dict(feats=eng.prepare_feats(hin['x'].to(dev), hin['d'].to(dev)), mask=hin['mask'].to(dev), prop=hin['prop'].to(dev),
+                 dprop=hin['dprop'].to(dev), depth_pred=torch.randn(F, 1, H, W, generator=g).to(dev), img_metas=[meta] * F,
+                 fpn=[torch.randn(F, C, 8 * H // s, 8 * W // s, generator=g).to(dev) for s in (4, 8, 16, 32)])
+    steps = max(3, min(args.steps, 10))
+    things = 0
+    for wave in range(2):
+        out = runner.step(batch, H, W, wave)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for wave in range(2, 2 + steps):
+        out = runner.step(batch, H, W, wave)
+    b.record()
+    barrier()
+    things = sum(int(len(np.unique(o['track'])) - 1) for o in out) * steps
+    runner.timing = {}
+    for wave in range(2 + steps, 5 + steps):           # three more waves with a synchronisation after every section
+        runner.step(batch, H, W, wave)
+    sections = {k: 1e3 * v / 3 for k, v in runner.timing.items()}
+    runner.timing = None
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # the tracking head alone on a fixed 30 RoIs per frame (random-weight decoders merge into few segments, so the step
+    # above exercises it lightly): mask -> box from a 30-segment panoptic map, RoIAlign + embedding head, association
+    K = 30
+    pan = torch.zeros((8 * H, 8 * W), dtype=torch.int32)
+    for k in range(K):
+        pan[(k // 6) * 70 + 5:(k // 6) * 70 + 60, (k % 6) * 200 + 10:(k % 6) * 200 + 150] = k + 1
+    pan = pan.to(dev)
+    fpn1 = [lv[0] for lv in batch['fpn']]
+    runner.tracker.reset()
+    labels = torch.arange(K, device=dev) % 8
+    scores = torch.linspace(0.95, 0.4, K, device=dev).view(-1, 1)
+
+    def track_once(fid):
+        rois, tight = trk.boxes_from_panoptic(pan, list(range(1, K + 1)))
+        emb = trk.embed(fpn1, rois)
+        return runner.tracker.match_async(torch.cat([tight, scores], 1), labels, emb, fid)
+
+    for i in range(3):
+        track_once(i + 1)
+    torch.cuda.synchronize()
+    c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c.record()
+    for i in range(20):
+        track_once(4 + i)
+    d.record()
+    torch.cuda.synchronize()
+    runner.tracker.reset()
+    ms = t.item() / steps
+    return dict(metric='video frames/sec (384x1248, 5-frame clips: decoder + panoptic merge + tracking head + association)',
+                value=world * F * steps / (t.item() / 1e3), unit='frames/s', ms_per_wave=ms, frames_per_rank_per_wave=F,
+                waves=steps, clip_len=clip, decoder_map='%dx%d' % (H, W), collective='one all_gather_into_tensor per wave '
+                '(%d B per rank) on a side stream' % (F * (2 + 100 * 262) * 4) if world > 1 else 'none (1 rank)',
+                tracked_things_per_frame=things / (F * steps), section_ms_per_wave_synchronised=sections,
+                tracking_head_ms_per_frame_30_rois=c.elapsed_time(d) / 20,
+                tracking_head_what='pf_track_boxes_from_panoptic + pf_track_embed (RoIAlign, 4 conv+GN, FC, FC) + '
+                                   'pf_tracker_match on 30 RoIs, 9 launches')
 
 
 def kernel_head_timing(args, B, dev, peak_gbs, cpu=True):

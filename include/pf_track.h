@@ -99,9 +99,10 @@ int pf_tracker_match(const pf_tracker_config* cfg, void* state, const float* bbo
                      const float* embeds, int K, int frame_id, int32_t* order, int32_t* ids, int32_t* n_kept,
                      int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* sem[p] = sem_lut[panoptic[p]] (uint8), track[p] = track_lut[panoptic[p]] (int32); luts have 256 entries */
+/* sem[p] = sem_lut[panoptic[p]] (uint8), track[p] = track_lut[panoptic[p]]; luts have 256 entries; `track` is int32
+ * [n_pixels], or float64 [n_pixels] when track_f64 != 0 (the reference's track map is np.zeros(shape): float64) */
 int pf_track_paint(const int32_t* panoptic, const uint8_t* sem_lut, const int32_t* track_lut, int n_pixels, uint8_t* sem,
-                   int32_t* track, void* stream);
+                   void* track, int track_f64, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

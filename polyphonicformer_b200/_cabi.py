@@ -82,7 +82,7 @@ _SIGS = {
     'pf_tracker_reset': (c_int, [c_void_p, c_void_p]),
     'pf_tracker_match': (c_int, [POINTER(TrackerConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    'pf_track_paint': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'pf_track_paint': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     # ---- include/pf_decoder.h
     'pf_cast_maps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_fpn_pred': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,

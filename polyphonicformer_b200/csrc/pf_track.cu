@@ -491,16 +491,17 @@ __global__ void __launch_bounds__(TM_THREADS) tracker_match_kernel(const pf_trac
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) track_paint_kernel(const int32_t* __restrict__ pan, const uint8_t* __restrict__ sem_lut,
                                                           const int32_t* __restrict__ track_lut, int n, uint8_t* __restrict__ sem,
-                                                          int32_t* __restrict__ track) {
+                                                          T* __restrict__ track) {
     __shared__ uint8_t s_sem[256];
     __shared__ int32_t s_trk[256];
     s_sem[threadIdx.x] = sem_lut[threadIdx.x], s_trk[threadIdx.x] = track_lut[threadIdx.x];
     __syncthreads();
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const int id = __ldg(pan + i) & 255;
-        sem[i] = s_sem[id], track[i] = s_trk[id];
+        sem[i] = s_sem[id], track[i] = static_cast<T>(s_trk[id]);
     }
 }
 
@@ -689,12 +690,14 @@ extern "C" int pf_tracker_match(const pf_tracker_config* cfg, void* state, const
 }
 
 extern "C" int pf_track_paint(const int32_t* panoptic, const uint8_t* sem_lut, const int32_t* track_lut, int n_pixels,
-                              uint8_t* sem, int32_t* track, void* stream) {
+                              uint8_t* sem, void* track, int track_f64, void* stream) {
     using namespace pf;
     if (int e = check_device()) return e;
     PF_REQUIRE(panoptic && sem_lut && track_lut && sem && track && n_pixels > 0, PF_ERR_ARG, "pf_track_paint: bad argument");
     const int blocks = min((n_pixels + 255) / 256, num_sms() * 8);
-    track_paint_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(panoptic, sem_lut, track_lut, n_pixels, sem, track);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (track_f64) track_paint_kernel<double><<<blocks, 256, 0, st>>>(panoptic, sem_lut, track_lut, n_pixels, sem, static_cast<double*>(track));
+    else track_paint_kernel<int32_t><<<blocks, 256, 0, st>>>(panoptic, sem_lut, track_lut, n_pixels, sem, static_cast<int32_t*>(track));
     PF_CHECK_LAUNCH("track_paint_kernel");
     return PF_OK;
 }

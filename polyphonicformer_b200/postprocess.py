@@ -42,7 +42,7 @@ def _segments_info(rec):
 
 
 def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, img_metas, depth_preds, depth_init,
-                       stride2_inputs=False, device_results=None):
+                       stride2_inputs=False, device_results=None, host_buffer=None):
     """get_panoptic (kernel_update.py:421-469) for the B frames of a batch in ONE set of launches and ONE device->host
     copy.  cls_scores [B,N,classes]; mask_preds / depth_preds [B,N,h,w]; depth_init [B,h,w] (or [B,1,h,w]).
 
@@ -52,7 +52,9 @@ def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, im
     kernel_update.py:339-351 loops over frames of one padded batch); mixed shapes go frame by frame.
     Returns the reference's list of (None, None, (panoptic, segments_info), depth_basic, depth_final), numpy.
     ``device_results``: an optional list that receives, per frame, a dict of the DEVICE tensors behind those arrays
-    (panoptic int32 [H0,W0], depth_final, depth_basic) -- the video model's tracking path keeps working on them."""
+    (panoptic int32 [H0,W0], depth_final, depth_basic) -- the video model's tracking path keeps working on them.
+    ``host_buffer``: an optional PINNED uint8 tensor the results are read back into (the returned arrays are then views of
+    it and live as long as the caller keeps it untouched); by default a fresh pageable array per call."""
     if not roi_head.merge_joint:
         raise NotImplementedError('merge_joint=False is not implemented by the reference (kernel_update.py:467)')
     if last_head.depth_act_mode not in _DEPTH_MODES:
@@ -93,7 +95,13 @@ def get_panoptic_batch(roi_head, last_head, cls_scores, mask_preds, test_cfg, im
     if device_results is not None:
         pd, fd, bd = (t.view(torch.int32 if i == 0 else torch.float32).view(B, H0, W0) for i, t in enumerate((pan, dfinal, dbasic)))
         device_results += [dict(panoptic=pd[b], depth_final=fd[b], depth_basic=bd[b]) for b in range(B)]
-    host = out.cpu().numpy()                                # the one host synchronisation of the post-processing
+    if host_buffer is not None and host_buffer.numel() >= out.numel():
+        host_t = host_buffer[:out.numel()]
+        host_t.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = host_t.numpy()
+    else:
+        host = out.cpu().numpy()                            # the one host synchronisation of the post-processing
     pan_h = host[offs[0]:offs[1]].view(np.int32).reshape(B, H0, W0)
     dfinal_h = host[offs[1]:offs[2]].view(np.float32).reshape(B, H0, W0)
     dbasic_h = host[offs[2]:offs[3]].view(np.float32).reshape(B, H0, W0)

@@ -33,19 +33,22 @@ def frames_per_rank(n_items, world):
 
 def pack_records(records, slots, max_k, device=None):
     """records: list of (frame_id, bboxes [K,5], labels [K], feats [K,256]) -> float32 [slots, 2 + max_k*RECORD_WIDTH].
-    Row layout: frame_id, K, then K records; unused slots have frame_id = -1.  K > max_k raises."""
-    out = torch.zeros((slots, 2 + max_k * RECORD_WIDTH), dtype=torch.float32, device=device)
-    out[:, 0] = -1
+    Row layout: frame_id, K, then K records; unused slots have frame_id = -1.  K > max_k raises.  The headers of all
+    slots go to the device in ONE copy; the bodies are device-to-device."""
     if len(records) > slots:
         raise ValueError('%d records for %d slots' % (len(records), slots))
+    out = torch.zeros((slots, 2 + max_k * RECORD_WIDTH), dtype=torch.float32, device=device)
+    head = torch.zeros((slots, 2), dtype=torch.float32)
+    head[:, 0] = -1
     for i, (fid, bboxes, labels, feats) in enumerate(records):
         k = int(bboxes.shape[0])
         if k > max_k:
             raise ValueError('frame %d has %d tracks > max_k=%d' % (fid, k, max_k))
-        out[i, 0], out[i, 1] = float(fid), float(k)
+        head[i, 0], head[i, 1] = float(fid), float(k)
         if k:
             body = torch.cat([bboxes.reshape(k, 5).float(), labels.reshape(k, 1).float(), feats.reshape(k, 256).float()], 1)
             out[i, 2:2 + k * RECORD_WIDTH] = body.reshape(-1).to(out.device)
+    out[:, :2] = head.to(out.device)
     return out
 
 

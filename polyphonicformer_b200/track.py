@@ -183,21 +183,45 @@ class DeviceTracker:
         return bboxes[order_d], labels[order_d], ids
 
 
+def paint_maps_batch(panoptic_devs, segments_infos, seg_ids_list, ids_list, default_sem, host_buffer=None):
+    """generate_track_id_maps + get_semantic_seg (polyphonic_former_video.py:436-451) for several frames of one shape: two
+    look-up tables per frame over its panoptic map (pf_track_paint), ONE upload of the tables and ONE read-back of the maps.
+    As in the reference, ids[i] (kept detections, descending score) is painted onto the i-th thing mask in segment order;
+    pixels of no segment get ``default_sem`` / track id 0.  Returns per frame numpy (sem uint8, track float64 -- the
+    reference's np.zeros(shape))."""
+    F = len(panoptic_devs)
+    if F == 0:
+        return []
+    dev, shape = panoptic_devs[0].device, tuple(panoptic_devs[0].shape)
+    n = panoptic_devs[0].numel()
+    luts = np.zeros((F, 1280), dtype=np.uint8)                     # per frame: track lut (256 x int32) | sem lut (256 x uint8)
+    for f in range(F):
+        trk_lut = np.zeros(256, dtype=np.int32)
+        for i, tid in enumerate(ids_list[f]):
+            trk_lut[seg_ids_list[f][i]] = int(tid)
+        luts[f, :1024] = trk_lut.view(np.uint8)
+        luts[f, 1024:] = default_sem
+        for s in segments_infos[f]:
+            luts[f, 1024 + s['id']] = s['category_id']
+    luts_d = torch.from_numpy(luts).to(dev)
+    out = torch.empty(F * n * 9, dtype=torch.uint8, device=dev)      # all track maps (float64), then all semantic maps (uint8)
+    trk = out[:F * n * 8].view(torch.float64).view(F, n)
+    sem = out[F * n * 8:].view(F, n)
+    for f in range(F):
+        _cabi.call('pf_track_paint', _ptr(panoptic_devs[f]), _ptr(luts_d[f, 1024:]), _ptr(luts_d[f]), n, _ptr(sem[f]), _ptr(trk[f]),
+                   1, _stream())
+    if host_buffer is not None and host_buffer.numel() >= out.numel():
+        host_t = host_buffer[:out.numel()]          # the caller's pinned buffer: the returned arrays are views of it
+        host_t.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = host_t.numpy()
+    else:
+        host = out.cpu().numpy()
+    trk_h = host[:F * n * 8].view(np.float64).reshape((F,) + shape)
+    sem_h = host[F * n * 8:].reshape((F,) + shape)
+    return [(sem_h[f], trk_h[f]) for f in range(F)]
+
+
 def paint_maps(panoptic_dev, segments_info, seg_ids, ids, default_sem):
-    """generate_track_id_maps + get_semantic_seg (polyphonic_former_video.py:436-451) as two look-up tables over the
-    panoptic map (pf_track_paint).  As in the reference, ids[i] (kept detections, descending score) is painted onto the
-    i-th thing mask in segment order; pixels of no segment get ``default_sem`` / track id 0.  Returns numpy
-    (sem uint8, track float64 -- the reference's np.zeros(shape))."""
-    dev = panoptic_dev.device
-    sem_lut = np.full(256, default_sem, dtype=np.uint8)
-    for s in segments_info:
-        sem_lut[s['id']] = s['category_id']
-    trk_lut = np.zeros(256, dtype=np.int32)
-    for i, tid in enumerate(ids):
-        trk_lut[seg_ids[i]] = int(tid)
-    luts = torch.from_numpy(np.concatenate([trk_lut.view(np.uint8), sem_lut])).to(dev)      # one small upload
-    sem = torch.empty(panoptic_dev.shape, dtype=torch.uint8, device=dev)
-    trk = torch.empty(panoptic_dev.shape, dtype=torch.int32, device=dev)
-    _cabi.call('pf_track_paint', _ptr(panoptic_dev), _ptr(luts[1024:]), _ptr(luts), panoptic_dev.numel(), _ptr(sem), _ptr(trk),
-               _stream())
-    return sem.cpu().numpy(), trk.cpu().numpy().astype(np.float64)
+    """One frame of paint_maps_batch."""
+    return paint_maps_batch([panoptic_dev], [segments_info], [seg_ids], [ids], default_sem)[0]

@@ -14,7 +14,9 @@ import torch
 import torch.distributed as dist
 
 from . import postprocess, sharding
-from .track import MAX_K, DeviceTracker, paint_maps
+import time
+
+from .track import MAX_K, DeviceTracker, paint_maps_batch
 
 
 class VideoShardRunner:
@@ -36,7 +38,8 @@ class VideoShardRunner:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.cnt = 1
         self.comm_stream = torch.cuda.Stream(self.device)
-        self.last_launches = 0
+        self._bufs = {}           # decoder output buffers and pinned read-back buffers, per batch shape
+        self.timing = None        # set to a dict to collect per-section host times (seconds, synchronised) in step()
 
     def global_ids(self, wave, n_local):
         """Global frame numbers of this rank's n_local frames of wave `wave` (a wave = world * n_local consecutive frames)."""
@@ -46,11 +49,20 @@ class VideoShardRunner:
     def decode_panoptic(self, batch, H, W):
         """Decoder + batched panoptic merge for this rank's frames.  Returns (the reference's per-frame result tuples, the
         device tensors behind them)."""
-        out = self.dec.decode(batch['feats'], batch['mask'], batch['prop'], batch['dprop'], H, W, upsample=False)
+        F, N = batch['mask'].shape[:2]
+        key = (F, N, H, W)
+        if key not in self._bufs:
+            npx = 64 * H * W
+            self._bufs[key] = dict(dec=self.dec.alloc_decode_buffers(F, N, H, W, upsample=False),
+                                   pan=torch.empty(F * (npx * 12 + 128 * 24 + 4), dtype=torch.uint8).pin_memory(),
+                                   paint=torch.empty(F * npx * 9, dtype=torch.uint8).pin_memory())
+        bufs = self._bufs[key]
+        out = self.dec.decode(batch['feats'], batch['mask'], batch['prop'], batch['dprop'], H, W, upsample=False,
+                              buffers=bufs['dec'])
         dev_res = []
         res = postprocess.get_panoptic_batch(self.roi_head, self.last_head, out['cls_score'], out['mask_preds'], self.test_cfg,
                                              batch['img_metas'], out['depth_preds'], batch['depth_pred'],
-                                             stride2_inputs=True, device_results=dev_res)
+                                             stride2_inputs=True, device_results=dev_res, host_buffer=bufs['pan'])
         return res, dev_res
 
     def track_records(self, res, dev_res, fpn):
@@ -70,13 +82,27 @@ class VideoShardRunner:
             recs.append((seg_ids, torch.cat([tight, scores.view(-1, 1)], 1), labels, embeds))
         return recs
 
+    def _mark(self, name, t0):
+        if self.timing is not None:
+            torch.cuda.synchronize()
+            self.timing[name] = self.timing.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     def step(self, batch, H, W, wave):
-        """One wave: this rank's frames end to end.  Returns the reference's per-frame dicts (sem, track, depth)."""
-        gids = self.global_ids(wave, batch['mask'].shape[0])
+        """One wave: this rank's frames end to end.  Returns the reference's per-frame dicts (sem, track, depth); sem and
+        depth are views of per-runner pinned buffers the next step overwrites (so are track maps)."""
+        F, N = batch['mask'].shape[:2]
+        gids = self.global_ids(wave, F)
+        t = time.perf_counter()
         res, dev_res = self.decode_panoptic(batch, H, W)
+        t = self._mark('decode_panoptic', t)
         recs = self.track_records(res, dev_res, batch['fpn'])
+        t = self._mark('track_records', t)
         ids = self.associate(recs, gids)
-        return self.paint(dev_res, res, recs, gids, ids)
+        t = self._mark('associate', t)
+        out = self.paint(dev_res, res, recs, gids, ids, host_buffer=self._bufs[(F, N, H, W)]['paint'])
+        self._mark('paint', t)
+        return out
 
     def associate(self, recs, gids):
         """The ONE collective + the replay.  Returns {global frame id: track ids (+1, 0 = none) of its kept detections}."""
@@ -126,11 +152,8 @@ class VideoShardRunner:
                 result[g] = ids.tolist()
         return result
 
-    def paint(self, dev_res, res, recs, gids, ids_by_frame):
-        out = []
-        for f, g in enumerate(gids):
-            seg_ids = recs[f][0] if recs[f] is not None else []
-            sem, trk = paint_maps(dev_res[f]['panoptic'], res[f][2][1], seg_ids, ids_by_frame.get(g, []),
-                                  self.num_thing_classes + self.num_stuff_classes)
-            out.append({'sem': sem, 'track': trk, 'depth': res[f][4]})
-        return out
+    def paint(self, dev_res, res, recs, gids, ids_by_frame, host_buffer=None):
+        maps = paint_maps_batch([d['panoptic'] for d in dev_res], [r[2][1] for r in res],
+                                [rec[0] if rec is not None else [] for rec in recs], [ids_by_frame.get(g, []) for g in gids],
+                                self.num_thing_classes + self.num_stuff_classes, host_buffer)
+        return [{'sem': sem, 'track': trk, 'depth': r[4]} for (sem, trk), r in zip(maps, res)]
