@@ -713,11 +713,41 @@ def _time_pipeline(pipe, pin_in, pin_out, steps, dev, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item() / steps
     h2d, d2h = pipe.h2d_bytes(), pipe.d2h_bytes()
+    # the ceiling the host side sets: the SAME copies (same pinned buffers, same two streams, all ranks at once) with no
+    # kernel in between -- what the step would cost if the device work were free
+    barrier()
+    s = pipe.slots[0]
+    src = [pin_in[0][k] for k in ('x', 'd', 'mask')]
+    dst = [s['x'], s['d'], s['mask']]
+    outs = [(v, torch.empty(v.shape, dtype=v.dtype, device=dev)) for v in pin_out[0].values()]
+    c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    c0.record(pipe.s_in)
+    pipe.s_out.wait_event(c0)
+    for _ in range(steps):
+        with torch.cuda.stream(pipe.s_in):
+            for a_, b_ in zip(dst, src):
+                a_.copy_(b_, non_blocking=True)
+        with torch.cuda.stream(pipe.s_out):
+            for h_, d_ in outs:
+                h_.copy_(d_, non_blocking=True)
+    c1.record(pipe.s_in)
+    c2.record(pipe.s_out)
+    pipe.drain()
+    barrier()
+    tc = torch.tensor([max(c0.elapsed_time(c1), c0.elapsed_time(c2))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    ms_copy = tc.item() / steps
     return dict(value=world * pipe.B * steps / (t.item() / 1e3), unit='frames/s', h2d_bytes_per_step=h2d,
                 d2h_bytes_per_step=d2h, steps=steps, ms_per_step=ms,
                 # the two copy directions run on their own streams: each one's rate if it alone filled the step
                 h2d_GBps_per_rank=h2d / ms / 1e6, d2h_GBps_per_rank=d2h / ms / 1e6,
-                host_GBps_all_ranks=world * (h2d + d2h) / ms / 1e6)
+                host_GBps_all_ranks=world * (h2d + d2h) / ms / 1e6,
+                copies_only=dict(ms_per_step=ms_copy, frames_per_s=world * pipe.B / (ms_copy / 1e3),
+                                 host_GBps_all_ranks=world * (h2d + d2h) / ms_copy / 1e6,
+                                 what='the same host<->device copies with no kernels, all ranks at once: the ceiling the host '
+                                      'link (PCIe / host DRAM) sets for this step'),
+                bound='host copies (PCIe / host DRAM): the step runs at %.0f %% of its copies-only ceiling' % (100 * ms_copy / ms))
 
 
 def run_e2e(args, eng, hin, B, N, H, W, dev, world, barrier):

@@ -59,6 +59,11 @@ class TrackWeights(Structure):
                 ('fc1_b', c_void_p), ('fc2_wt', c_void_p), ('fc2_b', c_void_p), ('gn_eps', c_float)]
 
 
+class FpnWeights(Structure):
+    """struct pf_fpn_weights (include/pf_fpn.h)."""
+    _fields_ = [('conv_w', c_void_p), ('gn_gamma', c_void_p), ('gn_beta', c_void_p), ('gn_eps', c_float)]
+
+
 class TrackerConfig(Structure):
     """struct pf_tracker_config (include/pf_track.h)."""
     _FLOATS = ['init_score_thr', 'obj_score_thr', 'match_score_thr', 'memo_momentum', 'nms_conf_thr',
@@ -83,6 +88,10 @@ _SIGS = {
     'pf_tracker_match': (c_int, [POINTER(TrackerConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'pf_track_paint': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    # ---- include/pf_fpn.h
+    'pf_semantic_fpn_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'pf_semantic_fpn': (c_int, [POINTER(FpnWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     # ---- include/pf_decoder.h
     'pf_cast_maps': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pf_fpn_pred': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,

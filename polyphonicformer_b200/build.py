@@ -11,7 +11,7 @@ LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libpf_decoder.so')
 OBJDIR = os.path.join(HERE, 'build')
 SOURCES = ['pf_host.cu', 'pf_elementwise.cu', 'pf_pool.cu', 'pf_update.cu', 'pf_stage.cu', 'pf_einsum.cu', 'pf_decoder.cu',
-           'pf_postprocess.cu', 'pf_head.cu', 'pf_track.cu']
+           'pf_postprocess.cu', 'pf_head.cu', 'pf_track.cu', 'pf_fpn.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

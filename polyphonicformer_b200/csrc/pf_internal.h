@@ -7,6 +7,7 @@
 
 #include "../../include/pf_decoder.h"
 #include "../../include/pf_track.h"
+#include "../../include/pf_fpn.h"
 
 namespace pf {
 

@@ -27,7 +27,7 @@ constexpr int SG_SMEM_USED = SG_STAT_OFF + 2 * 4 * 16 * 4;
 constexpr int SG_SMEM = SG_SMEM_USED + 1024;   // slack for the 1024-byte alignment of the ring
 
 enum { SG_CONV = 0, SG_FC = 1 };
-enum { SG_EPI_GN64 = 0, SG_EPI_PARTIAL = 1 };
+enum { SG_EPI_GN64 = 0, SG_EPI_PARTIAL = 1, SG_EPI_RAWSTATS = 2 };
 
 struct SgArgs {
     int mode;              // SG_CONV / SG_FC
@@ -38,6 +38,10 @@ struct SgArgs {
     int fc_pos_per_split;  // SG_FC: grid positions per split (blockIdx.z)
     int fc_grid, fc_pitch; // SG_FC: valid positions are (y, x) with y, x < fc_grid at row y * fc_pitch + x of an item
     int shift[9];          // SG_CONV: row shift of tap t
+    int plane[9];          // SG_CONV: plane (third tensor coordinate) of tap t inside an image: the four parity phases of a
+                           //          stride-2 convolution; 0 otherwise
+    int rows_per_img;      // SG_CONV: rows of one image (a multiple of 128): tile row m0 -> (image m0 / rows_per_img, row m0 %
+    int planes_per_img;    //          rows_per_img); the A tensor is [images * planes_per_img][rows_per_img][channels]
     // ---- epilogue
     int n_items;           // GN64: items (RoIs) that exist; rows of later items are written as zeros
     const float *gamma, *beta;   // GN64: [256] of this layer
@@ -45,6 +49,12 @@ struct SgArgs {
     uint16_t *out_hi, *out_lo;   // GN64: bf16 planes [rows][256]
     float* partial;              // PARTIAL: fp32 [split][part_rows][part_ld]
     int part_rows, part_ld;
+    // RAWSTATS: a convolution over a zero-padded (grid_h + 2) x (grid_w + 2) grid per image whose GroupNorm spans the whole
+    // image: raw fp32 output rows [row][256] for the interior positions + per-tile (sum, sum of squares) of every group of 8
+    // channels over them
+    float* raw;
+    float2* stats;               // [gridDim.y][32 groups]
+    int grid_h, grid_w;
 };
 
 __device__ __forceinline__ void sg_named_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -122,7 +132,8 @@ sgemm_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_constant_
             int ac0, ac1, ac2, wc0, wr;
             if (a.mode == SG_CONV) {
                 const int tap = it / a.cin_blocks, cb = it - tap * a.cin_blocks;
-                ac0 = cb * SG_KC, ac1 = m0 + a.shift[tap], ac2 = 0;
+                const int img = m0 / a.rows_per_img;
+                ac0 = cb * SG_KC, ac1 = m0 - img * a.rows_per_img + a.shift[tap], ac2 = img * a.planes_per_img + a.plane[tap];
                 wc0 = cb * SG_KC, wr = tap * a.w_tap_rows + n0;
             } else {
                 const int pi = split * a.fc_pos_per_split + (it >> 2), cb = it & 3;
@@ -210,6 +221,37 @@ sgemm_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_constant_
                     y[c] = valid ? fmaxf(v, 0.f) : 0.f;
                 }
                 sg_store_split32(a.out_hi + row * 256 + n0 + ch * 32, a.out_lo + row * 256 + n0 + ch * 32, y);
+            }
+        } else if (EPI == SG_EPI_RAWSTATS) {
+            const int img = m0 / a.rows_per_img, qrow = m0 - img * a.rows_per_img + r, pitch = a.grid_w + 2;
+            const int y1 = qrow / pitch, x1 = qrow - y1 * pitch;
+            const bool valid = y1 >= 1 && y1 <= a.grid_h && x1 >= 1 && x1 <= a.grid_w;
+            float* dst = a.raw + ((size_t)m0 + r) * 256 + n0;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float y[32];
+                sg_ld32(trow + ch * 32, y);
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + ch * 32 + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float s = 0.f, ss = 0.f;
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) s += y[g * 8 + c], ss += y[g * 8 + c] * y[g * 8 + c];
+                    }
+                    s = sg_warp_sum(s), ss = sg_warp_sum(ss);
+                    if (lane == 0) s_stat[q * 16 + ch * 4 + g] = s, s_stat[64 + q * 16 + ch * 4 + g] = ss;
+                }
+            }
+            sg_named_bar();
+            if (r < 16) {
+                const float s = (s_stat[r] + s_stat[16 + r]) + (s_stat[32 + r] + s_stat[48 + r]);
+                const float ss = (s_stat[64 + r] + s_stat[80 + r]) + (s_stat[96 + r] + s_stat[112 + r]);
+                a.stats[(size_t)blockIdx.y * 32 + blockIdx.x * 16 + r] = make_float2(s, ss);
             }
         } else if (EPI == SG_EPI_PARTIAL) {
             const bool ok = m0 + r < a.part_rows;

@@ -571,6 +571,7 @@ static int run_track_head(const pf_track_weights* w, const EmbedScratch& sc, int
         if (int e = make_tmap_bf16_2d(&wm, w->conv_w + (size_t)l * 2 * 9 * 256 * 256, 2 * 9 * 256, 256, 256, 128, SG_KC)) return e;
         SgArgs a = {};
         a.mode = SG_CONV, a.n_kb = 9 * 4, a.cin_blocks = 4, a.w_tap_rows = 256, a.w_lo = 9 * 256;
+        a.rows_per_img = (int)rows, a.planes_per_img = 1;
         for (int tp = 0; tp < 9; ++tp) a.shift[tp] = (tp / 3 - 1) * TR_PITCH + (tp % 3 - 1);
         a.n_items = K, a.gamma = w->gn_gamma + l * 256, a.beta = w->gn_beta + l * 256, a.eps = w->gn_eps;
         a.out_hi = sc.act[(l + 1) & 1][0], a.out_lo = sc.act[(l + 1) & 1][1];

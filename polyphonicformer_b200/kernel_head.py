@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _cabi
-from ._cabi import PF_C, HeadWeights
+from ._cabi import PF_C, FpnWeights, HeadWeights
 from .decoder import _ptr, _stream_ptr, round_up
 
 H_ROWS, H_ROW_SEG, H_ROW_DEP = 160, 112, 144   # head_w row blocks (include/pf_decoder.h)
@@ -87,16 +87,23 @@ class FpnPred:
         self.gn_eps = gn_eps
         self._ws = None
 
-    def forward(self, fused, want_fp32=False):
-        """fused: fp32 [B,256,H,W] (feature_add_all_level).  Returns (maps bf16 [3][B][256][HWp], maps32 or None)."""
+    def forward(self, fused, want_fp32=False, hw=None):
+        """fused: fp32 [B,256,H,W] (feature_add_all_level), or -- with hw = (H, W) -- the bf16 [B][256][HWp] buffer
+        SemanticFpnPyramid wrote.  Returns (maps bf16 [3][B][256][HWp], maps32 or None)."""
         lib = _cabi.load()
-        B, _, H, W = fused.shape
-        HW = H * W
-        HWp = round_up(HW, 8)
         st = _stream_ptr()
-        fused = fused.to(self.device, torch.float32).contiguous()
-        fb = torch.empty((B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
-        _cabi.call('pf_cast_maps', _ptr(fused), _ptr(fb), B * PF_C, HW, HWp, st)
+        if hw is not None:
+            (H, W), B, fb = hw, fused.shape[0], fused
+            HW = H * W
+            HWp = round_up(HW, 8)
+            assert fb.dtype == torch.bfloat16 and tuple(fb.shape) == (B, PF_C, HWp) and fb.is_contiguous()
+        else:
+            B, _, H, W = fused.shape
+            HW = H * W
+            HWp = round_up(HW, 8)
+            fused = fused.to(self.device, torch.float32).contiguous()
+            fb = torch.empty((B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
+            _cabi.call('pf_cast_maps', _ptr(fused), _ptr(fb), B * PF_C, HW, HWp, st)
         maps = torch.empty((3, B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
         maps32 = torch.empty((3, B, PF_C, H, W), dtype=torch.float32, device=self.device) if want_fp32 else None
         nbytes = lib.pf_kernel_head_workspace_bytes(B, HW)
@@ -106,6 +113,55 @@ class FpnPred:
                    _ptr(maps), _ptr(maps32), _ptr(self._ws), nbytes, B, HW, HWp, st)
         self.last_launches = lib.pf_last_launch_count()
         return maps, maps32
+
+
+class SemanticFpnPyramid:
+    """``SemanticFPNWrapper.forward`` up to ``feature_add_all_level`` (polyphonic/funcs/semantic_fpn.py:198-219) in the shipped
+    configuration, on ``pf_semantic_fpn``: seven 3x3 conv + GN32 + ReLU modules as shifted-row tensor-core GEMMs, the x2
+    bilinear steps and the four-level sum.  State-dict keys (prefix ``rpn_head.localization_fpn.``):
+    convs_all_levels.{0.conv0, 1.conv0, 2.conv0, 2.conv1, 3.conv0, 3.conv1, 3.conv2}.{conv.weight, gn.weight, gn.bias}."""
+    NAMES = ('convs_all_levels.0.conv0', 'convs_all_levels.1.conv0', 'convs_all_levels.2.conv0', 'convs_all_levels.2.conv1',
+             'convs_all_levels.3.conv0', 'convs_all_levels.3.conv1', 'convs_all_levels.3.conv2')
+
+    def __init__(self, state_dict, device, gn_eps=1e-5):
+        _cabi.load()
+        self.device = torch.device(device)
+        g = lambda k: state_dict[k].detach().to('cpu', torch.float32)
+        planes = []
+        for n in self.NAMES:
+            w = g(n + '.conv.weight')
+            if tuple(w.shape) != (PF_C, PF_C, 3, 3):
+                raise NotImplementedError('%s.conv.weight has shape %s, expected 256x256x3x3' % (n, tuple(w.shape)))
+            hi, lo = _hi_lo(w.permute(2, 3, 0, 1).reshape(9, PF_C, PF_C))          # [ky*3+kx][out][in]
+            planes += [hi, lo]
+        self.conv_w = torch.stack(planes).contiguous().to(self.device)            # [7*2][9][256][256]
+        self.gn_gamma = torch.stack([g(n + '.gn.weight') for n in self.NAMES]).contiguous().to(self.device)
+        self.gn_beta = torch.stack([g(n + '.gn.bias') for n in self.NAMES]).contiguous().to(self.device)
+        self.struct = FpnWeights(conv_w=self.conv_w.data_ptr(), gn_gamma=self.gn_gamma.data_ptr(),
+                                 gn_beta=self.gn_beta.data_ptr(), gn_eps=gn_eps)
+        self._ws = None
+
+    def forward(self, inputs, want_fp32=False):
+        """inputs: the four FPN levels fp32 [B,256,2H,2W], [B,256,H,W], [B,256,H/2,W/2], [B,256,H/4,W/4].
+        Returns (fused bf16 [B][256][HWp], fused fp32 [B,256,H,W] or None, (H, W))."""
+        lib = _cabi.load()
+        p = [t.to(self.device, torch.float32).contiguous() for t in inputs[:4]]
+        B, C, H, W = p[1].shape
+        want = [(B, PF_C, 2 * H, 2 * W), (B, PF_C, H, W), (B, PF_C, H // 2, W // 2), (B, PF_C, H // 4, W // 4)]
+        if H % 4 or W % 4 or [tuple(t.shape) for t in p] != want:
+            raise NotImplementedError('pf_semantic_fpn needs the four levels of a map whose sides are multiples of 4 (got %s)'
+                                      % [tuple(t.shape) for t in p])
+        HW = H * W
+        HWp = round_up(HW, 8)
+        fused = torch.empty((B, PF_C, HWp), dtype=torch.bfloat16, device=self.device)
+        fused32 = torch.empty((B, PF_C, H, W), dtype=torch.float32, device=self.device) if want_fp32 else None
+        nbytes = lib.pf_semantic_fpn_workspace_bytes(B, H, W)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _cabi.call('pf_semantic_fpn', ctypes.byref(self.struct), _ptr(p[0]), _ptr(p[1]), _ptr(p[2]), _ptr(p[3]), _ptr(fused),
+                   _ptr(fused32), _ptr(self._ws), nbytes, B, H, W, HWp, _stream_ptr())
+        self.last_launches = lib.pf_last_launch_count()
+        return fused, fused32, (H, W)
 
 
 class KernelHeadTail:
