@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-video', action='store_true')
+    ap.add_argument('--no-model', action='store_true')
     ap.add_argument('--no-check', action='store_true', help='skip the oracle check of one frame of the timed batch')
     ap.add_argument('--no-postprocess', action='store_true', help='skip the (non-headline) post-processing timing')
     ap.add_argument('--no-kernel-head', action='store_true', help='skip the (non-headline) KernelHead-tail timing')
@@ -371,6 +372,14 @@ def run_ours(args, rank, world, local_rank):
             if world > 1:
                 raise                # ... but ranks must not diverge around a collective
             video = dict(unavailable=repr(e)[:300])
+    mfps = None
+    if not args.no_model:
+        try:
+            mfps = model_fps(args, dev, world, barrier)
+        except Exception as e:
+            if world > 1:
+                raise
+            mfps = dict(unavailable=repr(e)[:300])
 
     if rank != 0:
         return
@@ -404,6 +413,8 @@ def run_ours(args, rank, world, local_rank):
         line['e2e_logits'] = e2e_logits
     if video:
         line['video'] = video
+    if mfps:
+        line['model_fps'] = mfps
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_baseline(args)
     if not args.no_postprocess and world == 1:
@@ -538,6 +549,105 @@ def run_video(args, eng, dev, world, rank, barrier):
                                    'pf_tracker_match on 30 RoIs, 9 launches')
 
 
+class StandInBackbone(torch.nn.Module):
+    """MEASUREMENT SCAFFOLDING, not product code: the backbone + FPN of poly_r50 stay the reference's PyTorch modules
+    (north-star) and mmdet's cannot be imported on the bench box, so `model_fps` runs torchvision's ResNet-50 (the same
+    architecture, random init) and a plain PyTorch FPN (mmdet FPN semantics: 1x1 laterals, nearest top-down, 3x3 outputs,
+    256 channels, strides 4 / 8 / 16 / 32) in front of this package's heads.  PyTorch eager fp32 (cuDNN), as the reference
+    would run them."""
+
+    def __init__(self):
+        super().__init__()
+        from torchvision.models import resnet50
+        r = resnet50(weights=None)
+        self.stem = torch.nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
+        self.layers = torch.nn.ModuleList([r.layer1, r.layer2, r.layer3, r.layer4])
+        self.lateral = torch.nn.ModuleList([torch.nn.Conv2d(c, 256, 1) for c in (256, 512, 1024, 2048)])
+        self.output = torch.nn.ModuleList([torch.nn.Conv2d(256, 256, 3, padding=1) for _ in range(4)])
+
+    def forward(self, img):
+        x, feats = self.stem(img), []
+        for layer in self.layers:
+            x = layer(x)
+            feats.append(x)
+        lat = [l(f) for l, f in zip(self.lateral, feats)]
+        for i in range(3, 0, -1):
+            lat[i - 1] = lat[i - 1] + torch.nn.functional.interpolate(lat[i], size=lat[i - 1].shape[-2:], mode='nearest')
+        return [o(l) for o, l in zip(self.output, lat)]
+
+
+def model_fps(args, dev, world, barrier):
+    """SURVEY.md section 8(d) "model fps": the whole image model through the detector API the reference's users call,
+    `Polyphonic.simple_test(img, img_metas)` (polyphonic_former.py:130-161) -- images in pinned HOST memory -> backbone +
+    FPN (PyTorch, see StandInBackbone) -> SemanticFPN neck + KernelHead + 3-stage decoder + batched panoptic merge (this
+    package's kernels) -> panoptic map + segments + two depth maps as numpy on the host.  Random-init weights of the
+    poly_r50 architecture; per-GPU batch as the headline.  Wall-clock between barriers (the call synchronises itself when
+    it reads the results back), max over ranks."""
+    import json as _json
+    import torch.distributed as dist
+    from polyphonicformer_b200 import registry
+    gold = os.path.join(ROOT, 'tests', 'golden')
+    pd = _json.load(open(os.path.join(gold, 'rpn_head_cfg.json')))
+    rd = _json.load(open(os.path.join(gold, 'roi_head_cfg.json')))
+    torch.manual_seed(0)
+    model = registry.build_detector(dict(type='Polyphonic', backbone=StandInBackbone(), neck=None, rpn_head=pd['rpn_head'],
+                                         roi_head=rd['roi_head'], test_cfg=dict(rpn=pd['test_cfg'], rcnn=rd['test_cfg']),
+                                         num_thing_classes=8, num_stuff_classes=11))
+    model.rpn_head.init_weights()
+    model.roi_head.init_weights()
+    model = model.to(dev).eval()
+    B, Hi, Wi = args.batch, args.height, args.width
+    img_host = torch.randn(B, 3, Hi, Wi).pin_memory()
+    metas = [dict(img_shape=(Hi, Wi, 3), ori_shape=(Hi, Wi, 3), pad_shape=(Hi, Wi, 3), scale_factor=1.0, flip=False,
+                  batch_input_shape=(Hi, Wi)) for _ in range(B)]
+
+    def step(parts=None):
+        t0 = time.perf_counter()
+        img = img_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            if parts is None:
+                return model.simple_test(img, metas)
+            x = model.extract_feat(img)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            rpn = model.rpn_head.simple_test_rpn(x, metas)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            out = model.roi_head.simple_test(rpn[1], rpn[0], rpn[2], rpn[3], metas, depth_preds=rpn[7], depth_feats=rpn[5],
+                                             depth_proposal=rpn[6])
+            t3 = time.perf_counter()
+            parts['backbone_fpn_pytorch'] += t1 - t0
+            parts['neck_kernel_head'] += t2 - t1
+            parts['decoder_panoptic_readback'] += t3 - t2
+            return out
+
+    for _ in range(2):
+        out = step()
+    n = 4
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        out = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    parts = dict(backbone_fpn_pytorch=0.0, neck_kernel_head=0.0, decoder_panoptic_readback=0.0)
+    for _ in range(2):
+        step(parts)
+    segs = [len(o[2][1]) for o in out]
+    del model
+    torch.cuda.empty_cache()
+    return dict(value=world * B * n / t.item(), unit='frames/s', ms_per_step=1e3 * t.item() / n, steps=n, batch_per_gpu=B,
+                api='Polyphonic.simple_test(img, img_metas) -> [(None, None, (panoptic, segments_info), depth_basic, depth_final)]',
+                h2d_bytes_per_step=img_host.numel() * 4, d2h_bytes_per_step=B * (Hi * Wi * 12 + 128 * 24 + 4),
+                section_ms_synchronised={k: 1e3 * v / 2 for k, v in parts.items()}, segments_per_frame=segs,
+                backbone='torchvision resnet50 + PyTorch FPN, random init, eager fp32 (stand-in for the reference\'s mmdet ResNet-50 '
+                         '+ FPN, which stay PyTorch by north-star and cannot be imported on this box)')
+
+
 def kernel_head_timing(args, B, dev, peak_gbs, cpu=True):
     """NOT part of the headline metric: the producer of the decoder's inputs, i.e. the
     tail of KernelHead._decode_init_proposals (kernel_head.py:250-336) = pf_kernel_head + pf_mask_pool +
@@ -570,9 +680,43 @@ def kernel_head_timing(args, B, dev, peak_gbs, cpu=True):
                     '%d frames of %dx%d maps; intermediate conv output (fp32, %.0f MB written + read) not counted as '
                     'algorithmic' % (B, H, W, B * 3 * C * HW * 4 / 1e6))
     del sets
+    # the neck in front of it: SemanticFPNWrapper's 3x3 conv + GN + ReLU pyramid
+    # (pf_semantic_fpn, semantic_fpn.py:198-219) + conv_pred / aux_convs (pf_fpn_pred, :221-229) from the four FPN levels
+    from polyphonicformer_b200.kernel_head import FpnPred, SemanticFpnPyramid
+    fsd = synth.synth_semantic_fpn_state(0)
+    pyr, pred = SemanticFpnPyramid(fsd, dev), FpnPred(fsd, dev)
+    levels = [torch.randn(B, C, 2 * H >> i, 2 * W >> i, generator=g).to(dev) for i in range(4)]
+
+    def neck():
+        fused_b, _, hw = pyr.forward(levels)
+        pred.forward(fused_b, hw=hw)
+
+    for _ in range(2):
+        neck()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        neck()
+    b.record()
+    torch.cuda.synchronize()
+    ms_neck = a.elapsed_time(b) / 5
+    flops = B * 2 * 9 * C * C * (4 * HW + 2 * HW // 4 + HW // 16) + B * 3 * 2 * C * C * HW
+    res['semantic_fpn'] = dict(ms_per_call=ms_neck, frames_per_s=B / ms_neck * 1e3, batch=B, launches=pyr.last_launches + pred.last_launches,
+                               algorithmic_GFLOP=flops / 1e9, achieved_TFLOPs=flops / ms_neck / 1e9,
+                               what='pf_semantic_fpn (7 x [3x3 conv + GN32 + ReLU], x2 steps, level sum) + pf_fpn_pred on the four '
+                                    'FPN levels of %d frames (%dx%d .. %dx%d); split-bf16 MMAs issue 3x the algorithmic FLOP'
+                                    % (B, 2 * H, 2 * W, H // 4, W // 4))
+    del levels
     if cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
+        from oracle import semantic_fpn_ref
+        lv1 = synth.synth_fpn_inputs(1, H, W, 0)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            semantic_fpn_ref.semantic_fpn_forward(fsd, lv1)
+            res['semantic_fpn']['cpu_port_ms_per_frame'] = 1e3 * (time.perf_counter() - t0)
         maps = [torch.relu(torch.randn(1, C, H, W, generator=g)) for _ in range(3)]
         with torch.no_grad():
             kernel_head_ref.decode_init_proposals(sd, maps)
@@ -614,7 +758,9 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
     specs = [
         ('binarise', 1, 'hbm', B * N * HW * 4 + B * words * 128 * 4, 0,
          lambda i: _cabi.call('pf_binarise', _ptr(maskR[i]), _ptr(bitsR[i]), B, N, HW, st)),
-        ('mask_pool', STAGES, 'hbm', 2 * B * C * HW * sx + B * words * 128 * 4 + 2 * B * S * N * C * 4,
+        # strict SURVEY 8(d) count: features + mask bits in, pooled [2B, N, C] out; the split-K partials this implementation also
+        # writes (2 * B * S * N * C * 4 bytes) are traffic, not algorithmic bytes
+        ('mask_pool', STAGES, 'hbm', 2 * B * C * HW * sx + B * words * 128 * 4 + 2 * B * N * C * 4,
          2 * 2 * B * N * C * HW,
          lambda i: _cabi.call('pf_mask_pool', _ptr(featsR[i]), _ptr(bitsR[i]), _ptr(partial), _ptr(cntp), B, N, HW, HWp,
                               2, S, st)),

@@ -452,6 +452,123 @@ class _ConvGN(nn.Module):
         self.gn = nn.GroupNorm(num_groups, channels)
 
 
+def _pyramid_supported(fpn):
+    """True iff ``fpn`` is a SemanticFPNWrapper in the configuration pf_semantic_fpn implements (the shipped one,
+    configs/_base_/models/polyphonic_former.py:78-96): levels 0..3 with 1 / 1 / 2 / 3 [3x3 conv 256->256 without bias + GN32
+    + ReLU] modules, the first of level 0 with stride 2, x2 bilinear steps after all but the last conv of levels 2 and 3,
+    sine positional encoding (128 feats, normalised) added to level 3, no coordinate channels, sum fusion."""
+    try:
+        if (fpn.start_level, fpn.end_level, fpn.upsample_times, fpn.cat_coors_level) != (0, 3, 2, 3) or fpn.cat_coors or \
+                fpn.fuse_by_cat or len(fpn.convs_all_levels) != 4:
+            return False
+        pe = fpn.positional_encoding
+        if pe is None or (pe.num_feats, bool(pe.normalize), pe.temperature, getattr(pe, 'offset', 0.0)) != (128, True, 10000, 0.0) \
+                or abs(pe.scale - 2 * math.pi) > 1e-9 or abs(getattr(pe, 'eps', 1e-6) - 1e-6) > 1e-12:
+            return False
+        for lvl, n_convs in enumerate((1, 1, 2, 3)):
+            seq = fpn.convs_all_levels[lvl]
+            names = [n for n, _ in seq.named_children()]
+            want = []
+            for j in range(n_convs):
+                want.append('conv%d' % j)
+                if lvl >= 2 and j < n_convs - 1:
+                    want.append('upsample%d' % j)
+            if names != want:
+                return False
+            for n, m in seq.named_children():
+                if n.startswith('conv'):
+                    conv, gn, act = m.conv, m.gn, getattr(m, 'activate', None)
+                    stride = (2, 2) if lvl == 0 else (1, 1)
+                    if not (tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == stride and tuple(conv.padding) == (1, 1)
+                            and conv.bias is None and conv.in_channels == conv.out_channels == 256 and conv.groups == 1
+                            and tuple(conv.dilation) == (1, 1) and gn.num_groups == 32 and abs(gn.eps - 1e-5) < 1e-12
+                            and isinstance(act, nn.ReLU)):
+                        return False
+                else:
+                    if not (m.scale_factor in (2, 2.0) and m.mode == 'bilinear' and m.align_corners is False):
+                        return False
+        return True
+    except AttributeError:
+        return False
+
+
+class _ConvModule(nn.Module):
+    """Parameters (and attribute names) of an mmcv ``ConvModule`` with GroupNorm and ReLU: conv (no bias), gn, activate."""
+
+    def __init__(self, k, stride, groups):
+        super().__init__()
+        self.conv = nn.Conv2d(256, 256, k, stride=stride, padding=k // 2, bias=False)
+        self.gn = nn.GroupNorm(groups, 256)
+        self.activate = nn.ReLU(inplace=False)
+
+
+class _SinePE:
+    """The attributes of mmdet's SinePositionalEncoding that pf_semantic_fpn bakes in (no parameters)."""
+
+    def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * math.pi, eps=1e-6, offset=0.0, **kwargs):
+        self.num_feats, self.temperature, self.normalize, self.scale, self.eps, self.offset = \
+            num_feats, temperature, normalize, scale, eps, offset
+
+
+class SemanticFPNWrapper(nn.Module):
+    """polyphonic/funcs/semantic_fpn.py:16-235 in the shipped configuration, inference only, under the reference's name,
+    kwargs and state-dict keys; ``forward`` runs pf_semantic_fpn + pf_fpn_pred.  (Inside ``KernelHead`` the bf16 maps go
+    straight on to pf_kernel_head; this ``forward`` returns the reference's list of three fp32 maps.)"""
+
+    def __init__(self, in_channels, feat_channels, out_channels, start_level, end_level, cat_coors=False,
+                 positional_encoding=None, cat_coors_level=3, fuse_by_cat=False, return_list=False, upsample_times=3,
+                 with_pred=True, num_aux_convs=0, act_cfg=dict(type='ReLU', inplace=True), out_act_cfg=dict(type='ReLU'),
+                 conv_cfg=None, norm_cfg=None, **kwargs):
+        super().__init__()
+        groups = (norm_cfg or {}).get('num_groups')
+        if (in_channels, feat_channels, out_channels, start_level, end_level, upsample_times, cat_coors_level, num_aux_convs) != \
+                (256, 256, 256, 0, 3, 2, 3, 2) or cat_coors or fuse_by_cat or not with_pred or conv_cfg is not None or \
+                (norm_cfg or {}).get('type') != 'GN' or groups != 32 or positional_encoding is None or \
+                (act_cfg or {}).get('type') != 'ReLU' or (out_act_cfg or {}).get('type') != 'ReLU':
+            _unsupported('SemanticFPNWrapper other than the shipped configuration (configs/_base_/models/polyphonic_former.py:78-96)')
+        pe = dict(positional_encoding)
+        if pe.pop('type', 'SinePositionalEncoding') != 'SinePositionalEncoding':
+            _unsupported('positional_encoding %r' % (positional_encoding,))
+        self.in_channels, self.feat_channels, self.out_channels = in_channels, feat_channels, out_channels
+        self.start_level, self.end_level, self.upsample_times = start_level, end_level, upsample_times
+        self.cat_coors, self.cat_coors_level, self.fuse_by_cat = cat_coors, cat_coors_level, fuse_by_cat
+        self.return_list, self.with_pred, self.num_aux_convs = return_list, with_pred, num_aux_convs
+        self.positional_encoding = _SinePE(**pe)
+        self.convs_all_levels = nn.ModuleList()
+        for lvl, n_convs in enumerate((1, 1, 2, 3)):
+            seq = nn.Sequential()
+            for j in range(n_convs):
+                seq.add_module('conv%d' % j, _ConvModule(3, 2 if lvl == 0 else 1, groups))
+                if lvl >= 2 and j < n_convs - 1:
+                    seq.add_module('upsample%d' % j, nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False))
+            self.convs_all_levels.append(seq)
+        self.conv_pred = _ConvModule(1, 1, groups)
+        self.aux_convs = nn.ModuleList([_ConvModule(1, 1, groups) for _ in range(num_aux_convs)])
+        if not _pyramid_supported(self):
+            _unsupported('SemanticFPNWrapper: this configuration')
+        self._engines = None
+
+    def init_weights(self):
+        """semantic_fpn.py:180-185."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, 0, 0.01)
+
+    def forward(self, inputs):
+        """semantic_fpn.py:198-235: the four FPN levels -> [conv_pred, aux_convs.0, aux_convs.1] outputs, fp32 [B,256,H,W]."""
+        from .kernel_head import FpnPred, SemanticFpnPyramid
+        dev = inputs[0].device
+        if dev.type != 'cuda':
+            _unsupported('SemanticFPNWrapper on a %s device' % dev.type)
+        key = (tuple((p.data_ptr(), p._version) for p in self.parameters()), str(dev))
+        if self._engines is None or self._engines[0] != key:
+            sd = self.state_dict()
+            self._engines = (key, SemanticFpnPyramid(sd, dev), FpnPred(sd, dev))
+        fused_b, _, hw = self._engines[1].forward(inputs[self.start_level:self.end_level + 1])
+        _, maps32 = self._engines[2].forward(fused_b, want_fp32=True, hw=hw)
+        return [maps32[0], maps32[1], maps32[2]]
+
+
 class KernelHead(nn.Module):
     """The proposal stage (reference: polyphonic/kernel_head.py:16-347, 700-706), inference only.
 
@@ -563,7 +680,24 @@ class KernelHead(nn.Module):
             if not isinstance(feats, (list, tuple)) or len(feats) != 3:
                 _unsupported('a localization_fpn that does not return [loc, semantic, depth] maps')
             return tail.cast_maps(list(feats)), feats[0].shape[-2:]
-        from .kernel_head import FpnPred
+        from .kernel_head import FpnPred, SemanticFpnPyramid
+        params = list(fpn.parameters())
+        key = (tuple((p.data_ptr(), p._version) for p in params), str(img[0].device))
+        if self._fpn_pred is None or self._fpn_pred[0] != key:
+            sd = fpn.state_dict()
+            pred = FpnPred({k: v for k, v in sd.items() if k.startswith('conv_pred.') or k.startswith('aux_convs.')}, img[0].device)
+            pyr = SemanticFpnPyramid(sd, img[0].device) if _pyramid_supported(fpn) else None
+            self._fpn_pred = (key, pred, pyr)
+        _, pred, pyr = self._fpn_pred
+        lv = img[fpn.start_level:fpn.end_level + 1]
+        if pyr is not None and len(lv) == 4 and lv[1].shape[-2] % 4 == 0 and lv[1].shape[-1] % 4 == 0 and \
+                all(tuple(t.shape[-2:]) == (lv[1].shape[-2] * 2 // (1 << i), lv[1].shape[-1] * 2 // (1 << i)) for i, t in enumerate(lv)):
+            # the whole neck on the kernels: pf_semantic_fpn (semantic_fpn.py:198-219) -> pf_fpn_pred (:221-229)
+            fused_b, _, hw = pyr.forward(lv)
+            maps, _ = pred.forward(fused_b, hw=hw)
+            return maps, hw
+        # a pyramid pf_semantic_fpn does not cover (other depths / strides / coordinate channels, ragged sizes): its 3x3
+        # convs stay the module's own PyTorch code, only conv_pred / aux_convs run on the kernels
         levels = []
         for i in range(fpn.start_level, fpn.end_level + 1):
             inp = img[i]
@@ -574,12 +708,7 @@ class KernelHead(nn.Module):
                     inp = torch.cat([inp, fpn.generate_coord(inp)], 1)
             levels.append(fpn.convs_all_levels[i](inp))
         fused = sum(levels)
-        pred_params = [p for m in (fpn.conv_pred, fpn.aux_convs) for p in m.parameters()]
-        key = (tuple((p.data_ptr(), p._version) for p in pred_params), str(fused.device))
-        if self._fpn_pred is None or self._fpn_pred[0] != key:
-            sd = {k: v for k, v in fpn.state_dict().items() if k.startswith('conv_pred.') or k.startswith('aux_convs.')}
-            self._fpn_pred = (key, FpnPred(sd, fused.device))
-        maps, _ = self._fpn_pred[1].forward(fused)
+        maps, _ = pred.forward(fused)
         return maps, fused.shape[-2:]
 
     def _decode_init_proposals(self, img, img_metas, train_tracking=False):

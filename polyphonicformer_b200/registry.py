@@ -121,8 +121,9 @@ def build_head(cfg):
 
 
 def build_neck(cfg):
-    """SemanticFPNWrapper is NOT rebuilt here: it comes from the reference's own NECKS
-    registry when a reference checkout + mmcv are importable, else from this registry if someone registered the type."""
+    """The reference's own NECKS registry when a reference checkout + mmcv are importable (its SemanticFPNWrapper then keeps
+    the parameters and KernelHead runs it on pf_semantic_fpn / pf_fpn_pred all the same), else this package's registry
+    (modules.SemanticFPNWrapper)."""
     if cfg is None or not isinstance(cfg, dict):
         return cfg                       # an already-built module (tests, custom pipelines) or None
     try:
@@ -154,7 +155,7 @@ def register_all(force=True, detectors=False):
     from . import detectors as d
     from . import modules as m
     heads = (m.KernelUpdateHead, m.KernelUpdateIterHead, m.KernelHead, d.QuasiDenseMaskEmbedHeadGTMask)
-    for cls in heads + (d.SingleRoIExtractor, d.Polyphonic, d.PolyphonicVideo):
+    for cls in heads + (d.SingleRoIExtractor, d.Polyphonic, d.PolyphonicVideo, m.SemanticFPNWrapper):
         MODELS.register_module(force=True, module=cls)
     TRANSFORMER_LAYER.register_module(force=True, module=m.KernelUpdator)
     TRACKERS.register_module(force=True, module=d.QuasiDenseEmbedTracker)

@@ -153,3 +153,26 @@ def test_head_weights_struct_and_packing():
     assert float(hw[100:H_ROW_SEG].abs().max()) == 0 and float(hw[H_ROW_DEP + 1:].abs().max()) == 0
     assert torch.equal(pk.head_b[H_ROW_SEG:H_ROW_SEG + 19], sd['conv_seg.bias'])
     assert pk.stuff_kernels.shape == (11, 256)
+
+
+def test_pinned_result_pool_lifetime(monkeypatch):
+    """postprocess._PinnedPool: the buffer behind a result returns to the pool only when the LAST array derived from it is
+    gone; a caller that keeps everything makes the pool stop lending (results then use ordinary pageable memory)."""
+    import gc
+    import numpy as np
+    from polyphonicformer_b200 import postprocess as pp
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)      # no CUDA here: plain memory stands in
+    pool = pp._PinnedPool(max_outstanding=2)
+    (a, ha), (b, hb) = pool.lend(3_000_000), pool.lend(100)
+    assert pool.outstanding == 2 and pool.lend(5) is None
+    arr = ha[:16].view(np.int32).reshape(2, 2)                              # what get_panoptic_batch hands out
+    a[:16] = torch.arange(16, dtype=torch.uint8)
+    assert arr[0, 0] == 0x03020100
+    del a, ha
+    gc.collect()
+    assert pool.outstanding == 2                                            # `arr` still owns the buffer
+    del arr
+    gc.collect()
+    assert pool.outstanding == 1 and len(pool.free[1 << 22]) == 1
+    c = pool.lend(4_000_000)
+    assert c is not None and pool.outstanding == 2 and not pool.free[1 << 22]

@@ -286,3 +286,39 @@ def test_kernel_head_tail_edge_cases(dev):
         assert torch.isfinite(a).all(), k
         # a constant map is the worst case for E[y^2] - mean^2: compare absolutely, at the scale of the outputs
         assert (a - b).abs().max() < 2e-4 * max(1.0, b.abs().max().item()), ('const', k, (a - b).abs().max().item())
+
+
+def test_kernel_head_with_semantic_fpn_on_the_kernels(dev):
+    """`KernelHead.simple_test_rpn` from the four FPN levels: SemanticFPNWrapper (pf_semantic_fpn + pf_fpn_pred) -> tail,
+    against oracle/semantic_fpn_ref.py -> oracle/kernel_head_ref.py with the same bf16 storage points."""
+    import json
+    import polyphonicformer_b200 as pf
+    from oracle import semantic_fpn_ref
+    B, H, W, seed = 2, 16, 24, 0
+    d = json.load(open(os.path.join(GOLDEN, 'rpn_head_cfg.json')))
+    head = pf.KernelHead(**dict(d['rpn_head'], train_cfg=None, test_cfg=d['test_cfg'], return_fp32_feats=True))
+    fsd = synth.synth_semantic_fpn_state(seed)
+    hsd = synth.synth_kernel_head_state(seed)
+    head.load_state_dict({**hsd, **{'localization_fpn.' + k: v for k, v in fsd.items()}}, strict=True)
+    head = head.to(dev).eval()
+    inputs = synth.synth_fpn_inputs(B, H, W, seed)
+    out = head.simple_test_rpn([t.to(dev) for t in inputs], [{}] * B)
+    torch.cuda.synchronize()
+    assert head._fpn_pred[2] is not None                                      # the pyramid engine was used
+    with torch.no_grad():
+        fused = semantic_fpn_ref.fused_levels(fsd, inputs)
+        maps = [synth.bf16_round(m) for m in ref.fpn_pred(fsd, synth.bf16_round(fused))]
+        want = ref.decode_init_proposals(hsd, maps)
+    names = ('proposal_feats', 'x_feats', 'mask_preds', 'cls_scores', 'seg_preds', 'depth_feats', 'depth_proposal', 'depth_pred')
+    got = dict(zip(names, out))
+    for k in ('x_feats', 'depth_feats', 'mask_preds', 'seg_preds', 'depth_pred'):
+        l2, mx = rel_err(got[k].float().cpu(), want[k])
+        # two bf16 storage points sit between the inputs and these maps: a 1e-5 difference ahead of one flips a few
+        # roundings (2^-9 each), so the bound is the storage resolution, not the kernels' 1e-5
+        assert l2 < 1e-3, (k, l2, mx)
+    # ... and a wrapper called on its own returns the reference's three fp32 maps
+    m3 = head.localization_fpn([t.to(dev) for t in inputs])
+    with torch.no_grad():
+        want_maps = ref.fpn_pred(fsd, synth.bf16_round(fused))
+    for a, b in zip(m3, want_maps):
+        assert rel_err(a.cpu(), b)[0] < 3e-4

@@ -108,11 +108,12 @@ def test_kernel_head_builds_from_reference_config():
     """`KernelHead` under the reference's name, with every kwarg of configs/_base_/models/polyphonic_former.py:30-97,
     exposes the reference's state-dict keys and refuses what the kernels do not cover."""
     assert 'KernelHead' in pf.MODELS
+    real = pf.MODELS._modules['SemanticFPNWrapper']
     pf.MODELS.register_module(name='SemanticFPNWrapper', force=True, module=_FakeNeck)
     try:
         head = pf.build_head(rpn_head_cfg())
     finally:
-        pf.MODELS._modules.pop('SemanticFPNWrapper', None)
+        pf.MODELS._modules['SemanticFPNWrapper'] = real
     assert isinstance(head, pf.KernelHead) and head.num_proposals == 100
     assert head.localization_fpn.cfg['num_aux_convs'] == 2
     own = {k: tuple(v.shape) for k, v in head.state_dict().items() if not k.startswith('localization_fpn.')}
@@ -182,6 +183,7 @@ def test_detectors_register_and_build_without_mmdet():
     v = video_cfg()
     rd = json.load(open(ROI_HEAD_JSON))
     pd = json.load(open(RPN_HEAD_JSON))
+    real = pf.MODELS._modules['SemanticFPNWrapper']
     pf.MODELS.register_module(name='SemanticFPNWrapper', force=True, module=_FakeNeck)
     try:
         model = registry.build_detector(dict(
@@ -190,7 +192,7 @@ def test_detectors_register_and_build_without_mmdet():
             test_cfg=dict(rpn=pd['test_cfg'], rcnn=rd['test_cfg']), track_head=v['track_head'], tracker=v['tracker'],
             bbox_roi_extractor=v['bbox_roi_extractor'], track_train_cfg=v['track_train_cfg']))
     finally:
-        pf.MODELS._modules.pop('SemanticFPNWrapper', None)
+        pf.MODELS._modules['SemanticFPNWrapper'] = real
     from polyphonicformer_b200 import detectors as d
     assert isinstance(model, d.PolyphonicVideo) and isinstance(model, d.Polyphonic)
     assert isinstance(model.rpn_head, pf.KernelHead) and isinstance(model.roi_head, pf.KernelUpdateIterHead)
@@ -215,3 +217,25 @@ def test_detectors_register_and_build_without_mmdet():
 def _cabi_error():
     from polyphonicformer_b200 import _cabi
     return _cabi.PFError
+
+
+def test_semantic_fpn_wrapper_builds_from_reference_config():
+    """The local `SemanticFPNWrapper` takes the reference's kwargs (configs/_base_/models/polyphonic_former.py:78-96), has the
+    reference's 30 state-dict tensors and is what `KernelHead` builds when mmdet is not importable."""
+    head = pf.build_head(rpn_head_cfg())
+    from polyphonicformer_b200.modules import SemanticFPNWrapper, _pyramid_supported
+    fpn = head.localization_fpn
+    assert isinstance(fpn, SemanticFPNWrapper) and _pyramid_supported(fpn)
+    got = {k: tuple(v.shape) for k, v in fpn.state_dict().items()}
+    assert got == {k: tuple(v.shape) for k, v in synth.synth_semantic_fpn_state(0).items()} and len(got) == 30
+    res = head.load_state_dict({**synth.synth_kernel_head_state(0),
+                                **{'localization_fpn.' + k: v for k, v in synth.synth_semantic_fpn_state(0).items()}}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    with pytest.raises(NotImplementedError):
+        fpn([torch.zeros(1, 256, 8, 8)] * 4)                                           # CPU tensors: no fallback
+    cfg = dict(rpn_head_cfg()['localization_fpn'])
+    cfg.pop('type')
+    with pytest.raises(NotImplementedError):
+        SemanticFPNWrapper(**dict(cfg, upsample_times=3))
+    with pytest.raises(NotImplementedError):
+        SemanticFPNWrapper(**dict(cfg, cat_coors=True))

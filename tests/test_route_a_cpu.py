@@ -40,6 +40,8 @@ SCRIPT = textwrap.dedent('''
     assert all(isinstance(h, pf.KernelUpdateHead) for h in model.roi_head.mask_head)
     assert all(isinstance(h.kernel_update_conv, pf.KernelUpdator) for h in model.roi_head.mask_head)
     assert type(model.rpn_head.localization_fpn).__module__.startswith('polyphonic.')   # the neck stays the reference's
+    from polyphonicformer_b200.modules import _pyramid_supported
+    assert _pyramid_supported(model.rpn_head.localization_fpn)      # ... and KernelHead runs it on pf_semantic_fpn
     sd = model.state_dict()
     assert list(sd.keys()) == list(ref_sd.keys()), set(sd) ^ set(ref_sd)
     assert all(sd[k].shape == ref_sd[k].shape and sd[k].dtype == ref_sd[k].dtype for k in sd)
