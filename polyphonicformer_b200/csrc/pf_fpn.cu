@@ -50,39 +50,49 @@ template <int PHASES>
 __global__ void __launch_bounds__(256) fpn_pack_kernel(const float* __restrict__ src, int hs, int ws, int R, int add_posenc,
                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     constexpr int S = PHASES == 4 ? 2 : 1;
+    constexpr int SC = 128, CPP = SC / S;              // source columns / padded columns per pass
     const int h = hs / S, w = ws / S, pitch = w + 2;
-    const int y1 = blockIdx.x, b = blockIdx.y, py = blockIdx.z;         // blockIdx.z: row parity (PHASES = 4)
-    const int t = threadIdx.x;
-    constexpr int CPP = 16;                            // padded columns per pass = CPP * S source columns
-    __shared__ float tile[256][CPP * 2 + 1];
+    // blockIdx.z = channel quarter (64 channels) [+ 4 * row parity for PHASES = 4]
+    const int y1 = blockIdx.x, b = blockIdx.y, cq = blockIdx.z & 3, py = blockIdx.z >> 2;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    __shared__ float tile[SC][65];                     // [source column][channel of the quarter]
     const bool ring_row = y1 == 0 || y1 == h + 1;
     const int ysrc = (y1 - 1) * S + py;
     for (int x0 = 0; x0 < pitch; x0 += CPP) {
         __syncthreads();
         if (!ring_row) {
-            // load: warp = channel group, lane = source column
-            const int ncol = CPP * S;
-            for (int i = t; i < 256 * ncol; i += 256) {
-                const int c = i / ncol, j = i - c * ncol;
-                const int xs = (x0 - 1) * S + j;      // source column of padded column x0 (phase 0) ...
-                float v = 0.f;
-                if (xs >= 0 && xs < ws) {
-                    v = __ldg(src + (((size_t)b * 256 + c) * hs + ysrc) * ws + xs);
-                    if (add_posenc) v += sine_posenc(c, ysrc, xs, hs, ws);
+            // load: warp = channel (8 per round), lane = 4 source columns 32 apart: 4 x 128 contiguous bytes per channel row
+            const int xs0 = (x0 - 1) * S + lane;       // source column of padded column x0, phase 0, + lane
+#pragma unroll 2
+            for (int cc = warp; cc < 64; cc += 8) {
+                const int c = cq * 64 + cc;
+                const float* p = src + (((size_t)b * 256 + c) * hs + ysrc) * ws;
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xs = xs0 + 32 * k;
+                    v[k] = (xs >= 0 && xs < ws) ? __ldg(p + xs) : 0.f;
                 }
-                tile[c][j] = v;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int xs = xs0 + 32 * k;
+                    if (add_posenc && xs >= 0 && xs < ws) v[k] += sine_posenc(c, ysrc, xs, hs, ws);
+                    tile[lane + 32 * k][cc] = v[k];
+                }
             }
         }
         __syncthreads();
-#pragma unroll 1
-        for (int px = 0; px < S; ++px) {
+        // store: warp = padded column (x S phases), lane = 2 channels -> 128 contiguous bytes per warp store and plane
+        for (int jj = warp; jj < SC; jj += 8) {
+            const int j = jj / S, px = jj - j * S, x1 = x0 + j;
+            if (x1 >= pitch) continue;
+            const bool ring = ring_row || x1 == 0 || x1 == w + 1;
+            const float a0 = ring ? 0.f : tile[jj][2 * lane], a1 = ring ? 0.f : tile[jj][2 * lane + 1];
+            const float h0 = bf16_round(a0), h1 = bf16_round(a1);
             const size_t plane = (size_t)b * PHASES + (PHASES == 4 ? py * 2 + px : 0);
-            for (int j = 0; j < CPP && x0 + j < pitch; ++j) {
-                const int x1 = x0 + j;
-                const bool ring = ring_row || x1 == 0 || x1 == w + 1;
-                const float v = ring ? 0.f : tile[t][j * S + px];
-                store_split(hi, lo, (plane * R + (size_t)y1 * pitch + x1) * 256 + t, v);
-            }
+            const size_t idx = ((plane * R + (size_t)y1 * pitch + x1) * 256 + cq * 64 + 2 * lane) * 2;      // bytes
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(hi) + idx) = pack_bf16x2(h0, h1);
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(lo) + idx) = pack_bf16x2(a0 - h0, a1 - h1);
         }
     }
 }
@@ -92,14 +102,19 @@ __global__ void __launch_bounds__(256) fpn_gn_finalize_kernel(const float2* __re
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, float2* __restrict__ affine) {
     pdl_wait();
+    __shared__ double s_s[8][32], s_ss[8][32];
     __shared__ float s_mean[32], s_rstd[32];
-    const int b = blockIdx.x, t = threadIdx.x;
+    const int b = blockIdx.x, t = threadIdx.x, g = t & 31, part = t >> 5;
+    double s = 0, ss = 0;
+    for (int i = part; i < tiles_per_img; i += 8) {     // fixed assignment and order: deterministic
+        const float2 v = __ldg(stats + ((size_t)b * tiles_per_img + i) * 32 + g);
+        s += v.x, ss += v.y;
+    }
+    s_s[part][g] = s, s_ss[part][g] = ss;
+    __syncthreads();
     if (t < 32) {
-        double s = 0, ss = 0;
-        for (int i = 0; i < tiles_per_img; ++i) {
-            const float2 v = stats[((size_t)b * tiles_per_img + i) * 32 + t];
-            s += v.x, ss += v.y;
-        }
+        s = ss = 0;
+        for (int k = 0; k < 8; ++k) s += s_s[k][t], ss += s_ss[k][t];
         const double mean = s / count, var = fmax(ss / count - mean * mean, 0.0);
         s_mean[t] = (float)mean, s_rstd[t] = (float)(1.0 / sqrt(var + (double)eps));
     }
@@ -181,16 +196,24 @@ __global__ void __launch_bounds__(256) fpn_sum_kernel(const __grid_constant__ Fp
     float2 af[4];
 #pragma unroll
     for (int l = 0; l < 4; ++l) af[l] = __ldg(a.affine[l] + b * 256 + t);
-    for (int j = 0; j < 32; ++j) {
-        const int p = p0 + j;
-        float v = 0.f;
-        if (p < HW) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < 32; j0 += 8) {
+        float r[8][4];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {               // 32 independent loads in flight per thread
+            const int p = p0 + j0 + jj;
             const int y = p / a.w, x = p - y * a.w;
             const size_t idx = ((size_t)b * a.R + (size_t)(y + 1) * pitch + x + 1) * 256 + t;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) v += fmaxf(fmaf(__ldg(a.raw[l] + idx), af[l].x, af[l].y), 0.f);   // ((l0 + l1) + l2) + l3
+            for (int l = 0; l < 4; ++l) r[jj][l] = p < HW ? __ldg(a.raw[l] + idx) : 0.f;
         }
-        tile[j][t] = v;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            float v = 0.f;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) v += fmaxf(fmaf(r[jj][l], af[l].x, af[l].y), 0.f);   // ((l0 + l1) + l2) + l3
+            tile[j0 + jj][t] = p0 + j0 + jj < HW ? v : 0.f;
+        }
     }
     __syncthreads();
     const int lane = t & 31, warp = t >> 5;
@@ -242,7 +265,7 @@ static int fpn_conv(const pf_fpn_weights* w, int cv, const FpnScratch& sc, int B
     const uint32_t abox[3] = {SG_KC, 128, 1};
     if (int e = make_tmap_bf16_nd(&ah, sc.planes[0], 3, adims, astr, abox)) return e;
     if (int e = make_tmap_bf16_nd(&al, sc.planes[1], 3, adims, astr, abox)) return e;
-    if (int e = make_tmap_bf16_2d(&wm, w->conv_w + (size_t)cv * 2 * 9 * 256 * 256, 2 * 9 * 256, 256, 256, 128, SG_KC)) return e;
+    if (int e = make_tmap_bf16_2d(&wm, w->conv_w + (size_t)cv * 2 * 9 * 256 * 256, 2 * 9 * 256, 256, 256, SC_TN, SG_KC)) return e;
     SgArgs a = {};
     a.mode = SG_CONV, a.n_kb = 9 * 4, a.cin_blocks = 4, a.w_tap_rows = 256, a.w_lo = 9 * 256;
     a.rows_per_img = R, a.planes_per_img = planes;
@@ -257,10 +280,11 @@ static int fpn_conv(const pf_fpn_weights* w, int cv, const FpnScratch& sc, int B
     }
     a.raw = sc.raw[cv], a.stats = sc.stats, a.grid_h = h, a.grid_w = wd;
     const int tiles = R / 128;
-    cudaError_t ce = cudaFuncSetAttribute(sgemm_kernel<SG_EPI_RAWSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM);
+    cudaError_t ce = cudaFuncSetAttribute(sgemm_conv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM);
     if (ce != cudaSuccess) return set_error(PF_ERR_CUDA, "sgemm smem attribute: %s", cudaGetErrorString(ce));
-    if (int e = launch_pdl("sgemm_kernel<RAWSTATS>", sgemm_kernel<SG_EPI_RAWSTATS>, dim3(2, B * tiles, 1), dim3(SG_THREADS), SG_SMEM,
-                           st, ah, al, wm, a))
+    const int n_mtiles = B * tiles;
+    if (int e = launch_pdl("sgemm_conv256_kernel", sgemm_conv256_kernel, dim3(n_mtiles < num_sms() ? n_mtiles : num_sms()),
+                           dim3(SG_THREADS), SC_SMEM, st, ah, al, wm, a, n_mtiles))
         return e;
     return launch_pdl("fpn_gn_finalize_kernel", fpn_gn_finalize_kernel, dim3(B), dim3(256), 0, st, (const float2*)sc.stats, tiles,
                       h * wd * 8, w->gn_gamma + cv * 256, w->gn_beta + cv * 256, w->gn_eps, sc.affine[cv]);
@@ -294,10 +318,10 @@ extern "C" int pf_semantic_fpn(const pf_fpn_weights* w, const float* p0, const f
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4;
     auto pack1 = [&](const float* src, int h, int wd, int posenc) {
-        fpn_pack_kernel<1><<<dim3(h + 2, B, 1), 256, 0, st>>>(src, h, wd, fpn_rows(h, wd), posenc, sc.planes[0], sc.planes[1]);
+        fpn_pack_kernel<1><<<dim3(h + 2, B, 4), 256, 0, st>>>(src, h, wd, fpn_rows(h, wd), posenc, sc.planes[0], sc.planes[1]);
     };
     // level 0: one stride-2 convolution on the four parity phases (semantic_fpn.py:92-104)
-    fpn_pack_kernel<4><<<dim3(H + 2, B, 2), 256, 0, st>>>(p0, 2 * H, 2 * W, fpn_rows(H, W), 0, sc.planes[0], sc.planes[1]);
+    fpn_pack_kernel<4><<<dim3(H + 2, B, 8), 256, 0, st>>>(p0, 2 * H, 2 * W, fpn_rows(H, W), 0, sc.planes[0], sc.planes[1]);
     PF_CHECK_LAUNCH("fpn_pack_kernel<4>");
     if (int e = fpn_conv(w, CV_L0, sc, B, H, W, true, st)) return e;
     // level 1
