@@ -396,7 +396,7 @@ def run_ours(args, rank, world, local_rank):
                     alg_bytes_per_launch=dom['alg_bytes'], ms_per_launch=dom['ms'],
                     timing=dom['timing'] + '; CUDA events on the launching stream',
                     ms_single_launch_l2_flushed=dom['ms_single_launch_l2_flushed'],
-                    traffic_source='profiles/r1_traffic.json (ncu --set full, dram__bytes_read.sum + '
+                    traffic_source='profiles/r2_traffic.json (ncu --set full, dram__bytes_read.sum + '
                                    'dram__bytes_write.sum per launch)' if dom['traffic'] else None)
     line = dict(metric=METRIC, value=value,
                 unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
@@ -818,7 +818,7 @@ def kernel_breakdown(args, eng, lib, feats, mask, prop, dprop, buf, B, N, H, W, 
                 'mask_einsum (fp32 logits, both branches)': ('einsum_kernel<1>', 2),   # the step launches it per branch
                 'upsample2x': ('upsample2x_kernel', 2)}     # the step launches it once per branch
     traffic = {}
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.exists(tpath) and (B, H, W) == (4, 128, 256):
         traffic = json.load(open(tpath))['kernels']
     for k in out:

@@ -130,7 +130,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
             // inside the decode loop the feature tiles are long-complete inputs: fill the ring before the grid
             // dependency resolves
             if (!p.early_feats) pdl_wait();
-            const uint64_t fhint = unit < p.B ? kEvictLast : kEvictFirst;   // x_feats stays L2-resident across kernels
+            // inside the decode loop x_feats stays L2-resident across kernels; a stand-alone call streams
+            const uint64_t fhint = (p.early_feats && unit < p.B) ? kEvictLast : kEvictFirst;
             for (int i = 0; i < ntiles; ++i) {
                 const int s = i % STAGES;
                 if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);

@@ -95,10 +95,11 @@ pool_kernel(const __grid_constant__ CUtensorMap tmap_feats, const PoolParams p) 
                 if (i == 4) DBG(2);
                 if (i == ntiles - 1) DBG(3);
                 mbar_arrive_expect_tx(&fullB[s], P_B_BYTES);
-                // x_feats (branch 0) is read by every kernel of every stage: keep it in the 126 MB L2 (evict-last);
-                // depth_feats is only read here (and by the last einsum): stream it (evict-first)
+                // Inside the decode loop x_feats (branch 0) is read by every kernel of every stage: keep it in the 126 MB L2
+                // (evict-last); depth_feats is only read here (and by the last einsum): stream it (evict-first).  A
+                // stand-alone call (pf_mask_pool) cannot assume a reader right behind it: pure streaming.
                 tma_load_2d(smem + s * P_STAGE_BYTES + P_A_BYTES, &tmap_feats, &fullB[s], (tile_begin + i) * P_BHW,
-                            ((unit / p.B) * p.Btot + p.b0 + b) * P_C, unit < p.B ? kEvictLast : kEvictFirst);
+                            ((unit / p.B) * p.Btot + p.b0 + b) * P_C, (p.early_feats && unit < p.B) ? kEvictLast : kEvictFirst);
             }
         }
     } else if (warp == 1) {

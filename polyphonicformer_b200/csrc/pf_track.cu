@@ -230,14 +230,24 @@ __global__ void __launch_bounds__(256) fc_tail_kernel(const float* __restrict__ 
     __shared__ float s_h[TR_FC1];
     const int k = blockIdx.x, t = threadIdx.x;
     for (int j = t; j < TR_FC1; j += 256) {
+        float pv[TR_SPLITS];
+#pragma unroll
+        for (int s = 0; s < TR_SPLITS; ++s) pv[s] = part[((size_t)s * part_rows + k) * TR_FC1 + j];
         float v = __ldg(b1 + j);
-        for (int s = 0; s < TR_SPLITS; ++s) v += part[((size_t)s * part_rows + k) * TR_FC1 + j];
+#pragma unroll
+        for (int s = 0; s < TR_SPLITS; ++s) v += pv[s];
         s_h[j] = fmaxf(v, 0.f);
     }
     __syncthreads();
-    float acc = __ldg(b2 + t);
-    for (int j = 0; j < TR_FC1; ++j) acc = fmaf(s_h[j], __ldg(w2t + (size_t)j * EMB + t), acc);
-    embeds[(size_t)k * EMB + t] = acc;
+    // 8 independent partial sums (fixed order: deterministic) keep 8 loads of the L2-resident W2^T in flight per thread
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = 0; j < TR_FC1; j += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(s_h[j + i], __ldg(w2t + (size_t)(j + i) * EMB + t), acc[i]);
+    }
+    embeds[(size_t)k * EMB + t] = __ldg(b2 + t) + (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])));
 }
 
 // ------------------------------------------------------------------------------------------------ association
@@ -259,6 +269,7 @@ __device__ __forceinline__ float box_iou(const float* a, const float* b) {
 }
 
 constexpr int TM_THREADS = 512;
+constexpr int TM_SC_CAP = 32768;      // floats of dynamic shared memory for the score matrix (128 KB)
 
 __global__ void __launch_bounds__(TM_THREADS) tracker_match_kernel(const pf_tracker_config cfg, TrackerState* __restrict__ st,
                                                                    const float* __restrict__ bboxes,
@@ -273,9 +284,9 @@ __global__ void __launch_bounds__(TM_THREADS) tracker_match_kernel(const pf_trac
     __shared__ const float* s_mptr[MAXM];
     __shared__ float s_cmax[MAXM], s_csum[MAXM];
     __shared__ int s_tmatch[MAXT], s_tdst[MAXT];
-    __shared__ float s_red_v[TM_THREADS / 32];
-    __shared__ int s_red_i[TM_THREADS / 32];
-    __shared__ int s_nk, s_M, s_zero_col, s_ntracks_new, s_nback;
+    __shared__ int s_nk, s_M, s_ntracks_new, s_nback;
+    __shared__ uint8_t s_taken[MAXM];
+    extern __shared__ float s_sc[];      // TM_SC_CAP floats: the score matrix when it fits (it does unless K * memo > 32 k)
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int cur = st->cur, n_tracks = st->n_tracks;
 
@@ -311,6 +322,9 @@ __global__ void __launch_bounds__(TM_THREADS) tracker_match_kernel(const pf_trac
     }
     __syncthreads();
     const int nk = s_nk, M = s_M;
+    float* sc = (nk * M <= TM_SC_CAP) ? s_sc : scores;      // row pitch M in shared memory, MAXM in the global workspace
+    const int ld = (nk * M <= TM_SC_CAP) ? M : MAXM;
+    for (int m = t; m < M; m += TM_THREADS) s_taken[m] = 0;
     if (t < nk) {
         const int o = s_kidx[t];
         s_kscore[t] = s_score[o], s_klabel[t] = labels[o], s_ids[t] = -1, s_kfound[t] = 0;
@@ -339,63 +353,58 @@ __global__ void __launch_bounds__(TM_THREADS) tracker_match_kernel(const pf_trac
                 const float4 u = e[c], v = q[c];
                 acc = fmaf(u.x, v.x, acc), acc = fmaf(u.y, v.y, acc), acc = fmaf(u.z, v.z, acc), acc = fmaf(u.w, v.w, acc);
             }
-            scores[(size_t)i * MAXM + m] = acc;
+            sc[(size_t)i * ld + m] = acc;
         }
         __syncthreads();
         for (int i = warp; i < nk; i += TM_THREADS / 32) {          // softmax over the memo (dim = 1)
             float mx = -INFINITY;
-            for (int m = lane; m < M; m += 32) mx = fmaxf(mx, scores[(size_t)i * MAXM + m]);
+            for (int m = lane; m < M; m += 32) mx = fmaxf(mx, sc[(size_t)i * ld + m]);
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float sum = 0.f;
-            for (int m = lane; m < M; m += 32) sum += expf(scores[(size_t)i * MAXM + m] - mx);
+            for (int m = lane; m < M; m += 32) sum += expf(sc[(size_t)i * ld + m] - mx);
             sum = sg_warp_sum(sum);
             if (lane == 0) s_rmax[i] = mx, s_rsum[i] = sum;
         }
         for (int m = t; m < M; m += TM_THREADS) {                   // softmax over the detections (dim = 0)
             float mx = -INFINITY;
-            for (int i = 0; i < nk; ++i) mx = fmaxf(mx, scores[(size_t)i * MAXM + m]);
+            for (int i = 0; i < nk; ++i) mx = fmaxf(mx, sc[(size_t)i * ld + m]);
             float sum = 0.f;
-            for (int i = 0; i < nk; ++i) sum += expf(scores[(size_t)i * MAXM + m] - mx);
+            for (int i = 0; i < nk; ++i) sum += expf(sc[(size_t)i * ld + m] - mx);
             s_cmax[m] = mx, s_csum[m] = sum;
         }
         __syncthreads();
         for (int idx = t; idx < nk * M; idx += TM_THREADS) {
             const int i = idx / M, m = idx - i * M;
-            const float v = scores[(size_t)i * MAXM + m];
-            float sc = (expf(v - s_rmax[i]) / s_rsum[i] + expf(v - s_cmax[m]) / s_csum[m]) / 2.f;
-            if (cfg.with_cats && s_klabel[i] != s_mlabel[m]) sc = 0.f;          // :185-187
-            scores[(size_t)i * MAXM + m] = sc;
+            const float v = sc[(size_t)i * ld + m];
+            float bs = (expf(v - s_rmax[i]) / s_rsum[i] + expf(v - s_cmax[m]) / s_csum[m]) / 2.f;
+            if (cfg.with_cats && s_klabel[i] != s_mlabel[m]) bs = 0.f;          // :185-187
+            sc[(size_t)i * ld + m] = bs;
         }
         __syncthreads();
-        // ---- :189-201 greedy assignment in score order
-        for (int i = 0; i < nk; ++i) {
-            float bv = -INFINITY;
-            int bi = 0x7fffffff;
-            for (int m = t; m < M; m += TM_THREADS) {
-                const float v = scores[(size_t)i * MAXM + m];
-                if (v > bv) bv = v, bi = m;
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
-            }
-            if (lane == 0) s_red_v[warp] = bv, s_red_i[warp] = bi;
-            __syncthreads();
-            if (t == 0) {
-                for (int w = 1; w < TM_THREADS / 32; ++w)
-                    if (s_red_v[w] > bv || (s_red_v[w] == bv && s_red_i[w] < bi)) bv = s_red_v[w], bi = s_red_i[w];
-                s_zero_col = -1;
-                if (bv > cfg.match_score_thr && s_mid[bi] > -1) {
-                    if (s_kscore[i] > cfg.obj_score_thr) s_ids[i] = s_mid[bi], s_zero_col = bi;
+        // ---- :189-201 greedy assignment in score order: sequential over the detections, so ONE warp runs it without block
+        // barriers.  Zeroing column j in every other row (:196-197) = marking the memo entry taken: rows before i are done,
+        // rows after i see 0 there.
+        if (warp == 0) {
+            for (int i = 0; i < nk; ++i) {
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int m = lane; m < M; m += 32) {
+                    const float v = s_taken[m] ? 0.f : sc[(size_t)i * ld + m];
+                    if (v > bv) bv = v, bi = m;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;     // torch.max: the first maximum
+                }
+                if (lane == 0 && bv > cfg.match_score_thr && s_mid[bi] > -1) {
+                    if (s_kscore[i] > cfg.obj_score_thr) s_ids[i] = s_mid[bi], s_taken[bi] = 1;
                     else if (bv > cfg.nms_conf_thr) s_ids[i] = -2;
                 }
+                __syncwarp();
             }
-            __syncthreads();
-            const int zc = s_zero_col;
-            if (zc >= 0 && t < nk && t != i) scores[(size_t)t * MAXM + zc] = 0.f;
-            __syncthreads();
         }
+        __syncthreads();
     }
     // ---- :202-208 new tracklets
     if (t == 0) {
@@ -683,7 +692,9 @@ extern "C" int pf_tracker_match(const pf_tracker_config* cfg, void* state, const
                "pf_tracker_match: memo_backdrop_frames=%d (0..%d)", cfg->memo_backdrop_frames, MAXBF);
     PF_REQUIRE(workspace_bytes >= pf_tracker_workspace_bytes(), PF_ERR_WORKSPACE, "pf_tracker_match: workspace %zu < %zu",
                workspace_bytes, pf_tracker_workspace_bytes());
-    tracker_match_kernel<<<1, TM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, static_cast<TrackerState*>(state), bboxes,
+    cudaError_t ea = cudaFuncSetAttribute(tracker_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SC_CAP * 4);
+    if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "tracker smem attribute: %s", cudaGetErrorString(ea));
+    tracker_match_kernel<<<1, TM_THREADS, TM_SC_CAP * 4, static_cast<cudaStream_t>(stream)>>>(*cfg, static_cast<TrackerState*>(state), bboxes,
                                                                                   labels, embeds, K, frame_id, order, ids, n_kept,
                                                                                   status_out, static_cast<float*>(workspace));
     PF_CHECK_LAUNCH("tracker_match_kernel");

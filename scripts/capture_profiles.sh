@@ -39,7 +39,7 @@ capx() {  # name, kernel regex, skip, count, driver args
     rm -f $OUT/${TAG}_$1.ncu-rep
     tail -1 $OUT/${TAG}_$1.log
 }
-capx ncu_full_neck "sgemm_kernel|fpn_" 50 25 neck
-capx ncu_full_track "sgemm_kernel|roi_align|box_|fc_tail|tracker_match" 18 9 track
+capx ncu_full_neck "sgemm_conv256|fpn_" 44 22 neck
+capx ncu_full_track "sgemm_kernel|roi_align|box_|fc_tail|tracker_match" 20 10 track
 capx ncu_full_panoptic "pp_" 8 4 panoptic
 ls -la $OUT
