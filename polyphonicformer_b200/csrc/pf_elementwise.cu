@@ -28,7 +28,7 @@ __global__ void cast_feats_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// mask logits fp32 [B][N][HW] -> bits u32 [B][WORDS][128]: one block per (b, group of 8 words); warp w ballots the
+// mask logits fp32 [B][N][HW] -> bits u32 [B][WORDS][128]: one block per (b, group of BIN_WORDS words); warp w ballots the
 // 32 pixels of a word for rows n = w, w+8, ...  (kernel_update_head.py:236-238: sigmoid(x) > 0.5  <=>  x > 0)
 constexpr int BIN_WORDS = 4;
 constexpr int BIN_WARPS = 16;

@@ -211,21 +211,30 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
     }
     __syncthreads();
     const int nlist = s_nlist;
-    const int tx = tid & (PP_TX - 1), ty0 = tid / PP_TX;   // 4 pixels per thread: rows ty0 + 4 j
+    // 4 vertically ADJACENT pixels per thread (rows 4 ty0 .. 4 ty0 + 3 of the tile): with a x4 up-sampling they sample at
+    // most THREE source rows (Y0 is a multiple of 4), so a mask costs 6 shared-memory loads and 3 horizontal + 4 vertical
+    // interpolations per thread instead of 16 loads and 4 x 3.  The arithmetic per pixel is unchanged:
+    // l0y * (l0x a + l1x b) + l1y * (l0x c + l1x d), ATen's order.
+    const int tx = tid & (PP_TX - 1), ty0 = tid / PP_TX;
     const int X = X0 + tx;
     const Tap cx = make_tap(X, w);
     const int ox0 = cx.i0 - px0, ox1 = cx.i1 - px0;
-    int o00[4], o10[4];
+    int r0[4], r1[4];          // source row of each pixel's two taps, relative to the first one (0..2)
     float ly0[4], ly1[4];
     bool inside[4];
+    int rbase = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int Y = Y0 + ty0 + 4 * j;
+        const int Y = Y0 + 4 * ty0 + j;
         const Tap cy = make_tap(Y, h);
-        o00[j] = (cy.i0 - py0) * PP_PC, o10[j] = (cy.i1 - py0) * PP_PC;
+        if (j == 0) rbase = cy.i0;
+        r0[j] = cy.i0 - rbase, r1[j] = cy.i1 - rbase;
         ly0[j] = cy.l0, ly1[j] = cy.l1;
         inside[j] = Y < H0 && X < W0;
     }
+    // rows beyond the map (bottom border) are never selected (r <= i1 <= h - 1); clamp the LOAD to the patch all the same
+    const int orow0 = (rbase - py0) * PP_PC;
+    const int orow1 = min(rbase + 1 - py0, PP_PR - 1) * PP_PC, orow2 = min(rbase + 2 - py0, PP_PR - 1) * PP_PC;
     float best[4] = {-1.f, -1.f, -1.f, -1.f};
     int best_e[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, best_n[4] = {0, 0, 0, 0};
     for (int li = 0; li < nlist; ++li) {
@@ -233,11 +242,16 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
         const float* sp = s_sig + n * PATCH;
         const float sc = s_score[n];
         const int e = s_entry[n];
+        float hr[3];
+        hr[0] = cx.l0 * sp[orow0 + ox0] + cx.l1 * sp[orow0 + ox1];
+        hr[1] = cx.l0 * sp[orow1 + ox0] + cx.l1 * sp[orow1 + ox1];
+        hr[2] = cx.l0 * sp[orow2 + ox0] + cx.l1 * sp[orow2 + ox1];
         int cnt = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float a = sp[o00[j] + ox0], b = sp[o00[j] + ox1], c = sp[o10[j] + ox0], d = sp[o10[j] + ox1];
-            const float m = ly0[j] * (cx.l0 * a + cx.l1 * b) + ly1[j] * (cx.l0 * c + cx.l1 * d);
+            const float ha = r0[j] == 0 ? hr[0] : (r0[j] == 1 ? hr[1] : hr[2]);
+            const float hb = r1[j] == 0 ? hr[0] : (r1[j] == 1 ? hr[1] : hr[2]);
+            const float m = ly0[j] * ha + ly1[j] * hb;
             cnt += __popc(__ballot_sync(0xffffffffu, inside[j] && m >= 0.5f));
             const float prob = sc * m;
             if (e >= 0 && (prob > best[j] || (prob == best[j] && e < best_e[j]))) best[j] = prob, best_e[j] = e, best_n[j] = n;
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(PP_THREADS) pp_argmax_kernel(const float* __re
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int Y = Y0 + ty0 + 4 * j;
+        const int Y = Y0 + 4 * ty0 + j;
         if (inside[j]) {
             ids[(size_t)Y * W0 + X] = (uint8_t)best_n[j];
             atomicAdd(&s_area[best_n[j]], 1);
