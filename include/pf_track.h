@@ -92,7 +92,7 @@ size_t pf_tracker_workspace_bytes(void);
 /* empties the memo (QuasiDenseEmbedTracker.__init__ / PolyphonicVideo.init_tracker) */
 int pf_tracker_reset(void* state, void* stream);
 /* One frame of QuasiDenseEmbedTracker.match (bisoftmax metric).  bboxes [K][5] (x1, y1, x2, y2, score), labels int32 [K],
- * embeds [K][256].  Outputs: n_kept[0] = detections that survive the duplicate removal; for i < n_kept: order[i] = index
+ * embeds [K][256] (16-byte aligned).  Outputs: n_kept[0] = detections that survive the duplicate removal; for i < n_kept: order[i] = index
  * of kept detection i in the inputs (descending score), ids[i] = its track id (>= 0), -1 (backdrop) or -2 (duplicate of
  * a confident track).  status_out[0] != 0 if the memo overflowed PF_TRACK_MAX_TRACKS (new tracks were dropped). */
 int pf_tracker_match(const pf_tracker_config* cfg, void* state, const float* bboxes, const int32_t* labels,

@@ -688,6 +688,7 @@ extern "C" int pf_tracker_match(const pf_tracker_config* cfg, void* state, const
     if (int e = check_device()) return e;
     PF_REQUIRE(cfg && state && order && ids && n_kept && workspace, PF_ERR_ARG, "pf_tracker_match: null pointer");
     PF_REQUIRE(K >= 0 && K <= MAXK && (K == 0 || (bboxes && labels && embeds)), PF_ERR_ARG, "pf_tracker_match: K=%d", K);
+    PF_REQUIRE(K == 0 || (reinterpret_cast<uintptr_t>(embeds) & 15) == 0, PF_ERR_ALIGN, "pf_tracker_match: embeds not 16-byte aligned");
     PF_REQUIRE(cfg->memo_backdrop_frames >= 0 && cfg->memo_backdrop_frames <= MAXBF && cfg->memo_tracklet_frames >= 0, PF_ERR_ARG,
                "pf_tracker_match: memo_backdrop_frames=%d (0..%d)", cfg->memo_backdrop_frames, MAXBF);
     PF_REQUIRE(workspace_bytes >= pf_tracker_workspace_bytes(), PF_ERR_WORKSPACE, "pf_tracker_match: workspace %zu < %zu",

@@ -165,6 +165,8 @@ class DeviceTracker:
         b = bboxes.to(self.device, torch.float32).contiguous()
         l = labels.to(self.device, torch.int32).contiguous()
         e = track_feats.to(self.device, torch.float32).contiguous()
+        if e.data_ptr() % 16:          # a one-row view of a larger buffer counts as contiguous whatever its offset
+            e = e.clone()
         o = self.out
         _cabi.call('pf_tracker_match', ctypes.byref(self.cfg), _ptr(self.state), _ptr(b), _ptr(l), _ptr(e), K, int(frame_id),
                    _ptr(o), _ptr(o[MAX_K:]), _ptr(o[2 * MAX_K:]), _ptr(o[2 * MAX_K + 1:]), _ptr(self.ws), self.ws_bytes,

@@ -136,6 +136,10 @@ def test_shard_runner_single_rank_matches_restatement(dev):
                               NUM_STUFF, clip_len=4)
     frames = clip_frames(seed=0) + clip_frames(seed=1)
     frames.append(dict(frames[0], info=[s for s in frames[0]['info'] if not s['isthing']]))     # a 9th frame without things
+    # ... and frames with exactly ONE thing: a one-row record is a "contiguous" view at an unaligned offset of the gathered
+    # buffer (this crashed the 8-rank bench once)
+    one = [s for s in frames[1]['info'] if s['isthing']][:1] + [s for s in frames[1]['info'] if not s['isthing']]
+    frames += [dict(frames[1], info=one), dict(frames[2], info=one), dict(frames[3], info=one)]
     tcfg = {k: v for k, v in cfg['tracker'].items() if k not in ('type', 'with_cats', 'match_metric')}
     ref = None
     want = []
@@ -151,7 +155,7 @@ def test_shard_runner_single_rank_matches_restatement(dev):
             for s in fr['info']:
                 sem[(fr['panoptic'] == s['id']).numpy()] = s['category_id']
             want.append(([], np.zeros(fr['panoptic'].shape), sem))
-    for wave in range(3):
+    for wave in range(4):
         gids = runner.global_ids(wave, 3)
         assert gids == [3 * wave, 3 * wave + 1, 3 * wave + 2]
         local = [frames[g] for g in gids]
