@@ -15,9 +15,14 @@
 // kernel merges them in fp64 into one (scale, shift) per channel, and normalisation + ReLU happen inside the kernel that
 // consumes the map: the x2 up-sampler that writes the next convolution's planes, or the final four-level sum.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pf_internal.h"
 #include "pf_sgemm.cuh"
+
+#ifndef PF_CONV_CLUSTER_DEFAULT
+#define PF_CONV_CLUSTER_DEFAULT 0
+#endif
 #include "pf_sm100.cuh"
 
 namespace pf {
@@ -257,6 +262,52 @@ static FpnScratch carve_fpn(void* base, int B, int H, int W) {
     return s;
 }
 
+// weight-multicast cluster size of the convolution kernel: 0 = plain persistent kernel; PF_CONV_CLUSTER overrides
+static int conv_cluster() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PF_CONV_CLUSTER");
+        v = e ? atoi(e) : PF_CONV_CLUSTER_DEFAULT;
+        if (v != 2 && v != 4) v = 0;
+    }
+    return v;
+}
+
+template <int CL>
+static int launch_conv_mc(const CUtensorMap& ah, const CUtensorMap& al, const uint16_t* wbase, const SgArgs& a, int n_mtiles,
+                          cudaStream_t st) {
+    CUtensorMap ws;
+    if (int e = make_tmap_bf16_2d(&ws, wbase, 2 * 9 * 256, 256, 256, SC_TN / CL, SG_KC)) return e;
+    auto kern = sgemm_conv256_mc_kernel<CL>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM);
+    if (ce != cudaSuccess) return set_error(PF_ERR_CUDA, "sgemm smem attribute: %s", cudaGetErrorString(ce));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.blockDim = dim3(SG_THREADS), cfg.dynamicSmemBytes = SC_SMEM, cfg.stream = st, cfg.attrs = attr, cfg.numAttrs = 2;
+    cfg.gridDim = dim3(CL);
+    static int max_clusters[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && max_clusters[dev] == 0) {
+        int n = 0;
+        cfg.gridDim = dim3(num_sms() / CL * CL);
+        ce = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (ce != cudaSuccess || n <= 0) return set_error(PF_ERR_CUDA, "cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(ce));
+        max_clusters[dev] = n;
+    }
+    int n_clusters = (n_mtiles + CL - 1) / CL;
+    if (dev >= 0 && dev < 64 && n_clusters > max_clusters[dev]) n_clusters = max_clusters[dev];
+    cfg.gridDim = dim3(n_clusters * CL);
+    ce = cudaLaunchKernelEx(&cfg, kern, ah, al, ws, a, n_mtiles);
+    if (ce != cudaSuccess) return set_error(PF_ERR_CUDA, "sgemm_conv256_mc_kernel launch: %s", cudaGetErrorString(ce));
+    count_launch();
+    return PF_OK;
+}
+
 // one [3x3 conv + GN statistics] over planes of grid (h, w): raw fp32 + (scale, shift)
 static int fpn_conv(const pf_fpn_weights* w, int cv, const FpnScratch& sc, int B, int h, int wd, bool stride2, cudaStream_t st) {
     const int R = fpn_rows(h, wd), pitch = wd + 2, planes = stride2 ? 4 : 1;
@@ -283,8 +334,14 @@ static int fpn_conv(const pf_fpn_weights* w, int cv, const FpnScratch& sc, int B
     cudaError_t ce = cudaFuncSetAttribute(sgemm_conv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM);
     if (ce != cudaSuccess) return set_error(PF_ERR_CUDA, "sgemm smem attribute: %s", cudaGetErrorString(ce));
     const int n_mtiles = B * tiles;
-    if (int e = launch_pdl("sgemm_conv256_kernel", sgemm_conv256_kernel, dim3(n_mtiles < num_sms() ? n_mtiles : num_sms()),
-                           dim3(SG_THREADS), SC_SMEM, st, ah, al, wm, a, n_mtiles))
+    const uint16_t* wbase = w->conv_w + (size_t)cv * 2 * 9 * 256 * 256;
+    const int cl = n_mtiles >= 16 ? conv_cluster() : 0;
+    if (cl == 4) {
+        if (int e = launch_conv_mc<4>(ah, al, wbase, a, n_mtiles, st)) return e;
+    } else if (cl == 2) {
+        if (int e = launch_conv_mc<2>(ah, al, wbase, a, n_mtiles, st)) return e;
+    } else if (int e = launch_pdl("sgemm_conv256_kernel", sgemm_conv256_kernel, dim3(n_mtiles < num_sms() ? n_mtiles : num_sms()),
+                                  dim3(SG_THREADS), SC_SMEM, st, ah, al, wm, a, n_mtiles))
         return e;
     return launch_pdl("fpn_gn_finalize_kernel", fpn_gn_finalize_kernel, dim3(B), dim3(256), 0, st, (const float2*)sc.stats, tiles,
                       h * wd * 8, w->gn_gamma + cv * 256, w->gn_beta + cv * 256, w->gn_eps, sc.affine[cv]);

@@ -278,8 +278,12 @@ sgemm_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_constant_
 // The same shifted-row convolution for image-sized problems (SemanticFPN): PERSISTENT CTAs over [128 rows][256 cols] tiles
 // (all output channels of 128 padded positions), two accumulators in tensor memory (2 x 256 columns) so that the epilogue
 // of tile i -- 128 KB of raw fp32 rows + the GroupNorm partial statistics -- runs under the main loop of tile i + 1.
-// Why N = 256: an SM takes in ~64 bytes per clock from L2 through TMA, and a [128][128] tile needs 64 KB of operands per
-// 768 clocks of MMA issue (85 B/clk): ingest-bound.  [128][256] needs 96 KB per 1536 clocks (62 B/clk): balanced.
+// What bounds it (measured: 0.34 ms per 128x256-map convolution at B = 4, ~2240 clocks per k-block against 1536 of MMA
+// issue): SHARED-MEMORY bandwidth.  The 3-MMA split reads every operand tile up to twice (Ah and Wh), 36 KB per K = 16 step,
+// and TMA writes 96 KB per k-block: ~240 KB through a 128 B/clk port per 1536 clocks of tensor work.  A [128][128] tile is
+// worse (same operand bytes for half the math), and cutting the L2 -> SM traffic does not help: the clustered variant below
+// (weight tiles TMA-multicast across 2 or 4 CTAs) runs at exactly the same speed.  The next step would be cta_group::2
+// MMAs (each SM of a pair supplies half of the B operand), not more L2 tricks.
 constexpr int SC_TN = 256, SC_NSTG = 2;
 constexpr int SC_APLANE = 128 * SG_KC * 2, SC_WPLANE = SC_TN * SG_KC * 2;
 constexpr int SC_STAGE = 2 * SC_APLANE + 2 * SC_WPLANE;          // 96 KB
@@ -419,5 +423,162 @@ sgemm_conv256_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_c
     __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
+
+// The clustered variant (opt-in: PF_CONV_CLUSTER=2|4; parity-tested, NOT faster, see above): CL consecutive tiles form a
+// thread-block cluster; the weight tile of a k-block is the same for
+// every tile, so each CTA fetches 1 / CL of it and TMA-multicasts the slice into all CL shared memories (L2 -> SM operand
+// traffic per tile and k-block: 32 KB of activations + 64 / CL KB of weights instead of 96 KB).  A ring stage is refilled
+// only after ALL CTAs of the cluster have consumed it: the MMA warp's commit arrives on the `empty` barrier of every peer.
+template <int CL>
+static __global__ void __launch_bounds__(SG_THREADS, 1)
+sgemm_conv256_mc_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_constant__ CUtensorMap tmap_al,
+                        const __grid_constant__ CUtensorMap tmap_ws, const __grid_constant__ SgArgs a, int n_mtiles) {
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    constexpr int WSLICE = SC_WPLANE / CL;          // bytes of this CTA's slice of one weight plane (256 / CL rows)
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int n_clusters = gridDim.x / CL, cid = blockIdx.x / CL;
+    const int rounds = (n_mtiles + n_clusters * CL - 1) / (n_clusters * CL);
+    extern __shared__ uint8_t sg_smem_raw[];
+    uint8_t* smem = sg_smem_raw + ((1024u - (smem_u32(sg_smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SC_BAR_OFF);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + SC_NSTG;
+    uint64_t* accfull = bars + 2 * SC_NSTG;
+    uint64_t* accempty = bars + 2 * SC_NSTG + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SC_NSTG + 4);
+    float* s_stat = reinterpret_cast<float*>(smem + SC_STAT_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_ah);
+        tma_prefetch_desc(&tmap_al);
+        tma_prefetch_desc(&tmap_ws);
+        for (int i = 0; i < SC_NSTG; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], CL);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&accfull[i], 1);
+            mbar_init(&accempty[i], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
+    // every CTA's barriers are initialised before a peer may multicast into it / arrive on it
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        int g = 0;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int tile = (rd * n_clusters + cid) * CL + (int)crank;   // tiles past the end: all-zero operands (out of range)
+            const int m0 = tile * 128, img = m0 / a.rows_per_img, q0 = m0 - img * a.rows_per_img;
+            for (int it = 0; it < a.n_kb; ++it, ++g) {
+                const int s = g % SC_NSTG;
+                if (g >= SC_NSTG) mbar_wait(&empty[s], ((g / SC_NSTG) & 1) ^ 1);
+                const int tap = it / a.cin_blocks, cb = it - tap * a.cin_blocks;
+                const int ac0 = cb * SG_KC, ac1 = q0 + a.shift[tap], ac2 = img * a.planes_per_img + a.plane[tap];
+                const int wr = tap * a.w_tap_rows;
+                uint8_t* st = smem + s * SC_STAGE;
+                mbar_arrive_expect_tx_warp(&full[s], SC_STAGE);
+                tma_load_3d_warp(st, &tmap_ah, &full[s], ac0, ac1, ac2, kEvictNormal);
+                tma_load_3d_warp(st + SC_APLANE, &tmap_al, &full[s], ac0, ac1, ac2, kEvictNormal);
+                const int wrow = wr + (int)crank * (SC_TN / CL);
+                tma_load_2d_mc_warp(st + 2 * SC_APLANE + crank * WSLICE, &tmap_ws, &full[s], ac0, wrow, kMask, kEvictLast);
+                tma_load_2d_mc_warp(st + 2 * SC_APLANE + SC_WPLANE + crank * WSLICE, &tmap_ws, &full[s], ac0, wrow + a.w_lo, kMask,
+                                    kEvictLast);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: D = Al*Wh + Ah*Wl + Ah*Wh =================
+        constexpr uint32_t idesc = make_idesc_bf16(128, SC_TN, 0, 0);
+        int g = 0, li = 0;
+        for (int rd = 0; rd < rounds; ++rd, ++li) {
+            const int buf = li & 1;
+            mbar_wait(&accempty[buf], ((li >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator (passes at first use)
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)buf * SC_TN;
+            for (int it = 0; it < a.n_kb; ++it, ++g) {
+                const int s = g % SC_NSTG;
+                mbar_wait(&full[s], (g / SC_NSTG) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * SC_STAGE);
+                const uint64_t dah = make_smem_desc_sw128(st, 16, 1024), dal = make_smem_desc_sw128(st + SC_APLANE, 16, 1024);
+                const uint64_t dwh = make_smem_desc_sw128(st + 2 * SC_APLANE, 16, 1024);
+                const uint64_t dwl = make_smem_desc_sw128(st + 2 * SC_APLANE + SC_WPLANE, 16, 1024);
+#pragma unroll
+                for (int k16 = 0; k16 < SG_KC / 16; ++k16) {
+                    const uint64_t o = (uint64_t)(k16 * 2);
+                    umma_bf16_ss_warp(d, dal + o, dwh + o, idesc, (it | k16) != 0);
+                    umma_bf16_ss_warp(d, dah + o, dwl + o, idesc, 1);
+                    umma_bf16_ss_warp(d, dah + o, dwh + o, idesc, 1);
+                }
+                umma_commit_mc_warp(&empty[s], kMask);
+            }
+            umma_commit_warp(&accfull[buf]);
+        }
+    } else {
+        // ================= epilogue: thread = output row (TMEM lane) =================
+        const int q = warp & 3, r = q * 32 + lane, pitch = a.grid_w + 2;
+        int li = 0;
+        for (int rd = 0; rd < rounds; ++rd, ++li) {
+            const int tile = (rd * n_clusters + cid) * CL + (int)crank;
+            const bool live = tile < n_mtiles;
+            const int buf = li & 1, m0 = tile * 128;
+            const int img = m0 / a.rows_per_img, qrow = m0 - img * a.rows_per_img + r;
+            const int y1 = qrow / pitch, x1 = qrow - y1 * pitch;
+            const bool valid = live && y1 >= 1 && y1 <= a.grid_h && x1 >= 1 && x1 <= a.grid_w;
+            float* dst = a.raw + ((size_t)m0 + r) * 256;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * SC_TN;
+            mbar_wait(&accfull[buf], (li >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < SC_TN / 32; ++ch) {
+                float y[32];
+                sg_ld32(trow + ch * 32, y);
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + ch * 32 + c) = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+                }
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    float s = 0.f, ss = 0.f;
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) s += y[gi * 8 + c], ss += y[gi * 8 + c] * y[gi * 8 + c];
+                    }
+                    s = sg_warp_sum(s), ss = sg_warp_sum(ss);
+                    if (lane == 0) s_stat[q * 32 + ch * 4 + gi] = s, s_stat[128 + q * 32 + ch * 4 + gi] = ss;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&accempty[buf]);          // all 128 epilogue threads: the accumulator may be overwritten
+            sg_named_bar();
+            if (r < 32 && live) {
+                const float s = (s_stat[r] + s_stat[32 + r]) + (s_stat[64 + r] + s_stat[96 + r]);
+                const float ss = (s_stat[128 + r] + s_stat[160 + r]) + (s_stat[192 + r] + s_stat[224 + r]);
+                a.stats[(size_t)tile * 32 + r] = make_float2(s, ss);
+            }
+            sg_named_bar();                       // s_stat is free again
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    // no CTA leaves while a peer may still multicast into its shared memory or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 
 }  // namespace pf

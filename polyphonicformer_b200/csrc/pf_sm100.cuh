@@ -117,6 +117,21 @@ __device__ __forceinline__ void tma_load_2d_warp(void* smem_dst, const CUtensorM
         : "memory");
 }
 
+// multicast: the box lands at the same shared-memory offset of every CTA of the cluster whose bit is set in `mask`, and
+// completes `bytes` on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc_warp(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                    uint16_t mask, uint64_t hint) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;\n\t}\n"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1),
+          "l"(hint)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d_warp(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                                  uint64_t hint) {
     asm volatile(
@@ -225,6 +240,17 @@ __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
         "{\n\t.reg .pred e;\n\t"
         "elect.sync _|e, 0xffffffff;\n\t"
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
+// ... on the mbarrier at the same offset in every CTA of the cluster whose bit is set in `mask`
+__device__ __forceinline__ void umma_commit_mc_warp(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
         : "memory");
 }
 
