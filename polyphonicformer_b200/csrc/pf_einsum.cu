@@ -53,6 +53,13 @@ struct EinsumParams {
     int fmod;            // feature map of unit u = u % fmod (pf_kernel_head: the two 128-row halves of a conv share a map)
     int out_blocked;     // 0, or the number of 32-pixel blocks per unit: logits leave as [unit][block][128 rows][32 px]
     float2* stats;       // STATS: [units][ctas_per_unit][128] per-row (sum, sum of squares) over the CTA's pixels
+    // apply (pf_fpn_pred's second pass; TMA_OUT = false, logits = bits = null): row n of unit u = half * 3B + v is channel
+    // half * 128 + n of map-image v; y = ReLU(acc * scale + shift) leaves as bf16 [3B][256][HWp] (+ optional fp32
+    // [3B][256][HW]): GroupNorm + ReLU inside the convolution's epilogue, no fp32 intermediate in memory
+    const float2* apply_affine;   // [3B][256] (scale, shift), or null
+    uint16_t* apply_out;
+    float* apply_out32;
+    int apply_units, HWp;         // 3B; row pitch of apply_out
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
@@ -197,6 +204,8 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
         const bool vec_ok = (p.HW & 3) == 0;
         uint32_t* brow = (p.bits && unit < p.B) ? p.bits + (size_t)unit * p.words * 128 + n : nullptr;
         float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
+        const int half = unit / p.apply_units, v3 = unit - half * p.apply_units, ch = half * 128 + n;   // apply mode only
+        const float2 af = p.apply_affine ? __ldg(p.apply_affine + (size_t)v3 * 256 + ch) : make_float2(1.f, 0.f);
         for (int i = 0; i < ntiles; ++i) {
             const int a = i % NACC;
             mbar_wait(&tfull[a], (i / NACC) & 1);
@@ -242,6 +251,35 @@ einsum_kernel(const __grid_constant__ CUtensorMap tmap_feats, const __grid_const
                         if (p.out_blocked) tma_store_3d(&tmap_out, tile, 0, 0, gunit * p.out_blocked + (hwb >> 5), kEvictNormal);
                         else tma_store_3d(&tmap_out, tile, hwb, 0, gunit, kEvictLast);
                         tma_store_commit();
+                    }
+                } else if (p.apply_affine) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        float a0 = fmaxf(fmaf(__uint_as_float(v[2 * c]), af.x, af.y), 0.f);
+                        float a1 = fmaxf(fmaf(__uint_as_float(v[2 * c + 1]), af.x, af.y), 0.f);
+                        if (2 * c >= valid) a0 = 0.f;          // pad columns [HW, HWp) are written as zero
+                        if (2 * c + 1 >= valid) a1 = 0.f;
+                        v[2 * c] = __float_as_uint(a0), v[2 * c + 1] = __float_as_uint(a1);
+                        pk[c] = pack_bf16x2(a0, a1);
+                    }
+                    uint16_t* dst = p.apply_out + ((size_t)v3 * 256 + ch) * p.HWp + hwb;
+                    const int validp = p.HWp - hwb;            // > 0, a multiple of 8
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (8 * c < validp) reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    if (p.apply_out32) {
+                        float* d32 = p.apply_out32 + ((size_t)v3 * 256 + ch) * p.HW + hwb;
+                        if (vec_ok && valid >= 32) {
+#pragma unroll
+                            for (int c = 0; c < 32; c += 4)
+                                __stcs(reinterpret_cast<float4*>(d32 + c), make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                                                       __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (c < valid) d32[c] = __uint_as_float(v[c]);
+                        }
                     }
                 } else if (orow && row_ok) {
                     float* dst = orow + hwb;
@@ -335,6 +373,7 @@ int pf::mask_einsum_window(const uint16_t* feats, const uint16_t* kern, const fl
     p.N = N, p.HW = HW, p.words = (HW + 31) / 32, p.B = B;
     p.Btot = Btot, p.b0 = b0, p.early_feats = early_feats, p.unit0 = branch0 * B;
     p.kdiv = 1, p.fmod = 0x7fffffff, p.stats = nullptr, p.out_blocked = 0;
+    p.apply_affine = nullptr, p.apply_out = nullptr, p.apply_out32 = nullptr, p.apply_units = 1, p.HWp = HWp;
     // fp32 logits through TMA stores when the row pitch allows it (HW * 4 bytes must be a 16-byte multiple)
     const bool tma_out = logits && (HW % 4) == 0;
     const int tile = 128;   // must match einsum_kernel::TILE
@@ -376,6 +415,7 @@ int pf::conv1x1_maps(const uint16_t* maps, int n_inputs, const uint16_t* conv_sp
     p.N = 128, p.HW = HW, p.words = (HW + 31) / 32, p.B = n_units;
     p.Btot = n_units, p.b0 = 0, p.early_feats = 0, p.unit0 = 0;
     p.kdiv = B, p.fmod = n_inputs * B, p.stats = stats;   // n_inputs = 1: the three convolutions read the same map
+    p.apply_affine = nullptr, p.apply_out = nullptr, p.apply_out32 = nullptr, p.apply_units = 3 * B, p.HWp = HWp;
     // blocked output: 16 KB [128 rows][32 px] blocks, written whole by the TMA stores (no row-pitch constraint) and
     // read back by head_apply_kernel with a compile-time channel stride
     const int nblk = (HW + 31) / 32;
@@ -391,4 +431,37 @@ int pf::conv1x1_maps(const uint16_t* maps, int n_inputs, const uint16_t* conv_sp
     if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
     return launch_pdl("einsum_kernel(conv1x1)", kern_fn, dim3(n_units * cpu), dim3(E_THREADS), E_SMEM,
                       static_cast<cudaStream_t>(stream), tmap, tmap_o, p);
+}
+
+// The same three convolutions WITHOUT the fp32 intermediate (pf_fpn_pred): pass 1 (affine == null) only accumulates the
+// GroupNorm statistics; pass 2 recomputes the convolution and applies (scale, shift) + ReLU in its epilogue, writing the
+// bf16 maps [3][B][256][HWp] (+ optional fp32 [3][B][256][HW]) directly.  The input map is read twice (2 x 67 MB at B = 4)
+// instead of writing and re-reading 2 x 403 MB of fp32.
+int pf::conv1x1_fused(const uint16_t* maps, int n_inputs, const uint16_t* conv_split, float2* stats, const float2* affine,
+                      uint16_t* out, float* out32, int B, int HW, int HWp, void* stream) {
+    using namespace pf;
+    const int n_units = 6 * B;
+    CUtensorMap tmap;
+    if (int e = make_tmap_bf16_2d(&tmap, maps, (uint64_t)n_inputs * B * E_C, (uint64_t)HW, (uint64_t)HWp, E_C, E_BHW)) return e;
+    EinsumParams p;
+    p.kern = conv_split, p.kbias = nullptr, p.logits = nullptr, p.bits = nullptr;
+    p.N = 128, p.HW = HW, p.words = (HW + 31) / 32, p.B = n_units;
+    p.Btot = n_units, p.b0 = 0, p.early_feats = 0, p.unit0 = 0;
+    p.kdiv = B, p.fmod = n_inputs * B, p.stats = stats, p.out_blocked = 0;
+    p.apply_affine = affine, p.apply_out = out, p.apply_out32 = out32, p.apply_units = 3 * B, p.HWp = HWp;
+    p.tiles_per_unit = (HW + 127) / 128;
+    p.ctas_per_unit = conv1x1_ctas_per_unit(B, HW);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!affine) {
+        auto kern_fn = einsum_kernel<false, true>;
+        cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
+        if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
+        return launch_pdl("einsum_kernel(conv1x1 statistics)", kern_fn, dim3(n_units * p.ctas_per_unit), dim3(E_THREADS), E_SMEM, st,
+                          tmap, tmap, p);
+    }
+    auto kern_fn = einsum_kernel<false, false>;
+    cudaError_t ea = cudaFuncSetAttribute(kern_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM);
+    if (ea != cudaSuccess) return set_error(PF_ERR_CUDA, "einsum smem attribute: %s", cudaGetErrorString(ea));
+    return launch_pdl("einsum_kernel(conv1x1 + GN + ReLU)", kern_fn, dim3(n_units * p.ctas_per_unit), dim3(E_THREADS), E_SMEM, st, tmap,
+                      tmap, p);
 }

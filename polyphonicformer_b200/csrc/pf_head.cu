@@ -433,13 +433,10 @@ extern "C" int pf_fpn_pred(const uint16_t* conv_split, const float* gn_gamma, co
     float2* stats = affine + (size_t)3 * B * 256;
     const int cpu = conv1x1_ctas_per_unit(B, HW);
     PF_REQUIRE(cpu <= 148, PF_ERR_WORKSPACE, "pf_fpn_pred: %d CTAs per unit exceed the statistics scratch", cpu);
-    if (int e = conv1x1_maps(fused, 1, conv_split, Y, stats, B, HW, HWp, stream)) return e;
+    (void)Y;   // two passes over the bf16 input instead of an fp32 intermediate: statistics, then conv + GN + ReLU -> maps
+    if (int e = conv1x1_fused(fused, 1, conv_split, stats, nullptr, nullptr, nullptr, B, HW, HWp, stream)) return e;
     if (int e = launch_pdl("gn_finalize_kernel", gn_finalize_kernel, dim3(32, 3 * B), dim3(32), 0, st, (const float2*)stats,
                            gn_gamma, gn_beta, affine, B, HW, cpu, gn_eps))
         return e;
-    long long nblocks = (long long)6 * B * nblk;
-    int grid = (int)((nblocks + 7) / 8);
-    if (grid > 8 * num_sms()) grid = 8 * num_sms();
-    return launch_pdl("gn_apply_kernel", gn_apply_kernel, dim3(grid), dim3(256), 0, st, (const float*)Y, (const float2*)affine,
-                      maps, maps32, B, HW, HWp, nblk);
+    return conv1x1_fused(fused, 1, conv_split, nullptr, affine, maps, maps32, B, HW, HWp, stream);
 }

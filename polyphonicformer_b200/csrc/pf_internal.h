@@ -52,6 +52,11 @@ int conv1x1_ctas_per_unit(int B, int HW);
 int conv1x1_maps(const uint16_t* maps, int n_inputs, const uint16_t* conv_split, float* Y, float2* stats, int B, int HW,
                  int HWp, void* stream);
 
+// the same convolutions without the fp32 intermediate: affine == null -> statistics only; else conv + (scale, shift) + ReLU ->
+// bf16 out [3][B][256][HWp] (+ optional fp32 out32 [3][B][256][HW])
+int conv1x1_fused(const uint16_t* maps, int n_inputs, const uint16_t* conv_split, float2* stats, const float2* affine,
+                  uint16_t* out, float* out32, int B, int HW, int HWp, void* stream);
+
 // Launch with programmatic stream serialization (PDL): the kernel may begin before its predecessor in the stream has
 // finished; it must execute griddepcontrol.wait (pdl_wait) before touching anything the predecessor wrote.
 template <typename... KArgs, typename... Args>

@@ -129,3 +129,45 @@ def test_tracker_random_sequences_match_restatement(dev, seed, backdrop_frames):
         assert got_ids.tolist() == want_ids.tolist(), (frame, got_ids.tolist(), want_ids.tolist())
         assert torch.equal(got_b.cpu(), want_b) and torch.equal(got_l.cpu(), want_l)
     assert ref.next_id > 10
+
+
+def test_embed_head_at_the_maximum_roi_count_and_on_degenerate_boxes(dev, engine):
+    """100 RoIs (max_per_img of the shipped configs: 50 tiles of two RoIs) incl. zero-area boxes at the origin (what an
+    empty mask produces), boxes outside the image and boxes of every pyramid level, against the restatement."""
+    gen = torch.Generator().manual_seed(9)
+    H, W = 256, 512
+    feats = [torch.randn(1, 256, H // s, W // s, generator=gen) for s in (4, 8, 16, 32)]
+    K = 100
+    c = torch.rand(K, 2, generator=gen) * torch.tensor([W * 1.1, H * 1.1])
+    half = torch.exp(torch.rand(K, 1, generator=gen) * 6.4) * 0.7 * (0.8 + 0.4 * torch.rand(K, 2, generator=gen))   # 0.6 .. 500 px
+    boxes = torch.cat([c - half, c + half], 1).clamp(min=0)
+    boxes[7] = 0.0                                                                   # an empty mask's RoI
+    boxes[8] = torch.tensor([W + 50.0, H + 50.0, W + 90.0, H + 70.0])               # entirely outside
+    rois = torch.cat([torch.zeros(K, 1), boxes], 1)
+    emb, rf = engine.embed([f.to(dev) for f in feats], rois.to(dev), want_roi_feats=True)
+    want_rf = tracking_ref.roi_features(feats, boxes)
+    l2, mx = rel_err(rf.cpu(), want_rf)
+    assert l2 < 1e-5 and mx < 1e-4, (l2, mx)
+    with torch.no_grad():
+        want = tracking_ref.embed_head(synth.synth_track_head_state(0), want_rf)
+    l2, mx = rel_err(emb.cpu(), want)
+    print('100 RoIs: embeddings rel err %.2e (l2) %.2e (max)' % (l2, mx))
+    assert l2 < 1e-3 and mx < 1e-3, (l2, mx)
+    lv = torch.floor(torch.log2(torch.sqrt((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])) / 56 + 1e-6)).clamp(0, 3)
+    assert set(lv.long().tolist()) == {0, 1, 2, 3}
+
+
+def test_tracker_memo_overflow_is_reported_not_silent(dev):
+    """More live tracklets than PF_TRACK_MAX_TRACKS (512): the kernel drops the surplus and raises the flag; the host wrapper
+    turns it into an error instead of returning wrong ids."""
+    from polyphonicformer_b200 import _cabi
+    from polyphonicformer_b200.track import DeviceTracker
+    trk = DeviceTracker(dev, **dict(TRACKER_CFG, memo_tracklet_frames=100))
+    gen = torch.Generator().manual_seed(2)
+    with pytest.raises(_cabi.PFError):
+        for frame in range(1, 8):                       # 7 x 100 new, mutually distinct tracks
+            boxes = torch.cat([torch.arange(100.0).view(-1, 1) * 30 + torch.tensor([[0.0, 0.0, 20.0, 20.0]]),
+                               0.9 - torch.arange(100.0).view(-1, 1) * 1e-3], 1)
+            emb = torch.randn(100, 256, generator=gen) * 3
+            _, _, ids = trk.match(boxes.to(dev), torch.zeros(100, dtype=torch.long, device=dev) + frame, emb.to(dev), frame)
+            assert ids.min() >= 0 and len(set(ids.tolist())) == 100
