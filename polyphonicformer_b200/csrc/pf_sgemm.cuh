@@ -278,12 +278,12 @@ sgemm_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_constant_
 // The same shifted-row convolution for image-sized problems (SemanticFPN): PERSISTENT CTAs over [128 rows][256 cols] tiles
 // (all output channels of 128 padded positions), two accumulators in tensor memory (2 x 256 columns) so that the epilogue
 // of tile i -- 128 KB of raw fp32 rows + the GroupNorm partial statistics -- runs under the main loop of tile i + 1.
-// What bounds it (measured: 0.34 ms per 128x256-map convolution at B = 4, ~2240 clocks per k-block against 1536 of MMA
-// issue): SHARED-MEMORY bandwidth.  The 3-MMA split reads every operand tile up to twice (Ah and Wh), 36 KB per K = 16 step,
-// and TMA writes 96 KB per k-block: ~240 KB through a 128 B/clk port per 1536 clocks of tensor work.  A [128][128] tile is
-// worse (same operand bytes for half the math), and cutting the L2 -> SM traffic does not help: the clustered variant below
-// (weight tiles TMA-multicast across 2 or 4 CTAs) runs at exactly the same speed.  The next step would be cta_group::2
-// MMAs (each SM of a pair supplies half of the B operand), not more L2 tricks.
+// What bounds it (ncu, profiles/r2_ncu_full_neck.raw.csv: 0.33 ms per 128x256-map convolution at B = 4): the TENSOR PIPE,
+// 86 % active -- 477 GFLOP of issued MMAs (1052 tiles x 36 k-blocks x 12 MMAs of M128 N256 K16) in 334 us = 1.43 PFLOP/s,
+// the measured sustained bf16 rate of the part (MEASURED_PEAKS.json: 1.40).  The algorithmic rate is a third of that: the
+// 3-MMA split is the price of fp32-level accuracy from bf16 tensor cores.  So cutting operand traffic cannot help -- the
+// clustered variant below (weight tiles TMA-multicast across 2 or 4 CTAs) runs at exactly the same speed -- only fewer MMAs
+// per product would, and those give up the 5e-6 parity of the pyramid.
 constexpr int SC_TN = 256, SC_NSTG = 2;
 constexpr int SC_APLANE = 128 * SG_KC * 2, SC_WPLANE = SC_TN * SG_KC * 2;
 constexpr int SC_STAGE = 2 * SC_APLANE + 2 * SC_WPLANE;          // 96 KB
@@ -424,7 +424,7 @@ sgemm_conv256_kernel(const __grid_constant__ CUtensorMap tmap_ah, const __grid_c
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// The clustered variant (opt-in: PF_CONV_CLUSTER=2|4; parity-tested, NOT faster, see above): CL consecutive tiles form a
+// The clustered variant (opt-in: PF_CONV_CLUSTER=2|4; parity-tested, NOT faster: the kernel is tensor-bound, see above): CL consecutive tiles form a
 // thread-block cluster; the weight tile of a k-block is the same for
 // every tile, so each CTA fetches 1 / CL of it and TMA-multicasts the slice into all CL shared memories (L2 -> SM operand
 // traffic per tile and k-block: 32 KB of activations + 64 / CL KB of weights instead of 96 KB).  A ring stage is refilled
