@@ -704,6 +704,9 @@ def kernel_head_timing(args, B, dev, peak_gbs, cpu=True):
     flops = B * 2 * 9 * C * C * (4 * HW + 2 * HW // 4 + HW // 16) + B * 3 * 2 * C * C * HW
     res['semantic_fpn'] = dict(ms_per_call=ms_neck, frames_per_s=B / ms_neck * 1e3, batch=B, launches=pyr.last_launches + pred.last_launches,
                                algorithmic_GFLOP=flops / 1e9, achieved_TFLOPs=flops / ms_neck / 1e9,
+                               issued_TFLOPs_3mma_split=3 * flops / ms_neck / 1e9,
+                               conv_kernel_bound='tensor pipe: ncu 86 % active, 1.43 PFLOP/s of issued MMAs in the 128x256 convolutions '
+                                                 '(profiles/r2_ncu_full_neck.raw.csv) against %.0f TFLOP/s measured sustained bf16' % peaks()['tf'],
                                what='pf_semantic_fpn (7 x [3x3 conv + GN32 + ReLU], x2 steps, level sum) + pf_fpn_pred on the four '
                                     'FPN levels of %d frames (%dx%d .. %dx%d); split-bf16 MMAs issue 3x the algorithmic FLOP'
                                     % (B, 2 * H, 2 * W, H // 4, W // 4))
