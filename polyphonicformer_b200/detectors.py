@@ -12,7 +12,6 @@ backbone and the FPN neck stay the reference's PyTorch modules (north-star) and 
 reference checkout is importable, or passed in as already-built ``nn.Module``s; the heads are this package's.  There is
 no PyTorch fallback for any head: they raise without an sm_100 device.
 """
-import numpy as np
 import torch
 import torch.nn as nn
 
