@@ -176,3 +176,27 @@ def test_pinned_result_pool_lifetime(monkeypatch):
     assert pool.outstanding == 1 and len(pool.free[1 << 22]) == 1
     c = pool.lend(4_000_000)
     assert c is not None and pool.outstanding == 2 and not pool.free[1 << 22]
+
+
+def test_track_and_fpn_struct_layouts_match_headers():
+    """ctypes mirrors of the structs in include/pf_track.h and include/pf_fpn.h: same field names, order and sizes."""
+    from polyphonicformer_b200 import _cabi
+
+    def fields(header, name):
+        hdr = open(os.path.join(ROOT, 'include', header)).read()
+        body = hdr[hdr.index('typedef struct %s {' % name):hdr.index('} %s;' % name)]
+        body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+        out = []
+        for typ, decl in re.findall(r'^\s*(const uint16_t\*|const float\*|float|int)\s+([^;]+);', body, flags=re.M):
+            out += [(n.strip().lstrip('*'), typ) for n in decl.split(',')]
+        return out
+
+    ctype = {'const uint16_t*': ctypes.c_void_p, 'const float*': ctypes.c_void_p, 'float': ctypes.c_float, 'int': ctypes.c_int}
+    for header, name, cls in (('pf_track.h', 'pf_track_weights', _cabi.TrackWeights),
+                              ('pf_track.h', 'pf_tracker_config', _cabi.TrackerConfig),
+                              ('pf_fpn.h', 'pf_fpn_weights', _cabi.FpnWeights)):
+        want = fields(header, name)
+        assert want, name
+        assert [(n, t) for n, t in cls._fields_] == [(n, ctype[t]) for n, t in want], name
+    assert ctypes.sizeof(_cabi.TrackWeights) == 7 * 8 + 8 and ctypes.sizeof(_cabi.TrackerConfig) == 40
+    assert ctypes.sizeof(_cabi.FpnWeights) == 3 * 8 + 8
