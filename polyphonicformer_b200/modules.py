@@ -698,6 +698,9 @@ class KernelHead(nn.Module):
             return maps, hw
         # a pyramid pf_semantic_fpn does not cover (other depths / strides / coordinate channels, ragged sizes): its 3x3
         # convs stay the module's own PyTorch code, only conv_pred / aux_convs run on the kernels
+        if isinstance(fpn, SemanticFPNWrapper):      # this package's neck holds parameters only: there is no PyTorch path
+            _unsupported('SemanticFPNWrapper on FPN levels %s (pf_semantic_fpn needs the four levels of a stride-8 map whose '
+                         'sides are multiples of 4, which Pad(size_divisor=32) guarantees)' % [tuple(t.shape) for t in lv])
         levels = []
         for i in range(fpn.start_level, fpn.end_level + 1):
             inp = img[i]
