@@ -25,6 +25,11 @@ ncu --set full --clock-control none -k regex:"head_apply|gn_finalize|einsum_kern
 ncu -i $OUT/${TAG}_ncu_full_kernel_head.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_full_kernel_head.raw.csv 2>/dev/null
 rm -f $OUT/${TAG}_ncu_full_kernel_head.ncu-rep
 cap stream "pool_kernel|einsum_kernel|upsample2x|binarise" 9 9
+# the same streaming kernels inside the step with the caches left alone between replays (L2 warm: x_feats evict-last)
+ncu --set full --clock-control none --cache-control none -k regex:"pool_kernel|einsum_kernel|upsample2x|binarise" -s 9 -c 9 \
+    -o $OUT/${TAG}_ncu_full_stream_l2warm python scripts/run_stage.py 4 128 256 3 > $OUT/${TAG}_ncu_full_stream_l2warm.log 2>&1
+ncu -i $OUT/${TAG}_ncu_full_stream_l2warm.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_full_stream_l2warm.raw.csv 2>/dev/null
+rm -f $OUT/${TAG}_ncu_full_stream_l2warm.ncu-rep
 cap tcgemm "tcgemm" 27 9
 cap helpers "prep_kernel|sumln_kernel|attention_kernel" 9 3
 # round 2: the neck (pf_semantic_fpn + pf_fpn_pred), the tracking path and the batched panoptic merge
